@@ -1,0 +1,122 @@
+/* pxmcmc_b200 -- C ABI of the B200 (sm_100a) implementation of pxmcmc's
+ * per-iteration proximal-Langevin hot path.
+ *
+ * The reference (auggiemarignier/pxmcmc) is pure Python; the arithmetic of its
+ * hot path lives in C libraries reached through Cython (pyssht, pys2let) and in
+ * numpy/scipy.  Each entry point below names the reference call it replaces
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - every d_* pointer is a DEVICE pointer; complex arrays are interleaved
+ *    (re, im) float64 (numpy complex128); batched arrays are [nchains][n]
+ *    row-major; the caller owns all buffers.
+ *  - `stream` is a cudaStream_t passed as void* (0 = default stream).
+ *  - return value 0 = success; otherwise pxm_last_error() describes the
+ *    failure (thread-local).  There is NO CPU fallback: pxm_init fails when no
+ *    sm_100-class device is visible.
+ *  - a plan is immutable after creation and may be used from one stream at a
+ *    time (it owns the workspace of its operators).
+ */
+#ifndef PXMCMC_B200_H
+#define PXMCMC_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pxm_sht_plan pxm_sht_plan;
+typedef struct pxm_wav_plan pxm_wav_plan;
+
+const char* pxm_last_error(void);
+int pxm_init(int device);
+
+/* ---- spin spherical harmonic transforms on MW sampling --------------------
+ * pyssht.inverse / forward / inverse_adjoint / forward_adjoint (Method="MW",
+ * Reality=False): pxmcmc/measurements.py:223,225,237,239.
+ * f: [nbatch][L][2L-1] complex, flm: [nbatch][L*L] complex (index l*l+l+m).
+ * d_gl (may be NULL): real per-degree multiplier g[l], l<L, applied to the
+ * harmonic side of the call (fuses WeakLensingHarmonic.harmonic_mapping,
+ * pxmcmc/measurements.py:162-171). */
+int pxm_sht_plan_create(int L, int spin, int max_batch, pxm_sht_plan** out);
+int pxm_sht_plan_destroy(pxm_sht_plan* plan);
+size_t pxm_sht_plan_table_bytes(const pxm_sht_plan* plan);
+int pxm_sht_inverse(pxm_sht_plan* plan, const void* d_flm, void* d_f, int nbatch, const double* d_gl, void* stream);
+int pxm_sht_forward(pxm_sht_plan* plan, const void* d_f, void* d_flm, int nbatch, const double* d_gl, void* stream);
+int pxm_sht_inverse_adjoint(pxm_sht_plan* plan, const void* d_f, void* d_flm, int nbatch, const double* d_gl,
+                            void* stream);
+int pxm_sht_forward_adjoint(pxm_sht_plan* plan, const void* d_flm, void* d_f, int nbatch, const double* d_gl,
+                            void* stream);
+
+/* ---- scale-discretised wavelet transform (N=1, spin 0, multiresolution) ----
+ * pys2let.synthesis_wav2px / synthesis_adjoint_px2wav / analysis_px2wav /
+ * analysis_adjoint_wav2px as wrapped by SphericalWaveletTransform.inverse /
+ * inverse_adjoint / forward / forward_adjoint: pxmcmc/transforms.py:95-154.
+ * coef: [nbatch][ncoefs] complex = [scaling map, wavelet maps j=J_min..J]
+ * (utils.flatten_mlm, pxmcmc/utils.py:11-22); pix: [nbatch][L(2L-1)] complex. */
+int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan** out);
+int pxm_wav_plan_destroy(pxm_wav_plan* plan);
+int pxm_wav_plan_info(const pxm_wav_plan* plan, int* nscales_total, long long* ncoefs, long long* nscal, int* J_max,
+                      long long* table_bytes);
+int pxm_wav_plan_bandlimits(const pxm_wav_plan* plan, int* out, int cap);
+int pxm_wav_synthesis(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int nbatch, void* stream);
+int pxm_wav_synthesis_adjoint(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
+int pxm_wav_analysis(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
+int pxm_wav_analysis_adjoint(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int nbatch, void* stream);
+/* host-only: kappa0[L], kappa[(J-J_min+1)][L] of pys2let.wavelet_tiling
+ * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
+int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);
+
+/* ---- fused elementwise passes ---------------------------------------------
+ * pxm_soft: utils.soft (pxmcmc/utils.py:55-67); T vector (d_T, length n) or scalar. */
+int pxm_soft(int is_complex, const void* d_x, const double* d_T, double T_scalar, void* d_out, long long n,
+             long long nchains, void* stream);
+/* pxm_myula_update: MYULA.chain_step (pxmcmc/mcmc.py:185-201) fused with the
+ * synthesis prox (pxmcmc/prior.py:49-50) when d_prox == NULL.
+ * noise_mode 0: none; 1: injected d_w_re (+ d_w_im); 2/3: Philox4x32-10 real/complex. */
+int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                     const double* d_w_re, const double* d_w_im, void* d_Xout, void* d_prox_out, long long n,
+                     long long nchains, double delta, double lmda, int noise_mode, unsigned long long seed,
+                     unsigned long long step, unsigned int stream0, void* stream);
+/* pxm_resid_invcov: invcov @ (preds - data) of ForwardOperator._gradg_analysis
+ * (pxmcmc/forward.py:66-69) for a diagonal, possibly complex, inverse covariance. */
+int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,
+                     long long nchains, void* stream);
+/* pxm_reduce: per-chain deterministic reductions -> d_out[nchains] complex.
+ *  kind 0: sum |w x|        (L1.prior, pxmcmc/prior.py:28-35,83-84)   a=x, w=weights or NULL
+ *  kind 1: vdot(d, ic*d), d=data-preds (PxMCMC.logpi, pxmcmc/mcmc.py:78-79)   a=preds b=data c=invcov
+ *  kind 2: sum (X2-X1-(delta/2) glp)^2 (PxMALA.calc_logtransition, pxmcmc/mcmc.py:285-289) a=X1 b=X2 c=prox d=gradg
+ * d_partial: scratch of nchains*pxm_reduce_scratch_elems() complex. */
+int pxm_reduce_scratch_elems(void);
+int pxm_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w, double delta,
+               double lmda, long long n, long long nchains, void* d_partial, void* d_out, void* stream);
+/* pxm_lincomb: out = c0 + sum_k coef_k x_k (+ cz*z, z real): SKROCK stages
+ * (pxmcmc/mcmc.py:349-368) and the analysis prox assembly (pxmcmc/prior.py:52-53). */
+int pxm_lincomb(int nx, const void* const* d_xs, const double* coefs, const double* d_z, double cz, double c0,
+                void* d_out, long long total, void* stream);
+/* pxm_gradlogpi: PxMCMC._gradlogpi (pxmcmc/mcmc.py:84-89): -((X - P)/lmda) - gradg with
+ * P = soft(X, T) when d_prox == NULL. */
+int pxm_gradlogpi(const void* d_X, const void* d_prox, const double* d_T, double T_scalar, const void* d_gradg,
+                  double lmda, void* d_out, long long n, long long nchains, void* stream);
+/* masked gather / zero-filled scatter with optional per-datum weight:
+ * WeakLensing.mask_forward/mask_adjoint/cov_weight (pxmcmc/measurements.py:242-304). */
+int pxm_masked_gather(const void* d_full, const int* d_idx, const double* d_w, void* d_sel, long long nsel,
+                      long long nfull, long long nchains, void* stream);
+int pxm_masked_scatter(const void* d_sel, const int* d_idx, const double* d_w, void* d_full, long long nsel,
+                       long long nfull, long long nchains, void* stream);
+int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* stream);
+
+/* ---- sparse path operator ---------------------------------------------------
+ * PathIntegral.forward / adjoint (pxmcmc/measurements.py:75-83): CSR with real
+ * float64 values times complex vectors; pass the CSR of A^T for the adjoint. */
+int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
+                 int nrows, long long ncols, long long nchains, void* stream);
+
+/* ---- debugging aids (tests only) ---------------------------------------------- */
+int pxm_debug_set_naive(int on); /* route Legendre contractions through the plain kernel */
+int pxm_debug_wigner_row_host(int grid_L, int ring, int m, int spin, int lmax, double* out); /* host, no GPU */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

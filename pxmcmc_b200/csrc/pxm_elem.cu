@@ -1,0 +1,541 @@
+// Fused elementwise / reduction / gather kernels of the proximal-Langevin step
+// (HBM-bound, coalesced, grid-stride).  Each replaces a chain of numpy passes in
+// the reference; file:line of what it follows is given per kernel.
+//
+// All per-chain arrays are [nchains][n] row-major; thresholds, data, inverse
+// covariance and weights are shared by all chains and indexed by i.
+#include "pxm_common.cuh"
+
+namespace {
+
+typedef double2 cplx;
+
+// ---------------------------------------------------------------------------
+// soft threshold, exactly the reference's operation order
+// (/root/reference/pxmcmc/utils.py:55-67, _sign :84-88):
+//   sign(x) * (|x| - T), 0 where |x| <= T (inclusive), sign(z) = z/|z| (0 at 0)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ cplx soft_c(cplx z, double T) {
+  const double a = hypot(z.x, z.y);
+  if (a <= T) return make_double2(0.0, 0.0);
+  const double r = a - T;
+  return make_double2((z.x / a) * r, (z.y / a) * r);
+}
+__device__ __forceinline__ double soft_r(double x, double T) {
+  const double a = fabs(x);
+  if (a <= T) return 0.0;
+  return (x / a) * (a - T);
+}
+
+__global__ void k_soft_c(const cplx* __restrict__ x, const double* __restrict__ Tv, double Ts, cplx* __restrict__ out,
+                         size_t n, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const double T = Tv ? Tv[i % n] : Ts;
+    out[i] = soft_c(x[i], T);
+  }
+}
+__global__ void k_soft_r(const double* __restrict__ x, const double* __restrict__ Tv, double Ts,
+                         double* __restrict__ out, size_t n, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const double T = Tv ? Tv[i % n] : Ts;
+    out[i] = soft_r(x[i], T);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator + Box-Muller (throughput mode noise)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// two independent N(0,1) for (seed, stream, step, pair index)
+__device__ __forceinline__ void philox_normal2(unsigned long long seed, unsigned int stream, unsigned long long step,
+                                               unsigned long long pair, double* z0, double* z1) {
+  uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)step, (uint32_t)(step >> 32) ^ (stream * 0x85EBCA6Bu)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32) ^ stream);
+  const unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
+  const unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);  // (0,1)
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double r = sqrt(-2.0 * log(u1));
+  double sn, cs;
+  sincospi(2.0 * u2, &sn, &cs);
+  *z0 = r * cs;
+  *z1 = r * sn;
+}
+
+// ---------------------------------------------------------------------------
+// MYULA / PxMALA proposal (/root/reference/pxmcmc/mcmc.py:185-201), fused with
+// the synthesis-setting prox (prior.py:49-50):
+//   X' = (1 - d/l) X + (d/l) P - d g + sqrt(2 d) w
+// P = soft(X, T) computed here (prox == nullptr) or given (analysis setting).
+// Noise: w_re (and w_im if the sampler is `complex`) injected from the host RNG
+// for parity, or Philox-generated (noise_mode 2).  Optionally also writes P.
+// ---------------------------------------------------------------------------
+struct MyulaArgs {
+  const cplx* X;
+  const cplx* prox;   // may be null -> soft(X,T)
+  const cplx* gradg;
+  const double* Tv;   // may be null -> Ts
+  double Ts;
+  const double* w_re;  // noise_mode 1
+  const double* w_im;  // may be null
+  cplx* Xout;
+  cplx* prox_out;  // may be null
+  size_t n, total;
+  double a, b, delta, sq2d;
+  int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex)
+  unsigned long long seed, step;
+  unsigned int stream0;
+};
+
+__global__ void k_myula_update(MyulaArgs p) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.total; i += (size_t)gridDim.x * blockDim.x) {
+    const cplx x = p.X[i];
+    cplx px;
+    if (p.prox) {
+      px = p.prox[i];
+    } else {
+      px = soft_c(x, p.Tv ? p.Tv[i % p.n] : p.Ts);
+    }
+    if (p.prox_out) p.prox_out[i] = px;
+    const cplx g = p.gradg[i];
+    double wr = 0.0, wi = 0.0;
+    if (p.noise_mode == 1) {
+      wr = p.w_re[i];
+      if (p.w_im) wi = p.w_im[i];
+    } else if (p.noise_mode >= 2) {
+      const size_t chain = i / p.n, e = i % p.n;
+      double z0, z1;
+      if (p.noise_mode == 3) {
+        philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, e, &z0, &z1);
+        wr = z0;
+        wi = z1;
+      } else {
+        philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, e >> 1, &z0, &z1);
+        wr = (e & 1) ? z1 : z0;
+      }
+    }
+    // same association order as the reference expression
+    cplx o;
+    o.x = ((p.a * x.x + p.b * px.x) - p.delta * g.x) + p.sq2d * wr;
+    o.y = ((p.a * x.y + p.b * px.y) - p.delta * g.y) + p.sq2d * wi;
+    p.Xout[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// data-fidelity residual (/root/reference/pxmcmc/forward.py:66-69):
+//   r = invcov (.) (preds - data), invcov diagonal, possibly complex (:80-82)
+// ---------------------------------------------------------------------------
+__global__ void k_resid(const cplx* __restrict__ preds, const cplx* __restrict__ data, const cplx* __restrict__ ic,
+                        cplx* __restrict__ out, size_t n, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t e = i % n;
+    const cplx p = preds[i], d = data[e], c = ic[e];
+    const double dx = p.x - d.x, dy = p.y - d.y;
+    out[i] = make_double2(c.x * dx - c.y * dy, c.x * dy + c.y * dx);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-chain reductions (deterministic two-stage)
+//  kind 0: sum |w_i x_i|                         (prior.py:28-35, :83-84)   -> (re, 0)
+//  kind 1: sum conj(d_i) ic_i d_i, d = data-preds (mcmc.py:78-79)           -> complex
+//  kind 2: sum (X2 - X1 - (delta/2) glp)^2, glp = -(X1-P)/lmda - g (mcmc.py:285-289) -> complex
+// ---------------------------------------------------------------------------
+struct ReduceArgs {
+  int kind;
+  const cplx* a;   // kind0: x ; kind1: preds ; kind2: X1
+  const cplx* b;   // kind1: data ; kind2: X2
+  const cplx* c;   // kind1: invcov ; kind2: P (prox of X1)
+  const cplx* d;   // kind2: gradg(X1)
+  const double* w; // kind0 weights (may be null)
+  double delta, lmda;
+  size_t n;
+  cplx* partial;  // [nchains][gridDim.x]
+  cplx* out;      // [nchains]
+};
+
+__device__ __forceinline__ cplx block_sum(cplx v) {
+  __shared__ cplx sh[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+      v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+    }
+  }
+  return v;
+}
+
+__global__ void k_reduce_stage1(ReduceArgs p) {
+  const size_t chain = blockIdx.y;
+  const size_t off = chain * p.n;
+  cplx acc = make_double2(0.0, 0.0);
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < p.n; e += (size_t)gridDim.x * blockDim.x) {
+    if (p.kind == 0) {
+      cplx x = p.a[off + e];
+      if (p.w) {
+        x.x *= p.w[e];
+        x.y *= p.w[e];
+      }
+      acc.x += hypot(x.x, x.y);
+    } else if (p.kind == 1) {
+      const cplx pr = p.a[off + e], da = p.b[e], ic = p.c[e];
+      const double dx = da.x - pr.x, dy = da.y - pr.y;
+      const double tx = ic.x * dx - ic.y * dy, ty = ic.x * dy + ic.y * dx;  // ic*d
+      acc.x += dx * tx + dy * ty;                                          // conj(d)*(ic*d)
+      acc.y += dx * ty - dy * tx;
+    } else {
+      const cplx x1 = p.a[off + e], x2 = p.b[off + e], px = p.c[off + e], g = p.d[off + e];
+      const double gx = -((x1.x - px.x) / p.lmda) - g.x, gy = -((x1.y - px.y) / p.lmda) - g.y;
+      const double vx = x2.x - x1.x - (p.delta / 2) * gx, vy = x2.y - x1.y - (p.delta / 2) * gy;
+      acc.x += vx * vx - vy * vy;
+      acc.y += 2.0 * vx * vy;
+    }
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) p.partial[chain * gridDim.x + blockIdx.x] = acc;
+}
+
+__global__ void k_reduce_stage2(const cplx* __restrict__ partial, int nparts, cplx* __restrict__ out) {
+  const size_t chain = blockIdx.x;
+  cplx acc = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    const cplx v = partial[chain * nparts + i];
+    acc.x += v.x;
+    acc.y += v.y;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) out[chain] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// grad log pi (/root/reference/pxmcmc/mcmc.py:84-89), same operation order:
+//   out = -((X - P)/lmda) - gradg,  P = soft(X,T) (prox == nullptr) or given
+// ---------------------------------------------------------------------------
+__global__ void k_gradlogpi(const cplx* __restrict__ X, const cplx* __restrict__ prox, const double* __restrict__ Tv,
+                            double Ts, const cplx* __restrict__ gradg, double lmda, cplx* __restrict__ out, size_t n,
+                            size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const cplx x = X[i];
+    const cplx px = prox ? prox[i] : soft_c(x, Tv ? Tv[i % n] : Ts);
+    const cplx g = gradg[i];
+    out[i] = make_double2(-((x.x - px.x) / lmda) - g.x, -((x.y - px.y) / lmda) - g.y);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generic complex linear combination with real coefficients (SKROCK stages,
+// analysis-setting prox assembly):  out = c0 + sum_k a_k x_k  (+ cz * z, z real)
+// (/root/reference/pxmcmc/mcmc.py:349-368, prior.py:52-53)
+// ---------------------------------------------------------------------------
+struct LinArgs {
+  const cplx* x[4];
+  double a[4];
+  int nx;
+  const double* z;  // real vector added to the real part (may be null)
+  double cz;
+  double c0;  // real constant added to the real part
+  cplx* out;
+  size_t total;
+};
+__global__ void k_lincomb(LinArgs p) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.total; i += (size_t)gridDim.x * blockDim.x) {
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < p.nx) {
+        const cplx v = p.x[k][i];
+        re += p.a[k] * v.x;
+        im += p.a[k] * v.y;
+      }
+    }
+    if (p.z) re += p.cz * p.z[i];
+    re += p.c0;
+    p.out[i] = make_double2(re, im);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// masked gather / scatter with covariance weighting (weak lensing,
+// /root/reference/pxmcmc/measurements.py:242-304)
+// ---------------------------------------------------------------------------
+__global__ void k_gather_w(const cplx* __restrict__ x, const int* __restrict__ idx, const double* __restrict__ w,
+                           cplx* __restrict__ out, size_t nsel, size_t nfull, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t chain = i / nsel, e = i % nsel;
+    cplx v = x[chain * nfull + idx[e]];
+    const double s = w ? w[e] : 1.0;
+    out[i] = make_double2(v.x * s, v.y * s);
+  }
+}
+__global__ void k_scatter_w(const cplx* __restrict__ y, const int* __restrict__ idx, const double* __restrict__ w,
+                            cplx* __restrict__ out, size_t nsel, size_t nfull, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t chain = i / nsel, e = i % nsel;
+    cplx v = y[i];
+    const double s = w ? w[e] : 1.0;
+    out[chain * nfull + idx[e]] = make_double2(v.x * s, v.y * s);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pyssht harmonic layout  flm[chain][l^2+l+m]  <->  internal per-m slots
+// (k4-interleaved rows lambda = l-|m|), with an optional real multiplier g[l]
+// (harmonic-space kernels: weak-lensing k_l, measurements.py:151-171).
+// ---------------------------------------------------------------------------
+struct LmArgs {
+  cplx* flm;          // [nchains][L*L]
+  double* H;          // internal
+  const unsigned long long* slot_off;  // per slot
+  const double* gl;   // may be null
+  int L, paired, nld, nchains, to_internal;
+};
+__global__ void k_lm_convert(LmArgs p) {
+  const size_t per = (size_t)p.L * p.L;
+  const size_t total = per * p.nchains;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int chain = (int)(i / per);
+    const int ind = (int)(i % per);
+    int l = (int)sqrt((double)ind);
+    while (l * l > ind) --l;
+    while ((l + 1) * (l + 1) <= ind) ++l;
+    const int m = ind - l * l - l;
+    const int am = m < 0 ? -m : m;
+    int slot, col;
+    double sg = 1.0;
+    if (p.paired) {
+      slot = am;
+      col = chain * 4 + (m < 0 ? 2 : 0);
+      if (m < 0 && (am & 1)) sg = -1.0;
+    } else {
+      slot = m + p.L - 1;
+      col = chain * 2;
+    }
+    const size_t base = p.slot_off[slot] + pxm_il_index(l - am, col, p.nld);
+    const double gl = p.gl ? p.gl[l] : 1.0;
+    if (p.to_internal) {
+      const cplx v = p.flm[i];
+      p.H[base] = sg * gl * v.x;
+      p.H[base + 4] = sg * gl * v.y;
+    } else {
+      p.flm[i] = make_double2(sg * gl * p.H[base], sg * gl * p.H[base + 4]);
+    }
+  }
+}
+
+// real -> complex widening copy (the reference's X.astype(complex))
+__global__ void k_r2c(const double* __restrict__ x, cplx* __restrict__ out, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = make_double2(x[i], 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// CSR SpMV, warp per row, real values x complex vectors
+// (/root/reference/pxmcmc/measurements.py:75-83: path_matrix.dot / getH().dot)
+// ---------------------------------------------------------------------------
+__global__ void k_csr_spmv(const int* __restrict__ indptr, const int* __restrict__ indices,
+                           const double* __restrict__ vals, const cplx* __restrict__ x, cplx* __restrict__ y,
+                           int nrows, size_t ncols) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const size_t chain = blockIdx.y;
+  if (row >= nrows) return;
+  const cplx* xc = x + chain * ncols;
+  double re = 0.0, im = 0.0;
+  for (int j = indptr[row] + lane; j < indptr[row + 1]; j += 32) {
+    const double v = vals[j];
+    const cplx xv = xc[indices[j]];
+    re += v * xv.x;
+    im += v * xv.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    re += __shfl_down_sync(0xffffffffu, re, o);
+    im += __shfl_down_sync(0xffffffffu, im, o);
+  }
+  if (lane == 0) y[chain * (size_t)nrows + row] = make_double2(re, im);
+}
+
+inline int grid_for(size_t total, int block = 256) {
+  size_t g = (total + block - 1) / block;
+  const size_t cap = 148 * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+// ------------------------------- launchers ---------------------------------
+int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, void* out, size_t n, size_t nchains,
+                    cudaStream_t st) {
+  const size_t total = n * nchains;
+  if (!total) return PXM_OK;
+  if (is_complex)
+    k_soft_c<<<grid_for(total), 256, 0, st>>>((const cplx*)x, Tv, Ts, (cplx*)out, n, total);
+  else
+    k_soft_r<<<grid_for(total), 256, 0, st>>>((const double*)x, Tv, Ts, (double*)out, n, total);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
+                     const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
+                     double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
+                     unsigned int stream0, cudaStream_t st) {
+  MyulaArgs p;
+  p.X = (const cplx*)X;
+  p.prox = (const cplx*)prox;
+  p.gradg = (const cplx*)gradg;
+  p.Tv = Tv;
+  p.Ts = Ts;
+  p.w_re = w_re;
+  p.w_im = w_im;
+  p.Xout = (cplx*)Xout;
+  p.prox_out = (cplx*)prox_out;
+  p.n = n;
+  p.total = n * nchains;
+  p.a = 1 - delta / lmda;  // same expressions as mcmc.py:197-200
+  p.b = delta / lmda;
+  p.delta = delta;
+  p.sq2d = sqrt(2 * delta);
+  p.noise_mode = noise_mode;
+  p.seed = seed;
+  p.step = step;
+  p.stream0 = stream0;
+  if (!p.total) return PXM_OK;
+  k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* out, size_t n, size_t nchains,
+                     cudaStream_t st) {
+  const size_t total = n * nchains;
+  if (!total) return PXM_OK;
+  k_resid<<<grid_for(total), 256, 0, st>>>((const cplx*)preds, (const cplx*)data, (const cplx*)ic, (cplx*)out, n, total);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+constexpr int PXM_REDUCE_PARTS = 148;
+
+int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
+                      double delta, double lmda, size_t n, size_t nchains, void* partial, void* out,
+                      cudaStream_t st) {
+  ReduceArgs p;
+  p.kind = kind;
+  p.a = (const cplx*)a;
+  p.b = (const cplx*)b;
+  p.c = (const cplx*)c;
+  p.d = (const cplx*)d;
+  p.w = w;
+  p.delta = delta;
+  p.lmda = lmda;
+  p.n = n;
+  p.partial = (cplx*)partial;
+  p.out = (cplx*)out;
+  if (!nchains) return PXM_OK;
+  dim3 grid(PXM_REDUCE_PARTS, (unsigned)nchains);
+  k_reduce_stage1<<<grid, 256, 0, st>>>(p);
+  PXM_CUDA(cudaGetLastError());
+  k_reduce_stage2<<<(unsigned)nchains, 256, 0, st>>>((const cplx*)partial, PXM_REDUCE_PARTS, (cplx*)out);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_lincomb(int nx, const void* const* xs, const double* as, const double* z, double cz, double c0,
+                       void* out, size_t total, cudaStream_t st) {
+  LinArgs p;
+  p.nx = nx;
+  for (int k = 0; k < 4; ++k) {
+    p.x[k] = k < nx ? (const cplx*)xs[k] : nullptr;
+    p.a[k] = k < nx ? as[k] : 0.0;
+  }
+  p.z = z;
+  p.cz = cz;
+  p.c0 = c0;
+  p.out = (cplx*)out;
+  p.total = total;
+  if (!total) return PXM_OK;
+  k_lincomb<<<grid_for(total), 256, 0, st>>>(p);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_gather(int scatter, const void* in, const int* idx, const double* w, void* out, size_t nsel,
+                      size_t nfull, size_t nchains, cudaStream_t st) {
+  const size_t total = nsel * nchains;
+  if (scatter) PXM_CUDA(cudaMemsetAsync(out, 0, nfull * nchains * sizeof(cplx), st));
+  if (!total) return PXM_OK;
+  if (scatter)
+    k_scatter_w<<<grid_for(total), 256, 0, st>>>((const cplx*)in, idx, w, (cplx*)out, nsel, nfull, total);
+  else
+    k_gather_w<<<grid_for(total), 256, 0, st>>>((const cplx*)in, idx, w, (cplx*)out, nsel, nfull, total);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_lm_convert(int to_internal, void* flm, double* H, const unsigned long long* d_slot_off,
+                          const double* d_gl, int L, int paired, int nld, int nchains, cudaStream_t st) {
+  LmArgs p;
+  p.flm = (cplx*)flm;
+  p.H = H;
+  p.slot_off = d_slot_off;
+  p.gl = d_gl;
+  p.L = L;
+  p.paired = paired;
+  p.nld = nld;
+  p.nchains = nchains;
+  p.to_internal = to_internal;
+  const size_t total = (size_t)L * L * nchains;
+  if (!total) return PXM_OK;
+  k_lm_convert<<<grid_for(total), 256, 0, st>>>(p);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st) {
+  if (!total) return PXM_OK;
+  k_r2c<<<grid_for(total), 256, 0, st>>>(x, (cplx*)out, total);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* vals, const void* x, void* y, int nrows,
+                        size_t ncols, size_t nchains, cudaStream_t st) {
+  if (!nrows || !nchains) return PXM_OK;
+  dim3 grid((unsigned)((nrows * 32 + 255) / 256), (unsigned)nchains);
+  k_csr_spmv<<<grid, 256, 0, st>>>(indptr, indices, vals, (const cplx*)x, (cplx*)y, nrows, ncols);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, double Ts, const void* gradg, double lmda,
+                         void* out, size_t n, size_t nchains, cudaStream_t st) {
+  const size_t total = n * nchains;
+  if (!total) return PXM_OK;
+  k_gradlogpi<<<grid_for(total), 256, 0, st>>>((const cplx*)X, (const cplx*)prox, Tv, Ts, (const cplx*)gradg, lmda,
+                                                (cplx*)out, n, total);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}

@@ -1,0 +1,297 @@
+// Grouped FP64 tensor-core (DMMA) Legendre contraction for sm_100a.
+//
+// This is the O(L^3) stage of every spherical harmonic / wavelet transform the
+// reference performs through pyssht/pys2let (call sites:
+// /root/reference/pxmcmc/transforms.py:95-98, pxmcmc/measurements.py:223-239).
+// For every azimuthal order m it multiplies a precomputed REAL table
+// T^m[t, l] (32x16 swizzled tiles, see pxm_common.cuh) with complex data stored
+// as real columns (re/im x +-m x chains):
+//
+//   ORIENT 0 (synthesis-type):  C[t, n] = sum_l T^m[t, l] B[l, n]
+//   ORIENT 1 (analysis-type) :  C[l, n] = sum_t T^m[t, l] B[t, n]   (sum may run
+//                               over several segments = wavelet scales)
+//
+// One CTA = one 64-row output tile of one m (work item) x one block of BN
+// columns.  Table tiles and data rows are staged by cp.async.bulk (1-D TMA
+// bulk copies) into a STAGES-deep shared-memory ring guarded by mbarriers; 8
+// warps issue mma.sync.m8n8k4.f64 (DMMA) from conflict-free fragment loads.
+// tcgen05/TMEM has no FP64 kind, so DMMA is the FP64 tensor path on Blackwell.
+#include "pxm_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
+struct LegCfg {
+  static constexpr int BM = 64;
+  static constexpr int BK = ORIENT == 0 ? 16 : 32;
+  static constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;
+  static constexpr int NT_M = BM / TILE_ROWS;
+  static constexpr int A_STAGE = NT_M * PXM_TILE_DOUBLES;
+  static constexpr int B_STAGE = BK * BN;
+  static constexpr int WM = BM / WARPS_M;
+  static constexpr int WN = BN / WARPS_N;
+  static constexpr int MI = WM / 8;
+  static constexpr int NI = WN / 8;
+  static constexpr size_t SMEM = 128 + (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
+  static_assert(WARPS_M * WARPS_N == 8, "8 warps");
+  static_assert(MI >= 1 && NI >= 1, "warp tile");
+};
+
+template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
+__global__ void __launch_bounds__(256)
+pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ bmat,
+                    double* __restrict__ cmat, const PxmLegItem* __restrict__ items,
+                    const PxmLegSeg* __restrict__ segs, int nld) {
+  using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  double* sA = reinterpret_cast<double*>(smem_raw + 128);
+  double* sB = sA + STAGES * C::A_STAGE;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const PxmLegItem item = items[blockIdx.x];
+  const int n0 = blockIdx.y * BN;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- producer cursor (thread 0 only) -----------------------------------
+  int pseg = 0, pk = 0, pit = 0;
+  int total = 0;
+  for (int s = 0; s < item.seg_count; ++s) total += segs[item.seg_begin + s].nk;
+
+  auto produce = [&]() {
+    // skip empty segments
+    while (pseg < item.seg_count && pk >= segs[item.seg_begin + pseg].nk) {
+      ++pseg;
+      pk = 0;
+    }
+    if (pseg >= item.seg_count) return;
+    const PxmLegSeg sg = segs[item.seg_begin + pseg];
+    const int slot = pit % STAGES;
+    uint64_t* bar = &full[slot];
+    const uint32_t bytes = (uint32_t)(sg.nmt * PXM_TILE_DOUBLES * 8 + C::BK * BN * 8);
+    mbar_expect_tx(bar, bytes);
+    double* dstA = sA + slot * C::A_STAGE + sg.mt0 * PXM_TILE_DOUBLES;
+    const double* srcA = tab + sg.a_off + (size_t)pk * (size_t)sg.a_kstride;
+    if (sg.a_mstride == PXM_TILE_DOUBLES) {
+      bulk_g2s(dstA, srcA, (uint32_t)(sg.nmt * PXM_TILE_DOUBLES * 8), bar);
+    } else {
+      for (int j = 0; j < sg.nmt; ++j)
+        bulk_g2s(dstA + j * PXM_TILE_DOUBLES, srcA + (size_t)j * (size_t)sg.a_mstride,
+                 PXM_TILE_DOUBLES * 8, bar);
+    }
+    double* dstB = sB + slot * C::B_STAGE;
+    const double* srcB = bmat + sg.b_off + ((size_t)pk * (C::BK / 4) * (size_t)nld + (size_t)n0) * 4;
+    if (BN == nld) {
+      bulk_g2s(dstB, srcB, (uint32_t)(C::BK * BN * 8), bar);
+    } else {
+#pragma unroll
+      for (int rg = 0; rg < C::BK / 4; ++rg)
+        bulk_g2s(dstB + rg * BN * 4, srcB + (size_t)rg * (size_t)nld * 4, BN * 32, bar);
+    }
+    ++pk;
+    ++pit;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES - 1 && s < total; ++s) produce();
+  }
+
+  double acc[C::MI][C::NI][2];
+#pragma unroll
+  for (int mi = 0; mi < C::MI; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < C::NI; ++ni) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+  int it = 0;
+  for (int s = 0; s < item.seg_count; ++s) {
+    const int seg_nk = segs[item.seg_begin + s].nk;
+    const int seg_mt0 = segs[item.seg_begin + s].mt0;
+    const int seg_mt1 = seg_mt0 + segs[item.seg_begin + s].nmt;
+    bool mv[C::MI];
+#pragma unroll
+    for (int mi = 0; mi < C::MI; ++mi) {
+      const int tl = (wm * C::WM + mi * 8) / C::TILE_ROWS;
+      mv[mi] = (tl >= seg_mt0) && (tl < seg_mt1);
+    }
+    for (int k = 0; k < seg_nk; ++k, ++it) {
+      if (tid == 0 && pit < total) produce();
+      const int slot = it % STAGES;
+      mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
+      const double* a_s = sA + slot * C::A_STAGE;
+      const double* b_s = sB + slot * C::B_STAGE;
+#pragma unroll
+      for (int kk = 0; kk < C::BK / 4; ++kk) {
+        double a[C::MI], b[C::NI];
+#pragma unroll
+        for (int mi = 0; mi < C::MI; ++mi) {
+          const int row = wm * C::WM + mi * 8 + g;
+          if (ORIENT == 0) {
+            const int tl = row >> 5, r = row & 31;
+            a[mi] = a_s[tl * PXM_TILE_DOUBLES + r * PXM_TILE_L + (((kk ^ (r & 3)) << 2) | q)];
+          } else {
+            const int tl = row >> 4, c = row & 15, r = kk * 4 + q;
+            a[mi] = a_s[tl * PXM_TILE_DOUBLES + r * PXM_TILE_L + (c ^ (q << 2))];
+          }
+        }
+#pragma unroll
+        for (int ni = 0; ni < C::NI; ++ni) b[ni] = b_s[(kk * BN + wn * C::WN + ni * 8 + g) * 4 + q];
+#pragma unroll
+        for (int mi = 0; mi < C::MI; ++mi) {
+          if (mv[mi]) {
+#pragma unroll
+            for (int ni = 0; ni < C::NI; ++ni) dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+          }
+        }
+      }
+      __syncthreads();  // everyone done with `slot` before thread 0 refills it next iteration
+    }
+  }
+
+  // ---- epilogue: k4-interleaved store ---------------------------------------
+#pragma unroll
+  for (int mi = 0; mi < C::MI; ++mi) {
+    const int row = wm * C::WM + mi * 8 + g;
+    if (row / C::TILE_ROWS >= item.nmt_out) continue;
+#pragma unroll
+    for (int ni = 0; ni < C::NI; ++ni) {
+      const int col = n0 + wn * C::WN + ni * 8 + 2 * q;
+      cmat[item.c_off + pxm_il_index(row, col, nld)] = acc[mi][ni][0];
+      cmat[item.c_off + pxm_il_index(row, col + 1, nld)] = acc[mi][ni][1];
+    }
+  }
+}
+
+// Plain one-thread-per-output contraction over the same descriptors.  Debugging
+// aid for the GPU tests (localises a fault to the tensor-core kernel or to the
+// tables/descriptors); never selected by the product path.
+template <int ORIENT>
+__global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const double* __restrict__ bmat,
+                                          double* __restrict__ cmat, const PxmLegItem* __restrict__ items,
+                                          const PxmLegSeg* __restrict__ segs, int nld) {
+  constexpr int BK = ORIENT == 0 ? 16 : 32;
+  constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;
+  const PxmLegItem item = items[blockIdx.x];
+  const int row = threadIdx.x & 63;
+  for (int col = blockIdx.y * blockDim.x / 64 + (threadIdx.x >> 6); col < nld; col += gridDim.y * (blockDim.x / 64)) {
+    const int tl = row / TILE_ROWS;
+    if (tl >= item.nmt_out) continue;
+    double acc = 0.0;
+    for (int s = 0; s < item.seg_count; ++s) {
+      const PxmLegSeg sg = segs[item.seg_begin + s];
+      if (tl < sg.mt0 || tl >= sg.mt0 + sg.nmt) continue;
+      for (int k = 0; k < sg.nk; ++k) {
+        const double* tile = tab + sg.a_off + (size_t)k * sg.a_kstride + (size_t)(tl - sg.mt0) * sg.a_mstride;
+        for (int kk = 0; kk < BK; ++kk) {
+          double a;
+          if (ORIENT == 0)
+            a = tile[pxm_tile_word(row & 31, kk)];
+          else
+            a = tile[pxm_tile_word(kk, row & 15)];
+          acc += a * bmat[sg.b_off + pxm_il_index(k * BK + kk, col, nld)];
+        }
+      }
+    }
+    cmat[item.c_off + pxm_il_index(row, col, nld)] = acc;
+  }
+}
+
+template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
+int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* items, const PxmLegSeg* segs,
+               int nitems, int nld, cudaStream_t stream) {
+  using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
+  static bool configured = false;
+  auto kern = pxm_legendre_kernel<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
+  if (!configured) {
+    PXM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  dim3 grid(nitems, nld / BN);
+  kern<<<grid, 256, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
+  PXM_CUDA(cudaGetLastError());
+  return PXM_OK;
+}
+
+template <int ORIENT>
+int launch_orient(const double* tab, const double* b, double* c, const PxmLegItem* items, const PxmLegSeg* segs,
+                  int nitems, int nld, cudaStream_t stream) {
+  if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  pxm_set_error("legendre: unsupported column count " + std::to_string(nld));
+  return PXM_ERR_ARG;
+}
+
+}  // namespace
+
+// valid leading dimensions: 8, 16, 32, 64 or a multiple of 128
+int pxm_legendre_pad_columns(int ncols) {
+  if (ncols <= 8) return 8;
+  if (ncols <= 16) return 16;
+  if (ncols <= 32) return 32;
+  if (ncols <= 64) return 64;
+  return pxm_round_up(ncols, 128);
+}
+
+int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
+                        const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive) {
+  if (nitems <= 0) return PXM_OK;
+  if (naive) {
+    dim3 grid(nitems, 4);
+    if (orient == 0)
+      pxm_legendre_naive_kernel<0><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
+    else
+      pxm_legendre_naive_kernel<1><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
+    PXM_CUDA(cudaGetLastError());
+    return PXM_OK;
+  }
+  if (orient == 0) return launch_orient<0>(tab, b, c, items, segs, nitems, nld, stream);
+  return launch_orient<1>(tab, b, c, items, segs, nitems, nld, stream);
+}

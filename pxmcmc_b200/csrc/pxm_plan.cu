@@ -1,0 +1,760 @@
+// Host-side plans and the C ABI (include/pxmcmc_b200.h).
+//
+// A plan owns: the Legendre table arena, the ring-FFT twiddle arena, a
+// zero-initialised workspace (ring-Fourier and harmonic buffers in the
+// k4-interleaved layout) and the work-item descriptors of every operator.
+// Every transform is the same four-stage pipeline
+//     [ring FFT in] -> [DMMA contraction over rings] -> [DMMA contraction over l] -> [ring FFT out]
+// with stages dropped at the harmonic-space boundary of the pyssht-level calls.
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pxmcmc_b200.h"
+#include "pxm_plan.h"
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+void pxm_set_error(const std::string& msg) { g_err = msg; }
+static int g_naive = 0;
+int pxm_debug_naive() { return g_naive; }
+
+namespace {
+
+typedef unsigned long long ull;
+
+struct RingBuf {
+  int ell = 0;
+  bool paired = true;
+  int nslots = 0;
+  ull off = 0;          // doubles into the workspace
+  ull slot_stride = 0;  // doubles
+  int slot_of(int m) const { return paired ? std::abs(m) : m + ell - 1; }
+  ull doubles() const { return (ull)nslots * slot_stride; }
+};
+
+struct HarmBuf {
+  int L = 0;
+  bool paired = true;
+  std::vector<ull> slot_off;  // absolute doubles into the workspace
+  PxmDevVec<ull> d_slot_off;
+  ull total = 0;
+  int slot_of(int m) const { return paired ? std::abs(m) : m + L - 1; }
+};
+
+void make_ring(RingBuf& R, int ell, bool paired, int nld, ull& cursor) {
+  R.ell = ell;
+  R.paired = paired;
+  R.nslots = paired ? ell : 2 * ell - 1;
+  R.slot_stride = (ull)pxm_round_up(ell, 32) * nld;
+  R.off = cursor;
+  cursor += R.doubles();
+}
+
+void make_harm(HarmBuf& H, int L, bool paired, int nld, ull& cursor) {
+  H.L = L;
+  H.paired = paired;
+  const int ns = paired ? L : 2 * L - 1;
+  H.slot_off.resize(ns);
+  ull c = cursor;
+  for (int s = 0; s < ns; ++s) {
+    const int am = paired ? s : std::abs(s - (L - 1));
+    H.slot_off[s] = c;
+    c += (ull)pxm_round_up(L - am, 64) * nld;
+  }
+  H.total = c - cursor;
+  cursor = c;
+}
+
+struct TableRef {
+  PxmTableLayout T;
+  ull base = 0;  // doubles into the plan's table arena (T.tile_off are relative to 0 with base folded in)
+  int family = 0;  // 0 lambda, 1 W
+  std::vector<double> g;
+  bool built = false;
+};
+
+struct Stage {
+  std::vector<PxmLegItem> items;
+  std::vector<PxmLegSeg> segs;
+  PxmDevVec<PxmLegItem> d_items;
+  PxmDevVec<PxmLegSeg> d_segs;
+  int orient = 0;
+  int upload() {
+    // heaviest items first: the hardware block scheduler then balances the triangular workload
+    std::vector<int> order(items.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return items[a].cost > items[b].cost; });
+    std::vector<PxmLegItem> sorted;
+    for (int i : order) sorted.push_back(items[i]);
+    items.swap(sorted);
+    PXM_TRY(d_items.upload(items));
+    PXM_TRY(d_segs.upload(segs));
+    return PXM_OK;
+  }
+  void release() {
+    d_items.release();
+    d_segs.release();
+  }
+};
+
+struct FftStage {
+  std::vector<PxmFftGroup> groups;
+  PxmDevVec<PxmFftGroup> d_groups;
+  int ctas = 0;
+  void release() { d_groups.release(); }
+};
+
+// ring-FFT twiddle bookkeeping: one (chirp, bhat, tw) triple per distinct ring length
+struct FftTables {
+  std::map<int, PxmFftGroup> by_n;
+  ull cursor = 0;  // complex elements
+  void* d_arena = nullptr;
+  PxmFftGroup get(int ell) {
+    const int n = 2 * ell - 1;
+    auto it = by_n.find(n);
+    if (it != by_n.end()) return it->second;
+    PxmFftGroup g = {};
+    g.ell = ell;
+    g.n = n;
+    g.M = pxm_fft_choose_M(n, &g.logM);
+    g.chirp_off = cursor;
+    cursor += (ull)pxm_round_up(n, 2);
+    g.bhat_off = cursor;
+    cursor += g.M;
+    g.tw_off = cursor;
+    cursor += g.M;
+    by_n[n] = g;
+    return g;
+  }
+  int finalize(cudaStream_t st) {
+    std::vector<PxmFftGroup> hs;
+    for (auto& kv : by_n) hs.push_back(kv.second);
+    PXM_CUDA(cudaMalloc(&d_arena, std::max<ull>(cursor, 1) * 16));
+    PxmDevVec<PxmFftGroup> dg;
+    PXM_TRY(dg.upload(hs));
+    PXM_TRY(pxm_fft_setup_tables(dg.d, hs.data(), (int)hs.size(), d_arena, st));
+    PXM_CUDA(cudaStreamSynchronize(st));
+    dg.release();
+    return PXM_OK;
+  }
+  void release() {
+    if (d_arena) cudaFree(d_arena);
+    d_arena = nullptr;
+  }
+};
+
+void add_fft_group(FftStage& S, FftTables& tabs, const RingBuf& R, ull pix_off, double scale) {
+  PxmFftGroup g = tabs.get(R.ell);
+  g.rings = R.ell;
+  g.rings_per_cta = pxm_fft_rings_per_cta(g.M);
+  g.cta_begin = S.ctas;
+  g.nslots = R.nslots;
+  g.paired = R.paired ? 1 : 0;
+  g.scale = scale;
+  g.pix_off = pix_off;
+  g.f_off = R.off;
+  g.slot_stride = R.slot_stride;
+  S.ctas += pxm_ceil_div(R.ell, g.rings_per_cta);
+  S.groups.push_back(g);
+}
+
+int slot_index(const PxmTableLayout& T, int m) { return T.paired ? std::abs(m) : m + T.lmax - 1; }
+
+// contraction over l:  ring buffer R  <-  table T  x  harmonic buffer H
+void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf& R, int nld) {
+  const PxmTableLayout& T = tr.T;
+  S.orient = 0;
+  for (int s = 0; s < T.nslots; ++s) {
+    if (T.nlb[s] == 0) continue;
+    const int m = T.slot_m[s];
+    const int hs = H.slot_of(m), rs = R.slot_of(m);
+    for (int i = 0; 2 * i < T.ntb; ++i) {
+      PxmLegSeg sg = {};
+      sg.a_off = T.tile_off[s] + (ull)(2 * i) * T.nlb[s] * PXM_TILE_DOUBLES;
+      sg.a_kstride = PXM_TILE_DOUBLES;
+      sg.a_mstride = T.nlb[s] * PXM_TILE_DOUBLES;
+      sg.mt0 = 0;
+      sg.nmt = std::min(2, T.ntb - 2 * i);
+      sg.nk = T.nlb[s];
+      sg.b_off = H.slot_off[hs] + (ull)T.lb0[s] * PXM_TILE_L * nld;
+      PxmLegItem it = {};
+      it.c_off = R.off + (ull)rs * R.slot_stride + (ull)(64 * i) * nld;
+      it.seg_begin = (int)S.segs.size();
+      it.seg_count = 1;
+      it.nmt_out = sg.nmt;
+      it.cost = sg.nk * sg.nmt;
+      S.segs.push_back(sg);
+      S.items.push_back(it);
+    }
+  }
+}
+
+struct ASource {
+  const TableRef* tr;
+  const RingBuf* R;
+};
+
+// contraction over rings:  harmonic buffer H  <-  sum over sources  table^T x ring buffer
+void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H, int nld) {
+  S.orient = 1;
+  const int ns = (int)H.slot_off.size();
+  for (int hs = 0; hs < ns; ++hs) {
+    const int m = H.paired ? hs : hs - (H.L - 1);
+    const int am = std::abs(m);
+    const int nlbH = pxm_ceil_div(H.L - am, PXM_TILE_L);
+    for (int lt = 0; 4 * lt < nlbH; ++lt) {
+      PxmLegItem it = {};
+      it.seg_begin = (int)S.segs.size();
+      it.cost = 0;
+      for (const ASource& src : srcs) {
+        const PxmTableLayout& T = src.tr->T;
+        if (am >= T.lmax) continue;
+        const int s = slot_index(T, m);
+        if (T.nlb[s] == 0) continue;
+        const int lbA = std::max(4 * lt, T.lb0[s]), lbB = std::min(4 * lt + 4, T.lb0[s] + T.nlb[s]);
+        if (lbA >= lbB) continue;
+        PxmLegSeg sg = {};
+        sg.a_off = T.tile_off[s] + (ull)(lbA - T.lb0[s]) * PXM_TILE_DOUBLES;
+        sg.a_kstride = T.nlb[s] * PXM_TILE_DOUBLES;
+        sg.a_mstride = PXM_TILE_DOUBLES;
+        sg.mt0 = lbA - 4 * lt;
+        sg.nmt = lbB - lbA;
+        sg.nk = T.ntb;
+        sg.b_off = src.R->off + (ull)src.R->slot_of(m) * src.R->slot_stride;
+        it.cost += sg.nk * sg.nmt;
+        S.segs.push_back(sg);
+      }
+      it.seg_count = (int)S.segs.size() - it.seg_begin;
+      it.c_off = H.slot_off[hs] + (ull)(64 * lt) * nld;
+      it.nmt_out = std::min(4, nlbH - 4 * lt);
+      S.items.push_back(it);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- tiling
+// Scale-discretised wavelet tiling (axisymmetric), restating s2let's
+// s2let_tiling_axisym / phi2_s2dw that the reference reaches through
+// pys2let.wavelet_tiling (/root/reference/pxmcmc/utils.py:117, prior.py:121,132).
+double f_s2dw(double k, double B) {
+  const double t = (k - (1.0 / B)) * (2.0 * B / (B - 1.0)) - 1.0;
+  return std::exp(-2.0 / (1.0 - t * t)) / k;
+}
+double quadtrap(double a, double b, int n, double B) {
+  if (a == b) return 0.0;
+  const double h = (b - a) / n;
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double f1 = f_s2dw(a + i * h, B), f2 = f_s2dw(a + (i + 1) * h, B);
+    if (std::isfinite(f1) && std::isfinite(f2)) sum += ((f1 + f2) * h) / 2.0;
+  }
+  return sum;
+}
+int j_max(int L, double B) { return (int)std::ceil(std::log((double)L) / std::log(B)); }
+
+struct Tiling {
+  int J = 0;
+  std::vector<int> bandlimits;                // scaling first, then j = J_min..J
+  std::vector<std::vector<double>> kernels;   // kappa0, kappa_j  (length L each)
+};
+
+Tiling make_tiling(int L, double B, int J_min) {
+  Tiling t;
+  t.J = j_max(L, B);
+  const int J = t.J, n = 300;
+  const double norm = quadtrap(1.0 / B, 1.0, n, B);
+  std::vector<std::vector<double>> phi2(J + 2, std::vector<double>(L, 0.0));
+  for (int j = 0; j <= J + 1; ++j)
+    for (int l = 0; l < L; ++l) {
+      if (l < std::pow(B, j - 1))
+        phi2[j][l] = 1.0;
+      else if (l > std::pow(B, j))
+        phi2[j][l] = 0.0;
+      else
+        phi2[j][l] = quadtrap((double)l / std::pow(B, j), 1.0, n, B) / norm;
+    }
+  t.bandlimits.push_back(std::min((int)std::ceil(std::pow(B, J_min)), L));
+  std::vector<double> k0(L);
+  for (int l = 0; l < L; ++l) k0[l] = std::sqrt(phi2[J_min][l]);
+  t.kernels.push_back(k0);
+  for (int j = J_min; j <= J; ++j) {
+    std::vector<double> k(L);
+    for (int l = 0; l < L; ++l) {
+      const double d = phi2[j + 1][l] - phi2[j][l];
+      k[l] = d > 0.0 ? std::sqrt(d) : 0.0;
+    }
+    t.bandlimits.push_back(std::min((int)std::ceil(std::pow(B, j + 1)), L));
+    t.kernels.push_back(k);
+  }
+  return t;
+}
+
+}  // namespace
+
+// =========================================================================
+//                               SHT plan
+// =========================================================================
+struct pxm_sht_plan {
+  int L = 0, spin = 0, nb = 0, nld = 0;
+  bool paired = true;
+  TableRef lam, w;
+  double* d_tab = nullptr;
+  double* d_ws = nullptr;
+  RingBuf R;
+  HarmBuf H;
+  FftTables ffttab;
+  FftStage fft_in_unit, fft_in_norm, fft_out_unit, fft_out_norm;
+  Stage s_lam, a_lam, s_w, a_w;
+  cudaStream_t setup_stream = 0;
+
+  int ensure(TableRef& tr) {
+    if (tr.built) return PXM_OK;
+    if (tr.family == 0)
+      PXM_TRY(pxm_generate_lambda(tr.T, d_tab, nullptr, setup_stream));
+    else
+      PXM_TRY(pxm_generate_w(tr.T, d_tab, nullptr, setup_stream));
+    tr.built = true;
+    return PXM_OK;
+  }
+};
+
+extern "C" {
+
+const char* pxm_last_error(void) { return g_err.c_str(); }
+
+int pxm_debug_set_naive(int on) {
+  g_naive = on;
+  return PXM_OK;
+}
+
+int pxm_init(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    pxm_set_error("no CUDA device visible: pxmcmc_b200 has no CPU fallback");
+    return PXM_ERR_NODEVICE;
+  }
+  PXM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PXM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    pxm_set_error(std::string("device ") + prop.name + " is not sm_100a (Blackwell); kernels are built for sm_100a only");
+    return PXM_ERR_UNSUPPORTED;
+  }
+  return PXM_OK;
+}
+
+int pxm_sht_plan_create(int L, int spin, int max_batch, pxm_sht_plan** out) {
+  PXM_REQUIRE(L >= 1 && L <= 1024, "L must be in [1, 1024]");
+  PXM_REQUIRE(std::abs(spin) < L || L == 1, "|spin| must be < L");
+  PXM_REQUIRE(max_batch >= 1, "max_batch >= 1");
+  std::unique_ptr<pxm_sht_plan> p(new pxm_sht_plan);
+  p->L = L;
+  p->spin = spin;
+  p->nb = max_batch;
+  p->paired = (spin == 0);
+  p->nld = pxm_legendre_pad_columns((p->paired ? 4 : 2) * max_batch);
+  ull tcur = 0;
+  pxm_make_table_layout(p->lam.T, L, L, L, spin, 0, L, tcur);
+  tcur += p->lam.T.doubles;
+  p->lam.family = 0;
+  pxm_make_table_layout(p->w.T, L, L, L, spin, 0, L, tcur);
+  tcur += p->w.T.doubles;
+  p->w.family = 1;
+  PXM_CUDA(cudaMalloc(&p->d_tab, std::max<ull>(tcur, 1) * 8));
+  PXM_CUDA(cudaMemset(p->d_tab, 0, std::max<ull>(tcur, 1) * 8));
+  ull wcur = 0;
+  make_ring(p->R, L, p->paired, p->nld, wcur);
+  make_harm(p->H, L, p->paired, p->nld, wcur);
+  PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
+  PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
+  PXM_TRY(p->H.d_slot_off.upload(p->H.slot_off));
+  const double inv_n = 1.0 / (2 * L - 1);
+  add_fft_group(p->fft_in_unit, p->ffttab, p->R, 0, 1.0);
+  add_fft_group(p->fft_in_norm, p->ffttab, p->R, 0, inv_n);
+  add_fft_group(p->fft_out_unit, p->ffttab, p->R, 0, 1.0);
+  add_fft_group(p->fft_out_norm, p->ffttab, p->R, 0, inv_n);
+  PXM_TRY(p->ffttab.finalize(0));
+  for (FftStage* f : {&p->fft_in_unit, &p->fft_in_norm, &p->fft_out_unit, &p->fft_out_norm})
+    PXM_TRY(f->d_groups.upload(f->groups));
+  build_s_items(p->s_lam, p->lam, p->H, p->R, p->nld);
+  build_s_items(p->s_w, p->w, p->H, p->R, p->nld);
+  build_a_items(p->a_lam, {{&p->lam, &p->R}}, p->H, p->nld);
+  build_a_items(p->a_w, {{&p->w, &p->R}}, p->H, p->nld);
+  for (Stage* s : {&p->s_lam, &p->s_w, &p->a_lam, &p->a_w}) PXM_TRY(s->upload());
+  *out = p.release();
+  return PXM_OK;
+}
+
+int pxm_sht_plan_destroy(pxm_sht_plan* p) {
+  if (!p) return PXM_OK;
+  for (Stage* s : {&p->s_lam, &p->s_w, &p->a_lam, &p->a_w}) s->release();
+  for (FftStage* f : {&p->fft_in_unit, &p->fft_in_norm, &p->fft_out_unit, &p->fft_out_norm}) f->release();
+  p->ffttab.release();
+  p->H.d_slot_off.release();
+  if (p->d_tab) cudaFree(p->d_tab);
+  if (p->d_ws) cudaFree(p->d_ws);
+  delete p;
+  return PXM_OK;
+}
+
+size_t pxm_sht_plan_table_bytes(const pxm_sht_plan* p) { return (p->lam.T.doubles + p->w.T.doubles) * 8; }
+
+// which: 0 inverse, 1 forward, 2 inverse_adjoint, 3 forward_adjoint
+static int sht_run(pxm_sht_plan* p, int which, void* d_flm, void* d_f, int nb, const double* d_gl, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)p->L * (2 * p->L - 1);
+  TableRef& tr = (which == 0 || which == 2) ? p->lam : p->w;
+  PXM_TRY(p->ensure(tr));
+  const int naive = pxm_debug_naive();
+  if (which == 0 || which == 3) {  // harmonic -> pixel
+    PXM_TRY(pxm_launch_lm_convert(1, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
+    Stage& S = which == 0 ? p->s_lam : p->s_w;
+    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+                                st, naive));
+    FftStage& F = which == 0 ? p->fft_out_unit : p->fft_out_norm;
+    PXM_TRY(pxm_fft_launch(1, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, st));
+  } else {  // pixel -> harmonic
+    FftStage& F = which == 2 ? p->fft_in_unit : p->fft_in_norm;
+    PXM_TRY(pxm_fft_launch(0, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, st));
+    Stage& S = which == 2 ? p->a_lam : p->a_w;
+    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+                                st, naive));
+    PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
+  }
+  return PXM_OK;
+}
+
+int pxm_sht_inverse(pxm_sht_plan* p, const void* d_flm, void* d_f, int nbatch, const double* d_gl, void* stream) {
+  return sht_run(p, 0, const_cast<void*>(d_flm), d_f, nbatch, d_gl, stream);
+}
+int pxm_sht_forward(pxm_sht_plan* p, const void* d_f, void* d_flm, int nbatch, const double* d_gl, void* stream) {
+  return sht_run(p, 1, d_flm, const_cast<void*>(d_f), nbatch, d_gl, stream);
+}
+int pxm_sht_inverse_adjoint(pxm_sht_plan* p, const void* d_f, void* d_flm, int nbatch, const double* d_gl,
+                            void* stream) {
+  return sht_run(p, 2, d_flm, const_cast<void*>(d_f), nbatch, d_gl, stream);
+}
+int pxm_sht_forward_adjoint(pxm_sht_plan* p, const void* d_flm, void* d_f, int nbatch, const double* d_gl,
+                            void* stream) {
+  return sht_run(p, 3, const_cast<void*>(d_flm), d_f, nbatch, d_gl, stream);
+}
+
+}  // extern "C"
+
+// =========================================================================
+//                             wavelet plan
+// =========================================================================
+struct WavDirection {  // tables + stages of one transform pair
+  TableRef full;                 // bandlimit-L table (lambda for synthesis pair, W for analysis pair)
+  std::vector<TableRef> scales;  // per-scale tables premultiplied by the harmonic kernels
+  Stage a_multi;                 // scale rings  -> harmonic (sum over scales)
+  Stage s_full;                  // harmonic     -> full-L rings
+  Stage a_full;                  // full-L rings -> harmonic
+  Stage s_multi;                 // harmonic     -> scale rings
+  FftStage fft_scales_in, fft_full_out, fft_full_in, fft_scales_out;
+  PxmDevVec<double> d_g;         // concatenated kernels
+  bool built = false;
+};
+
+struct pxm_wav_plan {
+  int L = 0, J_min = 0, nb = 0, nld = 0, nscales_total = 0;
+  double B = 0;
+  Tiling til;
+  std::vector<ull> coef_off;  // complex offset of every scale map inside the coefficient vector
+  ull ncoefs = 0, nscal = 0;
+  double* d_tab = nullptr;
+  double* d_ws = nullptr;
+  ull tab_doubles = 0;
+  RingBuf Rfull;
+  std::vector<RingBuf> Rsc;
+  HarmBuf H;
+  FftTables ffttab;
+  WavDirection syn, ana;  // syn: synthesis + synthesis_adjoint ; ana: analysis + analysis_adjoint
+
+  int ensure(WavDirection& D) {
+    if (D.built) return PXM_OK;
+    // per-scale kernels live contiguously on the device
+    std::vector<double> allg;
+    std::vector<size_t> goff;
+    for (auto& tr : D.scales) {
+      goff.push_back(allg.size());
+      allg.insert(allg.end(), tr.g.begin(), tr.g.end());
+    }
+    PXM_TRY(D.d_g.upload(allg));
+    if (D.full.family == 0)
+      PXM_TRY(pxm_generate_lambda(D.full.T, d_tab, nullptr, 0));
+    else
+      PXM_TRY(pxm_generate_w(D.full.T, d_tab, nullptr, 0));
+    for (size_t i = 0; i < D.scales.size(); ++i) {
+      if (D.scales[i].family == 0)
+        PXM_TRY(pxm_generate_lambda(D.scales[i].T, d_tab, D.d_g.d + goff[i], 0));
+      else
+        PXM_TRY(pxm_generate_w(D.scales[i].T, d_tab, D.d_g.d + goff[i], 0));
+    }
+    D.built = true;
+    return PXM_OK;
+  }
+};
+
+extern "C" {
+
+int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan** out) {
+  PXM_REQUIRE(L >= 2 && L <= 1024, "L must be in [2, 1024]");
+  PXM_REQUIRE(B > 1.0, "B must be > 1");
+  PXM_REQUIRE(J_min >= 0, "J_min >= 0");
+  PXM_REQUIRE(max_batch >= 1, "max_batch >= 1");
+  std::unique_ptr<pxm_wav_plan> p(new pxm_wav_plan);
+  p->L = L;
+  p->B = B;
+  p->J_min = J_min;
+  p->nb = max_batch;
+  p->nld = pxm_legendre_pad_columns(4 * max_batch);
+  p->til = make_tiling(L, B, J_min);
+  PXM_REQUIRE(p->til.J >= J_min, "J_min larger than J_max");
+  const int S = (int)p->til.bandlimits.size();
+  p->nscales_total = S;
+  ull c = 0;
+  for (int i = 0; i < S; ++i) {
+    p->coef_off.push_back(c);
+    const ull Lj = p->til.bandlimits[i];
+    c += Lj * (2 * Lj - 1);
+  }
+  p->ncoefs = c;
+  p->nscal = (ull)p->til.bandlimits[0] * (2 * p->til.bandlimits[0] - 1);
+
+  // ---- table layouts ----------------------------------------------------------
+  const double SQ2PI = std::sqrt(2.0 * 3.14159265358979323846);
+  ull tcur = 0;
+  auto add_table = [&](TableRef& tr, int fam, int ell, int lo, int hi, const std::vector<double>& g) {
+    tr.family = fam;
+    tr.g = g;
+    pxm_make_table_layout(tr.T, ell, ell, ell, 0, lo, hi, tcur);
+    tcur += tr.T.doubles;
+  };
+  std::vector<double> ones;
+  add_table(p->syn.full, 0, L, 0, L, ones);
+  add_table(p->ana.full, 1, L, 0, L, ones);
+  p->syn.scales.resize(S);
+  p->ana.scales.resize(S);
+  for (int i = 0; i < S; ++i) {
+    const int Lj = p->til.bandlimits[i];
+    std::vector<double> gs(Lj), ga(Lj);
+    int lo = Lj, hi = 0;
+    for (int l = 0; l < Lj; ++l) {
+      const double k = p->til.kernels[i][l];
+      // (2 pi)^(+-1/2): so3's N=1 normalisation split between analysis and synthesis
+      gs[l] = (i == 0) ? k : k * SQ2PI;
+      ga[l] = (i == 0) ? k : k / SQ2PI;
+      if (k != 0.0) {
+        lo = std::min(lo, l);
+        hi = std::max(hi, l + 1);
+      }
+    }
+    if (hi <= lo) {
+      lo = 0;
+      hi = Lj;
+    }
+    add_table(p->syn.scales[i], 1, Lj, lo, hi, gs);
+    add_table(p->ana.scales[i], 0, Lj, lo, hi, ga);
+  }
+  p->tab_doubles = tcur;
+  PXM_CUDA(cudaMalloc(&p->d_tab, std::max<ull>(tcur, 1) * 8));
+  PXM_CUDA(cudaMemset(p->d_tab, 0, std::max<ull>(tcur, 1) * 8));
+
+  // ---- workspace ------------------------------------------------------------------
+  ull wcur = 0;
+  make_ring(p->Rfull, L, true, p->nld, wcur);
+  p->Rsc.resize(S);
+  for (int i = 0; i < S; ++i) make_ring(p->Rsc[i], p->til.bandlimits[i], true, p->nld, wcur);
+  make_harm(p->H, L, true, p->nld, wcur);
+  PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
+  PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
+
+  // ---- stages -----------------------------------------------------------------------
+  const double inv_nL = 1.0 / (2 * L - 1);
+  for (WavDirection* D : {&p->syn, &p->ana}) {
+    const bool is_syn = (D == &p->syn);
+    // pixel-side normalisations: the 1/(2l-1) belongs to the W (quadrature) side
+    for (int i = 0; i < S; ++i) {
+      const double inv_n = 1.0 / (2 * p->til.bandlimits[i] - 1);
+      add_fft_group(D->fft_scales_in, p->ffttab, p->Rsc[i], p->coef_off[i], is_syn ? inv_n : 1.0);
+      add_fft_group(D->fft_scales_out, p->ffttab, p->Rsc[i], p->coef_off[i], is_syn ? inv_n : 1.0);
+    }
+    add_fft_group(D->fft_full_in, p->ffttab, p->Rfull, 0, is_syn ? 1.0 : inv_nL);
+    add_fft_group(D->fft_full_out, p->ffttab, p->Rfull, 0, is_syn ? 1.0 : inv_nL);
+    std::vector<ASource> srcs;
+    for (int i = 0; i < S; ++i) srcs.push_back({&D->scales[i], &p->Rsc[i]});
+    build_a_items(D->a_multi, srcs, p->H, p->nld);
+    build_s_items(D->s_full, D->full, p->H, p->Rfull, p->nld);
+    build_a_items(D->a_full, {{&D->full, &p->Rfull}}, p->H, p->nld);
+    for (int i = 0; i < S; ++i) build_s_items(D->s_multi, D->scales[i], p->H, p->Rsc[i], p->nld);
+    for (Stage* s : {&D->a_multi, &D->s_full, &D->a_full, &D->s_multi}) PXM_TRY(s->upload());
+  }
+  PXM_TRY(p->ffttab.finalize(0));
+  for (WavDirection* D : {&p->syn, &p->ana})
+    for (FftStage* f : {&D->fft_scales_in, &D->fft_scales_out, &D->fft_full_in, &D->fft_full_out})
+      PXM_TRY(f->d_groups.upload(f->groups));
+  *out = p.release();
+  return PXM_OK;
+}
+
+int pxm_wav_plan_destroy(pxm_wav_plan* p) {
+  if (!p) return PXM_OK;
+  for (WavDirection* D : {&p->syn, &p->ana}) {
+    for (Stage* s : {&D->a_multi, &D->s_full, &D->a_full, &D->s_multi}) s->release();
+    for (FftStage* f : {&D->fft_scales_in, &D->fft_scales_out, &D->fft_full_in, &D->fft_full_out}) f->release();
+    D->d_g.release();
+  }
+  p->ffttab.release();
+  if (p->d_tab) cudaFree(p->d_tab);
+  if (p->d_ws) cudaFree(p->d_ws);
+  delete p;
+  return PXM_OK;
+}
+
+int pxm_wav_plan_info(const pxm_wav_plan* p, int* nscales_total, long long* ncoefs, long long* nscal, int* J_max,
+                      long long* table_bytes) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  if (nscales_total) *nscales_total = p->nscales_total;
+  if (ncoefs) *ncoefs = (long long)p->ncoefs;
+  if (nscal) *nscal = (long long)p->nscal;
+  if (J_max) *J_max = p->til.J;
+  if (table_bytes) *table_bytes = (long long)p->tab_doubles * 8;
+  return PXM_OK;
+}
+
+int pxm_wav_plan_bandlimits(const pxm_wav_plan* p, int* out, int cap) {
+  PXM_REQUIRE(p != nullptr && cap >= p->nscales_total, "bandlimits: buffer too small");
+  for (int i = 0; i < p->nscales_total; ++i) out[i] = p->til.bandlimits[i];
+  return PXM_OK;
+}
+
+// host-only: harmonic kernels kappa0 / kappa_j (what pys2let.wavelet_tiling exposes)
+int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out) {
+  PXM_REQUIRE(L >= 1 && B > 1.0 && J_min >= 0, "tiling arguments");
+  Tiling t = make_tiling(L, B, J_min);
+  if (J_out) *J_out = t.J;
+  for (int l = 0; l < L; ++l) kappa0[l] = t.kernels[0][l];
+  for (size_t j = 1; j < t.kernels.size(); ++j)
+    for (int l = 0; l < L; ++l) kappa[(j - 1) * L + l] = t.kernels[j][l];
+  return PXM_OK;
+}
+
+// which: 0 synthesis (coef->pix), 1 synthesis_adjoint (pix->coef), 2 analysis (pix->coef), 3 analysis_adjoint (coef->pix)
+static int wav_run(pxm_wav_plan* p, int which, void* d_coef, void* d_pix, int nb, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = (which < 2) ? p->syn : p->ana;
+  PXM_TRY(p->ensure(D));
+  const int naive = pxm_debug_naive();
+  const size_t npix = (size_t)p->L * (2 * p->L - 1);
+  const bool coef_to_pix = (which == 0 || which == 3);
+  if (coef_to_pix) {
+    PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
+                           d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                                (int)D.a_multi.items.size(), p->nld, st, naive));
+    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_full.d_items.d, D.s_full.d_segs.d,
+                                (int)D.s_full.items.size(), p->nld, st, naive));
+    PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
+                           d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+  } else {
+    PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
+                           npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_full.d_items.d, D.a_full.d_segs.d,
+                                (int)D.a_full.items.size(), p->nld, st, naive));
+    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+                                (int)D.s_multi.items.size(), p->nld, st, naive));
+    PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, (int)D.fft_scales_out.groups.size(),
+                           D.fft_scales_out.ctas, d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+  }
+  return PXM_OK;
+}
+
+int pxm_wav_synthesis(pxm_wav_plan* p, const void* d_coef, void* d_pix, int nbatch, void* stream) {
+  return wav_run(p, 0, const_cast<void*>(d_coef), d_pix, nbatch, stream);
+}
+int pxm_wav_synthesis_adjoint(pxm_wav_plan* p, const void* d_pix, void* d_coef, int nbatch, void* stream) {
+  return wav_run(p, 1, d_coef, const_cast<void*>(d_pix), nbatch, stream);
+}
+int pxm_wav_analysis(pxm_wav_plan* p, const void* d_pix, void* d_coef, int nbatch, void* stream) {
+  return wav_run(p, 2, d_coef, const_cast<void*>(d_pix), nbatch, stream);
+}
+int pxm_wav_analysis_adjoint(pxm_wav_plan* p, const void* d_coef, void* d_pix, int nbatch, void* stream) {
+  return wav_run(p, 3, const_cast<void*>(d_coef), d_pix, nbatch, stream);
+}
+
+// =========================================================================
+//                 elementwise / reductions / sparse entry points
+// =========================================================================
+int pxm_soft(int is_complex, const void* d_x, const double* d_T, double T_scalar, void* d_out, long long n,
+             long long nchains, void* stream) {
+  return pxm_launch_soft(is_complex, d_x, d_T, T_scalar, d_out, (size_t)n, (size_t)nchains, (cudaStream_t)stream);
+}
+
+int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                     const double* d_w_re, const double* d_w_im, void* d_Xout, void* d_prox_out, long long n,
+                     long long nchains, double delta, double lmda, int noise_mode, unsigned long long seed,
+                     unsigned long long step, unsigned int stream0, void* stream) {
+  return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, d_w_re, d_w_im, d_Xout, d_prox_out, (size_t)n,
+                          (size_t)nchains, delta, lmda, noise_mode, seed, step, stream0, (cudaStream_t)stream);
+}
+
+int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,
+                     long long nchains, void* stream) {
+  return pxm_launch_resid(d_preds, d_data, d_invcov, d_out, (size_t)n, (size_t)nchains, (cudaStream_t)stream);
+}
+
+int pxm_reduce_scratch_elems(void) { return 148; }
+
+int pxm_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w, double delta,
+               double lmda, long long n, long long nchains, void* d_partial, void* d_out, void* stream) {
+  PXM_REQUIRE(kind >= 0 && kind <= 2, "reduce kind");
+  return pxm_launch_reduce(kind, a, b, c, d, w, delta, lmda, (size_t)n, (size_t)nchains, d_partial, d_out,
+                           (cudaStream_t)stream);
+}
+
+int pxm_lincomb(int nx, const void* const* d_xs, const double* coefs, const double* d_z, double cz, double c0,
+                void* d_out, long long total, void* stream) {
+  PXM_REQUIRE(nx >= 0 && nx <= 4, "lincomb supports up to 4 terms");
+  return pxm_launch_lincomb(nx, d_xs, coefs, d_z, cz, c0, d_out, (size_t)total, (cudaStream_t)stream);
+}
+
+int pxm_gradlogpi(const void* d_X, const void* d_prox, const double* d_T, double T_scalar, const void* d_gradg,
+                  double lmda, void* d_out, long long n, long long nchains, void* stream) {
+  return pxm_launch_gradlogpi(d_X, d_prox, d_T, T_scalar, d_gradg, lmda, d_out, (size_t)n, (size_t)nchains,
+                              (cudaStream_t)stream);
+}
+
+int pxm_masked_gather(const void* d_full, const int* d_idx, const double* d_w, void* d_sel, long long nsel,
+                      long long nfull, long long nchains, void* stream) {
+  return pxm_launch_gather(0, d_full, d_idx, d_w, d_sel, (size_t)nsel, (size_t)nfull, (size_t)nchains,
+                           (cudaStream_t)stream);
+}
+int pxm_masked_scatter(const void* d_sel, const int* d_idx, const double* d_w, void* d_full, long long nsel,
+                       long long nfull, long long nchains, void* stream) {
+  return pxm_launch_gather(1, d_sel, d_idx, d_w, d_full, (size_t)nsel, (size_t)nfull, (size_t)nchains,
+                           (cudaStream_t)stream);
+}
+
+int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* stream) {
+  return pxm_launch_r2c(d_x, d_out, (size_t)total, (cudaStream_t)stream);
+}
+
+int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
+                 int nrows, long long ncols, long long nchains, void* stream) {
+  return pxm_launch_csr_spmv(d_indptr, d_indices, d_vals, d_x, d_y, nrows, (size_t)ncols, (size_t)nchains,
+                             (cudaStream_t)stream);
+}
+
+}  // extern "C"

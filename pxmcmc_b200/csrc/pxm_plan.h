@@ -1,0 +1,83 @@
+// Host-side plan structures shared by the table generator and the plans.
+#pragma once
+#include <vector>
+
+#include "pxm_common.cuh"
+
+struct PxmWigSlot {
+  int m;
+  int lb0;
+  int nlb;
+  int pad;
+  unsigned long long tile_off;
+};
+
+template <class T>
+struct PxmDevVec {
+  T* d = nullptr;
+  size_t n = 0;
+  int upload(const std::vector<T>& h) {
+    release();
+    n = h.size();
+    if (n == 0) return PXM_OK;
+    PXM_CUDA(cudaMalloc(&d, n * sizeof(T)));
+    PXM_CUDA(cudaMemcpy(d, h.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+    return PXM_OK;
+  }
+  void release() {
+    if (d) cudaFree(d);
+    d = nullptr;
+    n = 0;
+  }
+};
+
+// One set of per-m Legendre tables (see pxm_tables.cu)
+struct PxmTableLayout {
+  int grid_L = 0, rings = 0, lmax = 0, spin = 0;
+  bool paired = true;
+  int l_lo = 0, l_hi = 0;
+  int nslots = 0, ntb = 0;
+  std::vector<int> slot_m, lb0, nlb;
+  std::vector<unsigned long long> tile_off;  // doubles, relative to the arena the layout was made for
+  size_t doubles = 0;
+};
+
+void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, int spin, int l_lo, int l_hi,
+                           unsigned long long base_off);
+int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
+int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
+
+// kernels' launchers -------------------------------------------------------------
+int pxm_legendre_pad_columns(int ncols);
+int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
+                        const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive);
+int pxm_fft_choose_M(int n, int* logM);
+int pxm_fft_rings_per_cta(int M);
+int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
+                         cudaStream_t stream);
+int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, int ngroups, int ctas_per_chain, void* pix,
+                   size_t pix_chain_stride, double* F, int nld, const void* d_arena, int nchains, cudaStream_t stream);
+
+int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, void* out, size_t n, size_t nchains,
+                    cudaStream_t st);
+int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
+                     const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
+                     double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
+                     unsigned int stream0, cudaStream_t st);
+int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* out, size_t n, size_t nchains,
+                     cudaStream_t st);
+int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
+                      double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st);
+int pxm_launch_lincomb(int nx, const void* const* xs, const double* as, const double* z, double cz, double c0,
+                       void* out, size_t total, cudaStream_t st);
+int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, double Ts, const void* gradg, double lmda,
+                         void* out, size_t n, size_t nchains, cudaStream_t st);
+int pxm_launch_gather(int scatter, const void* in, const int* idx, const double* w, void* out, size_t nsel,
+                      size_t nfull, size_t nchains, cudaStream_t st);
+int pxm_launch_lm_convert(int to_internal, void* flm, double* H, const unsigned long long* d_slot_off,
+                          const double* d_gl, int L, int paired, int nld, int nchains, cudaStream_t st);
+int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st);
+int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* vals, const void* x, void* y, int nrows,
+                        size_t ncols, size_t nchains, cudaStream_t st);
+
+int pxm_debug_naive();

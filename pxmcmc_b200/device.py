@@ -1,0 +1,265 @@
+"""Device plumbing: torch tensors own the HBM, the C ABI does the arithmetic.
+
+PyTorch is used only for allocation, host<->device copies and the current
+stream; every operation on the sampler's hot path is a kernel of
+libpxmcmc_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+CDT = torch.complex128
+FDT = torch.float64
+
+
+def dev():
+    _lib.ensure_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def is_dev(x):
+    return isinstance(x, torch.Tensor)
+
+
+def to_dev_c(x):
+    """anything array-like (real or complex) -> contiguous complex128 CUDA tensor"""
+    if is_dev(x):
+        t = x
+        if t.dtype != CDT:
+            if t.is_complex():
+                t = t.to(CDT)
+            else:
+                out = torch.empty(t.shape, dtype=CDT, device=t.device)
+                tt = t.to(FDT).contiguous()
+                check(lib.pxm_real_to_complex(ptr(tt), ptr(out), tt.numel(), stream_ptr()))
+                return out
+        return t.contiguous()
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.complex128)
+    return torch.from_numpy(a).to(dev())
+
+
+def to_dev_f(x):
+    if is_dev(x):
+        return x.to(FDT).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float64)).to(dev())
+
+
+def to_host(t):
+    return t.detach().cpu().numpy()
+
+
+def like_input(result, template):
+    """numpy in -> numpy out; device tensor in -> device tensor out"""
+    return result if is_dev(template) else to_host(result)
+
+
+def batch2d(t):
+    """view a [n] or [nb, n] tensor as ([nb, n], was_1d)"""
+    if t.dim() == 1:
+        return t.unsqueeze(0), True
+    if t.dim() == 2:
+        return t, False
+    raise ValueError("expected a 1-D vector or a [nchains, n] batch")
+
+
+# ---------------------------------------------------------------------------
+# plans
+# ---------------------------------------------------------------------------
+class WaveletPlan:
+    """pxm_wav_plan: all four wavelet operators for one (L, B, J_min, nbatch)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, L, B, J_min, nbatch):
+        key = (int(L), float(B), int(J_min), int(nbatch), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        if key not in cls._cache:
+            cls._cache[key] = cls(L, B, J_min, nbatch)
+        return cls._cache[key]
+
+    def __init__(self, L, B, J_min, nbatch):
+        dev()
+        self.L, self.B, self.J_min, self.nbatch = int(L), float(B), int(J_min), int(nbatch)
+        h = C.c_void_p()
+        check(lib.pxm_wav_plan_create(self.L, self.B, self.J_min, self.nbatch, C.byref(h)))
+        self.h = h
+        ns, nc, nsc, J, tb = C.c_int(), C.c_longlong(), C.c_longlong(), C.c_int(), C.c_longlong()
+        check(lib.pxm_wav_plan_info(h, C.byref(ns), C.byref(nc), C.byref(nsc), C.byref(J), C.byref(tb)))
+        self.nscales_total, self.ncoefs, self.nscal, self.J_max, self.table_bytes = ns.value, nc.value, nsc.value, J.value, tb.value
+        bl = (C.c_int * ns.value)()
+        check(lib.pxm_wav_plan_bandlimits(h, bl, ns.value))
+        self.bandlimits = list(bl)
+        self.npix = self.L * (2 * self.L - 1)
+
+    def _run(self, fn, x, n_in, n_out, in_first):
+        x2, was1 = batch2d(x)
+        nb = x2.shape[0]
+        if x2.shape[1] != n_in:
+            raise ValueError(f"expected vectors of length {n_in}, got {x2.shape[1]}")
+        if nb > self.nbatch:
+            raise ValueError("batch larger than the plan's")
+        out = torch.empty((nb, n_out), dtype=CDT, device=x2.device)
+        check(fn(self.h, ptr(x2), ptr(out), nb, stream_ptr()))
+        return out[0] if was1 else out
+
+    def synthesis(self, coef):
+        return self._run(lib.pxm_wav_synthesis, coef, self.ncoefs, self.npix, True)
+
+    def synthesis_adjoint(self, pix):
+        return self._run(lib.pxm_wav_synthesis_adjoint, pix, self.npix, self.ncoefs, True)
+
+    def analysis(self, pix):
+        return self._run(lib.pxm_wav_analysis, pix, self.npix, self.ncoefs, True)
+
+    def analysis_adjoint(self, coef):
+        return self._run(lib.pxm_wav_analysis_adjoint, coef, self.ncoefs, self.npix, True)
+
+
+class ShtPlan:
+    """pxm_sht_plan: the four pyssht-level transforms for one (L, spin, nbatch)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, L, spin, nbatch=1):
+        key = (int(L), int(spin), int(nbatch), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        if key not in cls._cache:
+            cls._cache[key] = cls(L, spin, nbatch)
+        return cls._cache[key]
+
+    def __init__(self, L, spin, nbatch=1):
+        dev()
+        self.L, self.spin, self.nbatch = int(L), int(spin), int(nbatch)
+        h = C.c_void_p()
+        check(lib.pxm_sht_plan_create(self.L, self.spin, self.nbatch, C.byref(h)))
+        self.h = h
+        self.npix = self.L * (2 * self.L - 1)
+        self.nlm = self.L * self.L
+
+    def _run(self, fn, x, n_in, n_out, gl):
+        x2, was1 = batch2d(x)
+        nb = x2.shape[0]
+        if x2.shape[1] != n_in:
+            raise ValueError(f"expected vectors of length {n_in}, got {x2.shape[1]}")
+        out = torch.empty((nb, n_out), dtype=CDT, device=x2.device)
+        check(fn(self.h, ptr(x2), ptr(out), nb, ptr(gl), stream_ptr()))
+        return out[0] if was1 else out
+
+    # argument order of the C ABI is (in, out) for every call
+    def inverse(self, flm, gl=None):
+        return self._run(lib.pxm_sht_inverse, flm, self.nlm, self.npix, gl)
+
+    def forward(self, f, gl=None):
+        return self._run(lib.pxm_sht_forward, f, self.npix, self.nlm, gl)
+
+    def inverse_adjoint(self, f, gl=None):
+        return self._run(lib.pxm_sht_inverse_adjoint, f, self.npix, self.nlm, gl)
+
+    def forward_adjoint(self, flm, gl=None):
+        return self._run(lib.pxm_sht_forward_adjoint, flm, self.nlm, self.npix, gl)
+
+
+# ---------------------------------------------------------------------------
+# elementwise wrappers (device tensors in / out)
+# ---------------------------------------------------------------------------
+def _T_args(T):
+    """threshold as (device vector or None, scalar)"""
+    if is_dev(T):
+        return T, 0.0
+    if np.ndim(T) == 0:
+        return None, float(T)
+    return to_dev_f(T), 0.0
+
+
+def soft_dev(x, Tvec, Tscalar):
+    x2, was1 = batch2d(x)
+    out = torch.empty_like(x2)
+    n = x2.shape[1]
+    if Tvec is not None and Tvec.numel() != n:
+        raise ValueError("threshold vector has the wrong length")
+    check(lib.pxm_soft(1 if x2.is_complex() else 0, ptr(x2), ptr(Tvec), Tscalar, ptr(out), n, x2.shape[0], stream_ptr()))
+    return out[0] if was1 else out
+
+
+def myula_update_dev(X, prox, gradg, Tvec, Tscalar, delta, lmda, w_re=None, w_im=None, noise_mode=0, seed=0, step=0,
+                     stream0=0, want_prox=False):
+    X2, was1 = batch2d(X)
+    nb, n = X2.shape
+    out = torch.empty_like(X2)
+    pout = torch.empty_like(X2) if want_prox else None
+    check(lib.pxm_myula_update(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(w_re), ptr(w_im), ptr(out),
+                               ptr(pout), n, nb, float(delta), float(lmda), int(noise_mode), int(seed), int(step),
+                               int(stream0), stream_ptr()))
+    if was1:
+        out = out[0]
+        pout = pout[0] if pout is not None else None
+    return (out, pout) if want_prox else out
+
+
+def gradlogpi_dev(X, prox, Tvec, Tscalar, gradg, lmda):
+    X2, was1 = batch2d(X)
+    out = torch.empty_like(X2)
+    check(lib.pxm_gradlogpi(ptr(X2), ptr(prox), ptr(Tvec), Tscalar, ptr(gradg), float(lmda), ptr(out), X2.shape[1],
+                            X2.shape[0], stream_ptr()))
+    return out[0] if was1 else out
+
+
+def resid_dev(preds, data, invcov):
+    p2, was1 = batch2d(preds)
+    out = torch.empty_like(p2)
+    check(lib.pxm_resid_invcov(ptr(p2), ptr(data), ptr(invcov), ptr(out), p2.shape[1], p2.shape[0], stream_ptr()))
+    return out[0] if was1 else out
+
+
+_scratch = {}
+
+
+def reduce_dev(kind, a, b=None, c=None, d=None, w=None, delta=0.0, lmda=1.0):
+    """per-chain complex reductions; returns a [nchains] complex128 device tensor"""
+    a2, _ = batch2d(a)
+    nb, n = a2.shape
+    key = (nb, a2.device)
+    if key not in _scratch:
+        _scratch[key] = torch.empty(nb * lib.pxm_reduce_scratch_elems(), dtype=CDT, device=a2.device)
+    out = torch.empty(nb, dtype=CDT, device=a2.device)
+    check(lib.pxm_reduce(kind, ptr(a2), ptr(b), ptr(c), ptr(d), ptr(w), float(delta), float(lmda), n, nb,
+                         ptr(_scratch[key]), ptr(out), stream_ptr()))
+    return out
+
+
+def lincomb_dev(terms, z=None, cz=0.0, c0=0.0):
+    """sum_k coef_k * x_k (+ cz*z real, + c0 real), complex128 device tensors of equal shape"""
+    xs = [t for _, t in terms]
+    n = len(xs)
+    arr = (C.c_void_p * 4)(*([x.data_ptr() for x in xs] + [0] * (4 - n)))
+    cf = (C.c_double * 4)(*([float(c) for c, _ in terms] + [0.0] * (4 - n)))
+    out = torch.empty_like(xs[0])
+    check(lib.pxm_lincomb(n, arr, cf, ptr(z), float(cz), float(c0), ptr(out), out.numel(), stream_ptr()))
+    return out
+
+
+def gather_dev(full, idx, w, nsel):
+    f2, was1 = batch2d(full)
+    out = torch.empty((f2.shape[0], nsel), dtype=CDT, device=f2.device)
+    check(lib.pxm_masked_gather(ptr(f2), ptr(idx), ptr(w), ptr(out), nsel, f2.shape[1], f2.shape[0], stream_ptr()))
+    return out[0] if was1 else out
+
+
+def scatter_dev(sel, idx, w, nfull):
+    s2, was1 = batch2d(sel)
+    out = torch.empty((s2.shape[0], nfull), dtype=CDT, device=s2.device)
+    check(lib.pxm_masked_scatter(ptr(s2), ptr(idx), ptr(w), ptr(out), s2.shape[1], nfull, s2.shape[0], stream_ptr()))
+    return out[0] if was1 else out
+
+
+def csr_spmv_dev(indptr, indices, vals, x, nrows, ncols):
+    x2, was1 = batch2d(x)
+    if x2.shape[1] != ncols:
+        raise ValueError("vector length does not match the matrix")
+    out = torch.empty((x2.shape[0], nrows), dtype=CDT, device=x2.device)
+    check(lib.pxm_csr_spmv(ptr(indptr), ptr(indices), ptr(vals), ptr(x2), ptr(out), nrows, ncols, x2.shape[0], stream_ptr()))
+    return out[0] if was1 else out

@@ -1,0 +1,426 @@
+"""Samplers mirroring ``pxmcmc/mcmc.py`` of the reference: ``PxMCMCParams``,
+``MYULA``, ``PxMALA``, ``SKROCK`` with the same constructor arguments, ``run``,
+``chain_step``, ``logpi``, tracked arrays and traces.
+
+The chain state lives in HBM for the whole run; each iteration is a fixed
+sequence of libpxmcmc_b200 kernels.  Two extra keyword-only knobs:
+
+* ``noise="host"`` (default) draws the Gaussian / Laplace / uniform variates from
+  numpy's global RNG in exactly the reference's call order, so a seeded run
+  reproduces the reference chain (parity mode).  ``noise="device"`` generates
+  Philox4x32-10 Gaussians inside the update kernel (throughput mode).
+* ``nchains`` runs that many independent chains as one batch (tracked arrays gain
+  a leading chain axis when ``nchains > 1``).
+"""
+import numpy as np
+import torch
+from scipy.stats import laplace
+
+from . import device as D
+from .prior import L1
+from .utils import cheb1der, chebyshev1
+
+
+class PxMCMCParams:
+    """Tuning and runtime parameters (pxmcmc/mcmc.py:6-43)."""
+
+    def __init__(
+        self,
+        lmda=3e-5,
+        delta=1e-5,
+        s=1,
+        mu=1,
+        nsamples=int(1e6),
+        nburn=int(1e3),
+        ngap=int(1e2),
+        complex=False,
+        verbosity=100,
+        track=["logposterior", "L2", "prior", "chain"],
+    ):
+        self.lmda = lmda
+        self.delta = delta
+        self.mu = mu
+        self.s = s
+        self.nsamples = nsamples
+        self.nburn = nburn
+        self.ngap = ngap
+        self.complex = complex
+        self.verbosity = verbosity
+        self.track = track
+
+
+def _cplx_lt(a, b):
+    """numpy's ordering of complex scalars (real part first, then imaginary),
+    which is what `np.log(u) < logalpha` uses when logalpha is complex
+    (pxmcmc/mcmc.py:245)."""
+    a, b = complex(a), complex(b)
+    return (a.real < b.real) or (a.real == b.real and a.imag < b.imag)
+
+
+class PxMCMC:
+    """Common machinery (pxmcmc/mcmc.py:46-140)."""
+
+    def __init__(self, forward, prior, mcmcparams=PxMCMCParams(), *, noise="host", nchains=1, seed=0):
+        self.forward = forward
+        self.prior = prior
+        for attr in mcmcparams.__dict__.keys():
+            setattr(self, attr, getattr(mcmcparams, attr))
+        if noise not in ("host", "device"):
+            raise ValueError("noise must be 'host' or 'device'")
+        self.noise = noise
+        self.nchains = int(nchains)
+        self.seed = int(seed)
+        self._step_counter = 0
+        self._initialise_tracking_arrays()
+
+    # ------------------------------------------------------------------ helpers
+    def _native(self):
+        return bool(getattr(self.forward, "_pxm_native", False)) and isinstance(self.prior, L1)
+
+    def _fused_prox(self):
+        """(Tvec, Tscalar) when the prox is a plain soft threshold that the update
+        kernel can fuse, else None"""
+        if isinstance(self.prior, L1) and self.prior.setting == "synthesis":
+            return self.prior._T_args()
+        return None
+
+    def _state(self, X):
+        """[nchains, nparams] complex device tensor from a numpy vector / tensor"""
+        x = D.to_dev_c(X)
+        return x.unsqueeze(0) if x.dim() == 1 else x
+
+    def _prior_dev(self, Xd):
+        if isinstance(self.prior, L1):
+            return D.reduce_dev(0, Xd, w=self.prior._weights_dev()).real
+        vals = [self.prior.prior(D.to_host(Xd[c])) for c in range(Xd.shape[0])]
+        return torch.as_tensor(np.real(vals), device=Xd.device)
+
+    def _proxf_dev(self, Xd):
+        if getattr(self.prior, "_pxm_native", False):
+            return D.to_dev_c(self.prior.proxf(Xd))
+        return torch.stack([D.to_dev_c(self.prior.proxf(D.to_host(Xd[c]))) for c in range(Xd.shape[0])])
+
+    def _forward_dev(self, Xd):
+        if getattr(self.forward, "_pxm_native", False):
+            return self.forward.forward(Xd)
+        return torch.stack([D.to_dev_c(self.forward.forward(D.to_host(Xd[c]))) for c in range(Xd.shape[0])])
+
+    def _gradg_dev(self, Pd):
+        if getattr(self.forward, "_pxm_native", False):
+            return self.forward.calc_gradg(Pd)
+        return torch.stack([D.to_dev_c(self.forward.calc_gradg(D.to_host(Pd[c]))) for c in range(Pd.shape[0])])
+
+    def _logpi_dev(self, Xd, Pd):
+        """per-chain (logPi, L2, prior) as host numpy arrays (complex, complex, real)"""
+        if getattr(self.forward, "_diag", None) is not None:
+            data_d, ic_d = self.forward._upload()
+            L2 = D.to_host(D.reduce_dev(1, Pd, b=data_d, c=ic_d))
+        else:
+            L2 = np.array([self._host_L2(D.to_host(Pd[c])) for c in range(Pd.shape[0])])
+        pr = D.to_host(self._prior_dev(Xd))
+        return -self.mu * pr - L2, L2, pr
+
+    def _host_L2(self, preds):
+        diff = np.asarray(self.forward.data) - preds
+        return np.vdot(diff, self.forward.invcov @ diff)
+
+    # ------------------------------------------------------------------ reference API
+    def run(self, start_point=None):
+        raise NotImplementedError
+
+    def logpi(self, X, preds):
+        """log posterior, L2 misfit and prior of a model (pxmcmc/mcmc.py:71-82):
+        L2 = vdot(d, invcov d) with d = data - preds, logPi = -mu*prior - L2."""
+        lp, l2, pr = self._logpi_dev(self._state(X), self._state(preds))
+        return lp[0], l2[0], pr[0]
+
+    def _gradlogpi_dev(self, Xd, Pd=None):
+        if Pd is None:
+            Pd = self._forward_dev(Xd)
+        gradg = D.to_dev_c(self._gradg_dev(Pd))
+        fused = self._fused_prox()
+        if fused is not None:
+            return D.gradlogpi_dev(Xd, None, fused[0], fused[1], gradg, self.lmda)
+        return D.gradlogpi_dev(Xd, self._proxf_dev(Xd), None, 0.0, gradg, self.lmda)
+
+    def _gradlogpi(self, X, preds=None):
+        """-(X - prox(X))/lmda - gradg(forward(X)) (pxmcmc/mcmc.py:84-89)"""
+        out = self._gradlogpi_dev(self._state(X), None if preds is None else self._state(preds))
+        return out if D.is_dev(X) else D.to_host(out[0])
+
+    def _print_progress(self, i, logpi, **kwargs):
+        print(
+            f"{i+1:,}/{self.nsamples:,} - logposterior: {logpi:.8e} - "
+            + " - ".join([f"{k}: {kwargs[k]:.8e}" for k in kwargs]),
+        )
+
+    def _initial_sample(self, initial_sample=None):
+        """Laplace draw (or the user's 1-D start point), and its predictions
+        (pxmcmc/mcmc.py:97-111).  Returns device tensors [nchains, .]."""
+        n = self.forward.nparams
+        if initial_sample is None:
+            X = laplace.rvs(size=n * self.nchains)
+            if self.complex:
+                X = X + laplace.rvs(size=n * self.nchains) * 1j
+            X = X.reshape(self.nchains, n)
+        else:
+            if D.is_dev(initial_sample):
+                X = initial_sample
+                if X.shape[-1] != n:
+                    raise ValueError("Inital sample given has incorrect size")
+            else:
+                if not isinstance(initial_sample, np.ndarray) or np.ndim(initial_sample) not in (1, 2):
+                    raise TypeError("Expected a 1D numpy array as an initial sample")
+                if np.ndim(initial_sample) == 2 and self.nchains == 1:
+                    raise TypeError("Expected a 1D numpy array as an initial sample")
+                if initial_sample.shape[-1] != n:
+                    raise ValueError("Inital sample given has incorrect size")
+                X = initial_sample
+                if np.ndim(X) == 1 and self.nchains > 1:
+                    X = np.tile(X, (self.nchains, 1))
+        Xd = self._state(X)
+        return Xd, D.to_dev_c(self._forward_dev(Xd))
+
+    def _initialise_tracking_arrays(self):
+        """pxmcmc/mcmc.py:113-128 (leading chain axis only when nchains > 1)"""
+        lead = (self.nchains,) if self.nchains > 1 else ()
+        if "logposterior" in self.track:
+            self.logPi = np.zeros(lead + (self.nsamples,))
+        if "predictions" in self.track:
+            self.preds = np.zeros(lead + (self.nsamples, len(self.forward.data)), dtype=float)
+        if "chain" in self.track:
+            self.chain = np.zeros(lead + (self.nsamples, self.forward.nparams), dtype=complex if self.complex else float)
+        if "L2" in self.track:
+            self.L2s = np.zeros(lead + (self.nsamples,), dtype=float)
+        if "prior" in self.track:
+            self.priors = np.zeros(lead + (self.nsamples,), dtype=float)
+
+    def _tracking(self, j, X_curr, curr_preds, logPi, L2, prior):
+        """store sample j; complex values are truncated to their real part exactly
+        as numpy does when the reference assigns them into float arrays
+        (pxmcmc/mcmc.py:130-140)"""
+        def put(arr, val):
+            val = np.asarray(val)
+            if not np.iscomplexobj(arr):
+                val = val.real
+            if self.nchains > 1:
+                arr[:, j] = val
+            else:
+                arr[j] = val[0] if val.ndim and val.shape[0] == 1 else val
+
+        if hasattr(self, "logPi"):
+            put(self.logPi, logPi)
+        if hasattr(self, "L2s"):
+            put(self.L2s, L2)
+        if hasattr(self, "priors"):
+            put(self.priors, prior)
+        if hasattr(self, "preds"):
+            put(self.preds, D.to_host(curr_preds) if D.is_dev(curr_preds) else curr_preds)
+        if hasattr(self, "chain"):
+            put(self.chain, D.to_host(X_curr) if D.is_dev(X_curr) else X_curr)
+
+    def _on_grid(self, i):
+        return i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
+
+    def _host_noise(self, n):
+        """Gaussian draw(s) in the reference's order: real part, then imaginary if `complex`"""
+        w_re = D.to_dev_f(np.random.randn(n * self.nchains))
+        w_im = D.to_dev_f(np.random.randn(n * self.nchains)) if self.complex else None
+        return w_re, w_im
+
+
+class MYULA(PxMCMC):
+    """Moreau-Yosida unadjusted Langevin algorithm (pxmcmc/mcmc.py:143-201)."""
+
+    def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), **kw):
+        super().__init__(forward, prox, mcmcparams, **kw)
+
+    def _propose_dev(self, Xd, proxd, gradgd):
+        """X' = (1-d/l) X + (d/l) prox - d gradg + sqrt(2d) w, one fused kernel;
+        proxd None -> the soft threshold is evaluated inside the kernel"""
+        n = self.forward.nparams
+        if proxd is None:
+            Tv, Ts = self._fused_prox()
+        else:
+            Tv, Ts = None, 0.0
+        if self.noise == "host":
+            w_re, w_im = self._host_noise(n)
+            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im, noise_mode=1)
+        else:
+            self._step_counter += 1
+            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
+                                     noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter)
+        return out
+
+    def run(self, start_point=None):
+        """the loop of pxmcmc/mcmc.py:150-183"""
+        i = 0
+        j = 0
+        X_curr, curr_preds = self._initial_sample(start_point)
+        fused = self._fused_prox() is not None
+        while j < self.nsamples:
+            gradg = D.to_dev_c(self._gradg_dev(curr_preds))
+            proxf = None if fused else self._proxf_dev(X_curr)
+            X_curr = self._propose_dev(X_curr, proxf, gradg)
+            curr_preds = D.to_dev_c(self._forward_dev(X_curr))
+            if i >= self.nburn:
+                if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
+                    logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
+                    self._tracking(j, X_curr, curr_preds, logPi, L2, prior)
+                    j += 1
+                if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                    self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
+                                         prior=np.ravel(self.priors)[j - 1])
+            else:
+                if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                    print("Burning in...")
+            i += 1
+        self._final_state = (X_curr, curr_preds)
+        print("\nDONE")
+
+    def chain_step(self, X, proxf, gradg):
+        """One proposal from (X, prox(X), gradg) (pxmcmc/mcmc.py:185-201)."""
+        out = self._propose_dev(self._state(X), self._state(proxf), self._state(gradg))
+        return out if D.is_dev(X) else D.to_host(out[0] if np.ndim(X) == 1 else out)
+
+
+class PxMALA(MYULA):
+    """MYULA + Metropolis-Hastings correction, optional step-size tuning
+    (pxmcmc/mcmc.py:204-289).  The accept decision uses numpy's global RNG after the
+    Gaussian draw, as in the reference."""
+
+    def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), tune_delta=True, **kw):
+        super().__init__(forward, prox, mcmcparams, **kw)
+        if self.nchains != 1:
+            raise NotImplementedError("PxMALA runs one chain per sampler object")
+        self.tune_delta = tune_delta
+
+    def _logtrans_dev(self, X1, X2, proxf, gradg):
+        s = complex(D.to_host(D.reduce_dev(2, X1, b=X2, c=proxf, d=gradg, delta=self.delta, lmda=self.lmda))[0])
+        return -(1 / 2 * self.delta) * s ** 2
+
+    def calc_logtransition(self, X1, X2, proxf, gradg):
+        """log q(X2|X1) exactly as the reference codes it (pxmcmc/mcmc.py:281-289)"""
+        val = self._logtrans_dev(self._state(X1), self._state(X2), self._state(proxf), self._state(gradg))
+        return val if np.iscomplexobj(X1) or np.iscomplexobj(X2) or np.iscomplexobj(proxf) or np.iscomplexobj(gradg) or D.is_dev(X1) else val.real
+
+    def run(self, start_point=None):
+        """the loop of pxmcmc/mcmc.py:218-275"""
+        self.acceptance_trace = []
+        self.deltas_trace = [self.delta]
+        i = 0
+        j = 0
+        X_curr, curr_preds = self._initial_sample(start_point)
+        gradg_curr = D.to_dev_c(self._gradg_dev(curr_preds))
+        proxf_curr = self._proxf_dev(X_curr)
+        lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
+        logpiXc, L2Xc, priorXc = lp[0], l2[0], pr[0]
+        while j < self.nsamples:
+            X_prop = self._propose_dev(X_curr, proxf_curr, gradg_curr)
+            prop_preds = D.to_dev_c(self._forward_dev(X_prop))
+            gradg_prop = D.to_dev_c(self._gradg_dev(prop_preds))
+            proxf_prop = self._proxf_dev(X_prop)
+            logtransXcXp = self._logtrans_dev(X_curr, X_prop, proxf_curr, gradg_curr)
+            logtransXpXc = self._logtrans_dev(X_prop, X_curr, proxf_prop, gradg_prop)
+            lp, l2, pr = self._logpi_dev(X_prop, prop_preds)
+            logpiXp, L2Xp, priorXp = lp[0], l2[0], pr[0]
+            logalpha = logtransXpXc + logpiXp - logtransXcXp - logpiXc
+            accept = _cplx_lt(np.log(np.random.rand()), logalpha)
+            if accept:
+                X_curr, curr_preds, gradg_curr, proxf_curr = X_prop, prop_preds, gradg_prop, proxf_prop
+                logpiXc, L2Xc, priorXc = logpiXp, L2Xp, priorXp
+                self.acceptance_trace.append(1)
+            else:
+                self.acceptance_trace.append(0)
+            if self.tune_delta:
+                self._tune_delta(i)
+                self.deltas_trace.append(self.delta)
+            if i >= self.nburn:
+                if (self.ngap == 0 or (i - self.nburn) % self.ngap == 0) and accept:
+                    self._tracking(j, X_curr, curr_preds, [logpiXc], [L2Xc], [priorXc])
+                    j += 1
+            if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                self._print_progress(j - 1, np.real(logpiXc), L2=np.real(L2Xc), prior=priorXc,
+                                     acceptanceRate=np.mean(self.acceptance_trace))
+            i += 1
+        self._final_state = (X_curr, curr_preds)
+        print("\nDONE")
+
+    def _tune_delta(self, i):
+        """pxmcmc/mcmc.py:277-279"""
+        delta = self.delta * (1 + (self.acceptance_trace[i] - 0.5) / ((i + 1) ** 0.75))
+        self.delta = min(max(delta, self.lmda * 1e-8), self.lmda / 2)
+
+
+class SKROCK(PxMCMC):
+    """Stochastic orthogonal Runge-Kutta-Chebyshev sampler (pxmcmc/mcmc.py:292-383).
+    The reference evaluates K_s by naive recursion (4 059 gradient evaluations at
+    s=10); K_0..K_s are evaluated bottom-up here (s evaluations, identical values)."""
+
+    def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), **kw):
+        super().__init__(forward, prox, mcmcparams=mcmcparams, **kw)
+        self.eta = 0.05
+        self.omega_0 = 1 + self.eta / (self.s * self.s)
+        self.omega_1 = chebyshev1(self.omega_0, self.s) / cheb1der(self.omega_0, self.s)
+        self._recursion_coefs()
+
+    def run(self, start_point=None):
+        """the loop of pxmcmc/mcmc.py:308-336"""
+        i = 0
+        j = 0
+        X_curr, curr_preds = self._initial_sample(start_point)
+        while j < self.nsamples:
+            X_curr = self._chain_step_dev(X_curr)
+            curr_preds = D.to_dev_c(self._forward_dev(X_curr))
+            if i >= self.nburn:
+                if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
+                    logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
+                    self._tracking(j, X_curr, curr_preds, logPi, L2, prior)
+                    j += 1
+            if self.verbosity > 0 and (i + 1) % self.verbosity == 0 and j > 0:
+                self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
+                                     prior=np.ravel(self.priors)[j - 1])
+            i += 1
+        self._final_state = (X_curr, curr_preds)
+        print("\nDONE")
+
+    def _chain_step_dev(self, Xd, Z=None):
+        n = Xd.shape[-1]
+        if Z is None:
+            if self.complex:
+                raise NotImplementedError("complex SKROCK noise is not implemented on the device path")
+            Z = D.to_dev_f(np.random.randn(n * Xd.shape[0])).reshape(Xd.shape)
+        return self._K_recursion(Xd, self.s, Z)
+
+    def chain_step(self, X):
+        """one SKROCK step (pxmcmc/mcmc.py:338-347)"""
+        out = self._chain_step_dev(self._state(X))
+        return out if D.is_dev(X) else D.to_host(out[0])
+
+    def _K_recursion(self, Xd, s, Z):
+        """K_s of pxmcmc/mcmc.py:349-368, memoised"""
+        sq = np.sqrt(2 * self.delta)
+        K_prev2 = Xd
+        if s == 0:
+            return Xd
+        Y = D.lincomb_dev([(1.0, Xd)], z=Z, cz=self.nus[1] * sq)
+        K_prev = D.lincomb_dev([(1.0, Xd), (self.mus[1] * self.delta, self._gradlogpi_dev(Y))], z=Z, cz=self.ks[1] * sq)
+        for j in range(2, s + 1):
+            g = self._gradlogpi_dev(K_prev)
+            K = D.lincomb_dev([(self.mus[j] * self.delta, g), (self.nus[j], K_prev), (-1.0, K_prev2)], c0=self.ks[j])
+            K_prev2, K_prev = K_prev, K
+        return K_prev
+
+    def _recursion_coefs(self):
+        """coefficients exactly as the reference computes them (pxmcmc/mcmc.py:370-383)"""
+        self.mus = np.zeros(self.s + 1)
+        self.nus = np.zeros(self.s + 1)
+        self.ks = np.zeros(self.s + 1)
+        self.mus[1] = self.omega_1 / self.omega_0
+        self.nus[1] = self.s * self.omega_1 / 2
+        self.ks[1] = self.s * self.omega_1 / self.omega_0
+        for j in range(2, self.s + 1):
+            cheb_ratio = chebyshev1(self.omega_0, j - 1) / chebyshev1(self.omega_1, j)
+            self.mus[j] = 2 * self.omega_1 * cheb_ratio
+            self.nus[j] = 2 * self.omega_0 * cheb_ratio
+            self.ks[j] = 1 - self.nus[0]
