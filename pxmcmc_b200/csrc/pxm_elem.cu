@@ -15,11 +15,26 @@ typedef double2 cplx;
 // (/root/reference/pxmcmc/utils.py:55-67, _sign :84-88):
 //   sign(x) * (|x| - T), 0 where |x| <= T (inclusive), sign(z) = z/|z| (0 at 0)
 // ---------------------------------------------------------------------------
+// |z| exactly as numpy's vectorised complex abs computes it
+// (numpy/_core/src/umath/loops_unary_complex.dispatch.c.src, simd_cabs_f64):
+//   larger * sqrt(fma(r, r, 1)),  r = smaller/larger
+__device__ __forceinline__ double np_cabs(double re, double im) {
+  re = fabs(re);
+  im = fabs(im);
+  const double larger = fmax(re, im), smaller = fmin(im, re);
+  if (larger == 0.0 || isinf(larger)) return larger;
+  const double ratio = smaller / larger;
+  return sqrt(fma(ratio, ratio, 1.0)) * larger;
+}
+
 __device__ __forceinline__ cplx soft_c(cplx z, double T) {
-  const double a = hypot(z.x, z.y);
+  const double a = np_cabs(z.x, z.y);
   if (a <= T) return make_double2(0.0, 0.0);
   const double r = a - T;
-  return make_double2((z.x / a) * r, (z.y / a) * r);
+  // numpy evaluates z/|z| through its complex division loop, i.e. as a product
+  // with the reciprocal 1/|z| (loops.c.src, *_divide); replicate it bit for bit
+  const double scl = 1.0 / a;
+  return make_double2((z.x * scl) * r, (z.y * scl) * r);
 }
 __device__ __forceinline__ double soft_r(double x, double T) {
   const double a = fabs(x);
@@ -198,7 +213,7 @@ __global__ void k_reduce_stage1(ReduceArgs p) {
         x.x *= p.w[e];
         x.y *= p.w[e];
       }
-      acc.x += hypot(x.x, x.y);
+      acc.x += np_cabs(x.x, x.y);
     } else if (p.kind == 1) {
       const cplx pr = p.a[off + e], da = p.b[e], ic = p.c[e];
       const double dx = da.x - pr.x, dy = da.y - pr.y;
@@ -323,11 +338,12 @@ __global__ void k_lm_convert(LmArgs p) {
     const int m = ind - l * l - l;
     const int am = m < 0 ? -m : m;
     int slot, col;
-    double sg = 1.0;
+    // harmonic-side arrays hold the TRUE f_lm for both signs of m; the (-1)^m of
+    // Lambda^{-m} = (-1)^m Lambda^{m} lives on the ring side only (ring FFT kernel)
+    const double sg = 1.0;
     if (p.paired) {
       slot = am;
       col = chain * 4 + (m < 0 ? 2 : 0);
-      if (m < 0 && (am & 1)) sg = -1.0;
     } else {
       slot = m + p.L - 1;
       col = chain * 2;

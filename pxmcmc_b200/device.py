@@ -39,13 +39,18 @@ def to_dev_c(x):
                 return out
         return t.contiguous()
     a = np.ascontiguousarray(np.asarray(x), dtype=np.complex128)
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).to(dev())
 
 
 def to_dev_f(x):
     if is_dev(x):
         return x.to(FDT).contiguous()
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float64)).to(dev())
+    a = np.ascontiguousarray(np.asarray(x), dtype=np.float64)
+    if not a.flags.writeable:
+        a = a.copy()
+    return torch.from_numpy(a).to(dev())
 
 
 def to_host(t):

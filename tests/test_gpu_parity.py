@@ -1,0 +1,386 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+Every test drives the CUDA path through the public Python classes, i.e. through
+the C ABI of libpxmcmc_b200.so, and compares with
+  * the committed fixtures produced by the unmodified reference (tests/golden), and
+  * the CPU oracle (oracle/) on seeded inputs.
+Tolerance: 1e-10 relative L2 in FP64 (BASELINE.json north_star); the prox
+support / sign pattern and the real soft threshold must match exactly.
+"""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import golden, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pxmcmc_b200
+    from pxmcmc_b200 import forward, mcmc, measurements, prior, sht, transforms, utils
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.forward, ns.mcmc, ns.measurements, ns.prior, ns.sht, ns.transforms, ns.utils = (
+        forward, mcmc, measurements, prior, sht, transforms, utils)
+    return ns
+
+
+# ------------------------------------------------------------------ elementwise
+def test_soft_known_answers_bit_exact(px):
+    # reference tests/test_utils.py:35-44 (exact ==)
+    soft = px.utils.soft
+    assert all(soft([1, 2, 3], T=2) == [0, 0, 1])
+    assert all(soft([-1, -2, -3], T=2) == [0, 0, -1])
+    assert all(soft([1 + 1j, 0.5 - 0.5j, 0], T=1) == [(1 + 1j) * (np.sqrt(2) - 1) / np.sqrt(2), 0, 0])
+
+
+def test_soft_golden_bit_exact(px):
+    g = golden("ref_soft.npz")
+    soft = px.utils.soft
+    assert np.array_equal(soft(g["xr"], 0.8), g["soft_r_scalar"])
+    assert np.array_equal(soft(g["xr"], g["tv"]), g["soft_r_vec"])
+    assert np.array_equal(soft(g["xc"], 1.0), g["soft_c_scalar"])
+    assert np.array_equal(soft(g["xc"], g["tv"]), g["soft_c_vec"])
+
+
+def test_soft_edge_cases(px):
+    soft = px.utils.soft
+    assert soft(np.zeros(0), 1.0).size == 0                       # empty
+    x = np.array([0.0, -0.0, 1e-300, -1e300, 0.25, -0.25])
+    assert np.array_equal(soft(x, 0.25), [0, 0, 0, -1e300 + 0.25, 0, 0])  # |x| == T zeroed (inclusive)
+    big = np.random.default_rng(1).standard_normal(1 << 20)       # larger than one grid pass
+    from oracle import pxmcmc_ref as R
+    assert np.array_equal(soft(big, 0.5), R.soft(big, 0.5))
+
+
+def test_l1_prox_matches_soft(px):
+    # reference tests/test_proxes.py:17-21
+    X = np.arange(100)
+    for setting in ("synthesis",):
+        reg = px.prior.L1(setting, lambda v: v, lambda v: v, 50)
+        assert np.all(reg.proxf(X) == px.utils.soft(X, 50))
+    reg = px.prior.L1("analysis", lambda v: v, lambda v: v, 50)
+    assert np.allclose(reg.proxf(X), px.utils.soft(X, 50))
+
+
+# ------------------------------------------------------------------ SHT primitives
+@pytest.mark.parametrize("spin", [0, 2])
+def test_sht_golden(px, spin):
+    g = golden("ref_sht_L12.npz")
+    L = int(g["L"])
+    s = px.sht
+    assert rel_l2(s.inverse(g[f"flm_s{spin}"], L, Spin=spin), g[f"inverse_s{spin}"]) < TOL
+    assert rel_l2(s.forward(g["f"], L, Spin=spin), g[f"forward_s{spin}"]) < TOL
+    assert rel_l2(s.inverse_adjoint(g["f"], L, Spin=spin), g[f"inverse_adjoint_s{spin}"]) < TOL
+    assert rel_l2(s.forward_adjoint(g[f"flm_s{spin}"], L, Spin=spin), g[f"forward_adjoint_s{spin}"]) < TOL
+
+
+@pytest.mark.parametrize("L,spin", [(3, 0), (4, 2), (17, 0), (33, 2), (64, 0), (100, -2)])
+def test_sht_vs_oracle_and_properties(px, L, spin):
+    from oracle import ssht_ref
+
+    rng = np.random.default_rng(100 + L)
+    s = px.sht
+    flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    flm[: spin * spin] = 0
+    f = rng.standard_normal((L, 2 * L - 1)) + 1j * rng.standard_normal((L, 2 * L - 1))
+    fi = s.inverse(flm, L, Spin=spin)
+    assert rel_l2(fi, ssht_ref.inverse(flm, L, spin)) < TOL
+    assert rel_l2(s.forward(f, L, Spin=spin), ssht_ref.forward(f, L, spin)) < TOL
+    assert rel_l2(s.inverse_adjoint(f, L, Spin=spin), ssht_ref.inverse_adjoint(f, L, spin)) < TOL
+    assert rel_l2(s.forward_adjoint(flm, L, Spin=spin), ssht_ref.forward_adjoint(flm, L, spin)) < TOL
+    # exactness and adjointness (reference tests/test_measurements.py, test_utils.py:85-100)
+    assert rel_l2(s.forward(fi, L, Spin=spin), flm) < TOL
+    assert abs(np.vdot(f, fi) - np.vdot(s.inverse_adjoint(f, L, Spin=spin), flm)) < 1e-9 * np.linalg.norm(f) * np.linalg.norm(fi)
+
+
+def test_sht_batched_equals_single(px):
+    import torch
+    from pxmcmc_b200 import device as D
+
+    L, nb = 20, 7
+    rng = np.random.default_rng(5)
+    flm = rng.standard_normal((nb, L * L)) + 1j * rng.standard_normal((nb, L * L))
+    out = D.to_host(D.ShtPlan.get(L, 0, nb).inverse(D.to_dev_c(flm)))
+    for i in range(nb):
+        assert rel_l2(out[i], px.sht.inverse(flm[i], L).ravel()) < 1e-13
+    back = D.to_host(D.ShtPlan.get(L, 0, nb).forward(D.to_dev_c(out)))
+    assert rel_l2(back, flm) < TOL
+
+
+def test_sht_large_bandlimit_properties(px):
+    """size-independent properties at the BASELINE bandlimit: exact round trip and linearity"""
+    L = 256
+    rng = np.random.default_rng(9)
+    flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    f = px.sht.inverse(flm, L)
+    assert rel_l2(px.sht.forward(f, L), flm) < TOL
+    g = rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape)
+    a = px.sht.inverse_adjoint(g, L)
+    assert abs(np.vdot(g, f) - np.vdot(a, flm)) < 1e-10 * np.linalg.norm(g) * np.linalg.norm(f)
+
+
+# ------------------------------------------------------------------ wavelets
+@pytest.mark.parametrize("tag", ["L10B2", "L16B1p5"])
+def test_wavelet_golden(px, tag):
+    g = golden(f"ref_wavelet_{tag}.npz")
+    L, B, J = int(g["L"]), float(g["B"]), int(g["J_min"])
+    t = px.transforms.SphericalWaveletTransform(L, B, J)
+    assert (t.nscal, t.nwav, t.ncoefs) == (int(g["nscal"]), int(g["nwav"]), int(g["nscal"]) + int(g["nwav"]))
+    assert rel_l2(t.forward(g["x_pix"]), g["forward"]) < TOL
+    assert rel_l2(t.inverse(g["x_coef"]), g["inverse"]) < TOL
+    assert rel_l2(t.inverse_adjoint(g["x_pix"]), g["inverse_adjoint"]) < TOL
+    assert rel_l2(t.forward_adjoint(g["x_coef"]), g["forward_adjoint"]) < TOL
+    # prior weight vectors of the S2 priors
+    assert rel_l2(px.prior.S2_Wavelets_L1("synthesis", None, None, 1.0, L, B, J).T, g["s2_T"]) < 1e-14
+    pw = px.prior.S2_Wavelets_L1_Power_Weights("synthesis", None, None, 1.0, L, B, J, eta=1)
+    assert rel_l2(pw.T, g["s2pw_T"]) < 1e-14 and rel_l2(pw.map_weights, g["s2pw_w"]) < 1e-14
+
+
+@pytest.mark.parametrize("L,B,J", [(10, 2, 2), (32, 1.5, 2), (28, 2, 2), (64, 3, 1)])
+def test_wavelet_vs_oracle_and_reference_properties(px, L, B, J):
+    from oracle import pxmcmc_ref as R
+
+    rng = np.random.default_rng(L)
+    t = px.transforms.SphericalWaveletTransform(L, B, J)
+    o = R.WaveletTransform(L, B, J)
+    assert t.ncoefs == o.ncoefs and t.nscal == o.nscal
+    xp = rng.standard_normal(L * (2 * L - 1)) + 1j * rng.standard_normal(L * (2 * L - 1))
+    xc = rng.standard_normal(t.ncoefs) + 1j * rng.standard_normal(t.ncoefs)
+    assert rel_l2(t.inverse(xc), o.inverse(xc)) < TOL
+    assert rel_l2(t.inverse_adjoint(xp), o.inverse_adjoint(xp)) < TOL
+    assert rel_l2(t.forward(xp), o.forward(xp)) < TOL
+    assert rel_l2(t.forward_adjoint(xc), o.forward_adjoint(xc)) < TOL
+    # reference tests/test_transforms.py:16-46 on a band-limited real map
+    x = px.sht.inverse(px.sht.forward(xp.real, L), L).ravel()
+    assert np.allclose(t.inverse(t.forward(x)), x)
+    assert np.isclose(np.vdot(xc, t.forward(x)) - np.vdot(t.forward_adjoint(xc), x), 0, atol=1e-8)
+    assert np.isclose(np.vdot(x, t.inverse(xc)) - np.vdot(t.inverse_adjoint(x), xc), 0, atol=1e-8)
+
+
+def test_wavelet_full_size_properties(px):
+    """BASELINE size (L=256, B=1.5): dot test of the hot pair and exact reconstruction"""
+    L, B, J = 256, 1.5, 2
+    rng = np.random.default_rng(3)
+    t = px.transforms.SphericalWaveletTransform(L, B, J)
+    assert t.ncoefs == 398342
+    xc = rng.standard_normal(t.ncoefs) + 1j * rng.standard_normal(t.ncoefs)
+    xp = rng.standard_normal(L * (2 * L - 1)) + 1j * rng.standard_normal(L * (2 * L - 1))
+    y, g = t.inverse(xc), t.inverse_adjoint(xp)
+    assert abs(np.vdot(xp, y) - np.vdot(g, xc)) < 1e-10 * np.linalg.norm(xp) * np.linalg.norm(y)
+    x = px.sht.inverse(px.sht.forward(xp, L), L).ravel()
+    assert rel_l2(t.inverse(t.forward(x)), x) < TOL
+
+
+# ------------------------------------------------------------------ operators
+def test_operator_output_lengths(px):
+    # reference tests/test_forward.py
+    L, B, J = 10, 2, 2
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal(L * (2 * L - 1))
+    for setting in ("analysis", "synthesis"):
+        for sig in (0.1, np.full(data.size, 0.1)):
+            op = px.forward.SphericalWaveletTransformOperator(data, sig, setting, L, B, J)
+            assert len(op.forward(rng.random(op.nparams).astype(complex))) == len(op.data)
+            assert len(op.calc_gradg(rng.random(len(op.data)))) == op.nparams
+            A = sparse.random(len(data), L * (2 * L - 1), density=0.05, random_state=1)
+            op = px.forward.PathIntegralOperator(A, data, sig, setting, L, B, J)
+            assert len(op.forward(rng.random(op.nparams).astype(complex))) == len(op.data)
+            assert len(op.calc_gradg(rng.random(len(op.data)))) == op.nparams
+    with pytest.raises(ValueError):
+        px.forward.ForwardOperator(data, 0.1, "nonsense")
+    with pytest.raises(TypeError):
+        px.forward.ForwardOperator(data, np.ones(3), "analysis")
+
+
+def test_pathintegral(px):
+    # reference tests/test_measurements.py:8-45
+    L = 10
+    rng = np.random.default_rng(2)
+    A = sparse.random(100, L * (2 * L - 1), density=0.05, random_state=2, format="csr")
+    p = px.measurements.PathIntegral(A)
+    x = rng.standard_normal(L * (2 * L - 1)) + 1j * rng.standard_normal(L * (2 * L - 1))
+    y = rng.random(100) + 0j
+    assert rel_l2(p.forward(x), A @ x) < 1e-14
+    assert rel_l2(p.adjoint(y), A.T @ y) < 1e-14
+    ring = np.zeros((L, 2 * L - 1))
+    ring[(L - 1) // 2, :] = 2 * np.pi / (2 * L - 1)
+    pr = px.measurements.PathIntegral(sparse.csr_matrix(ring.reshape(1, -1)))
+    assert np.isclose(pr.forward(np.ones(L * (2 * L - 1)))[0], 2 * np.pi)
+    empty = px.measurements.PathIntegral(sparse.csr_matrix((5, L * (2 * L - 1))))   # rows without entries
+    assert np.all(empty.forward(x) == 0)
+
+
+def test_weaklensing_golden(px):
+    g = golden("ref_weaklensing_L12.npz")
+    L = int(g["L"])
+    wl = px.measurements.WeakLensing(L, mask=g["mask"], ngal=g["ngal"])
+    assert np.array_equal(wl.harmonic_kernel, g["kernel"])
+    assert rel_l2(wl.inv_cov, g["inv_cov"]) < 1e-15
+    assert rel_l2(wl.forward(g["kappa"]), g["forward"]) < TOL
+    assert rel_l2(wl.adjoint(g["gamma"]), g["adjoint"]) < TOL
+    wl0 = px.measurements.WeakLensing(L)
+    assert rel_l2(wl0.forward(g["kappa"]), g["forward_nomask"]) < TOL
+    assert rel_l2(wl0.adjoint(g["kappa"]), g["adjoint_nomask"]) < TOL
+    a = abs(np.vdot(g["kappa"], wl.adjoint(g["gamma"])))
+    b = abs(np.vdot(g["gamma"], wl.forward(g["kappa"])))
+    assert np.isclose(a, b)
+    t = px.transforms.SphericalWaveletTransform(L, 2, 2)
+    fo = px.forward.ForwardOperator(g["gdata"], 1 / wl.inv_cov, "synthesis", transform=t, measurement=wl, nparams=t.ncoefs)
+    assert rel_l2(fo.invcov.diagonal(), g["op_invcov"]) < 1e-15
+    assert rel_l2(fo.forward(g["X"]), g["op_forward"]) < TOL
+    assert rel_l2(fo.calc_gradg(g["op_forward"]), g["op_gradg"]) < TOL
+    with pytest.raises(ValueError):
+        px.measurements.WeakLensing(L, mask=np.ones((3, 3)))
+    with pytest.raises(ValueError):
+        px.measurements.WeakLensing(0)
+
+
+# ------------------------------------------------------------------ samplers
+def _myula_from_golden(px, g, **kw):
+    L, B, J = int(g["L"]), float(g["B"]), int(g["J_min"])
+    sig = g["sig_d"] if g["sig_d"].ndim else float(g["sig_d"])
+    op = px.forward.SphericalWaveletTransformOperator(g["data"], sig, "synthesis", L, B, J)
+    p = px.mcmc.PxMCMCParams(nsamples=int(g["nsamples"]), nburn=int(g["nburn"]), ngap=int(g["ngap"]),
+                             delta=float(g["delta"]), lmda=float(g["lmda"]), mu=float(g["mu"]), verbosity=0,
+                             track=["logposterior", "L2", "prior", "chain", "predictions"])
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu, L=L, B=B, J_min=J)
+    return px.mcmc.MYULA(op, reg, p, **kw)
+
+
+@pytest.mark.parametrize("tag", ["L10_complex", "L10_real_sigvec", "L16B1p5_complex"])
+def test_myula_chain_reproduces_reference(px, tag):
+    """seeded run with host noise == the unmodified reference's chain"""
+    import warnings
+
+    g = golden(f"ref_myula_{tag}.npz")
+    m = _myula_from_golden(px, g)
+    np.random.seed(int(g["seed"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.run()
+    assert rel_l2(m.chain, g["chain"]) < TOL
+    assert rel_l2(m.preds, g["preds"]) < TOL
+    assert rel_l2(m.logPi, g["logPi"]) < TOL
+    assert rel_l2(m.L2s, g["L2s"]) < TOL
+    assert rel_l2(m.priors, g["priors"]) < TOL
+
+
+def test_myula_single_step_golden(px):
+    g = golden("ref_myula_step_L10.npz")
+    L, B, J = int(g["L"]), float(g["B"]), int(g["J_min"])
+    op = px.forward.SphericalWaveletTransformOperator(g["data"], float(g["sig_d"]), "synthesis", L, B, J)
+    p = px.mcmc.PxMCMCParams(delta=float(g["delta"]), lmda=float(g["lmda"]), mu=float(g["mu"]), verbosity=0, nsamples=1)
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu, L=L, B=B, J_min=J)
+    m = px.mcmc.MYULA(op, reg, p)
+    assert rel_l2(op.invcov.diagonal(), g["invcov"]) < 1e-15
+    assert rel_l2(reg.T, g["T"]) < 1e-14
+    assert rel_l2(op.forward(g["X"]), g["preds"]) < TOL
+    assert rel_l2(op.calc_gradg(g["preds"]), g["gradg"]) < TOL
+    prox = reg.proxf(g["X"])
+    assert np.array_equal(prox == 0, g["prox"] == 0)                      # support identical
+    assert np.array_equal(np.sign(prox.real), np.sign(g["prox"].real))    # sign pattern identical
+    assert np.array_equal(np.sign(prox.imag), np.sign(g["prox"].imag))
+    assert rel_l2(prox, g["prox"]) < 1e-15
+    np.random.seed(5)
+    assert rel_l2(m.chain_step(g["X"], g["prox"], g["gradg"]), g["Xn"]) < 1e-14
+    lp, l2, pr = m.logpi(g["X"], g["preds"])
+    assert np.isclose(lp, g["logpi"], rtol=1e-11) and np.isclose(l2, g["L2"], rtol=1e-11) and np.isclose(pr, g["prior"], rtol=1e-12)
+
+
+def test_pxmala_reproduces_reference(px):
+    import warnings
+
+    g = golden("ref_pxmala_L10.npz")
+    L, B, J = int(g["L"]), float(g["B"]), int(g["J_min"])
+    op = px.forward.SphericalWaveletTransformOperator(g["data"], float(g["sig_d"]), "analysis", L, B, J)
+    p = px.mcmc.PxMCMCParams(nsamples=int(g["nsamples"]), nburn=int(g["nburn"]), ngap=int(g["ngap"]),
+                             delta=float(g["delta"]), lmda=float(g["lmda"]), mu=float(g["mu"]), verbosity=0,
+                             track=["logposterior", "L2", "prior", "chain", "predictions"])
+    reg = px.prior.L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu)
+    m = px.mcmc.PxMALA(op, reg, p, tune_delta=True)
+    assert np.isclose(m.calc_logtransition(g["X1"], g["X2"], g["proxf"], g["gradg"]), g["logtrans"], rtol=1e-10)
+    assert rel_l2(reg.proxf(g["X1"]), g["proxf"]) < TOL
+    np.random.seed(int(g["seed"]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m.run()
+    assert list(m.acceptance_trace) == list(g["acceptance_trace"])
+    assert np.allclose(m.deltas_trace, g["deltas_trace"], rtol=1e-13, atol=0)
+    assert rel_l2(m.chain, g["chain"]) < TOL
+    assert rel_l2(m.logPi, g["logPi"]) < TOL
+
+
+def test_skrock_reproduces_reference(px):
+    g = golden("ref_skrock_L10.npz")
+    L, B, J = int(g["L"]), float(g["B"]), int(g["J_min"])
+    A = sparse.csr_matrix((g["A_data"], g["A_indices"], g["A_indptr"]), shape=tuple(g["A_shape"]))
+    op = px.forward.PathIntegralOperator(A, g["data"], g["sig_d"], "synthesis", L, B, J)
+    p = px.mcmc.PxMCMCParams(delta=float(g["delta"]), lmda=float(g["lmda"]), mu=float(g["mu"]), s=3, verbosity=0, nsamples=1)
+    reg = px.prior.S2_Wavelets_L1_Power_Weights("synthesis", op.transform.inverse, op.transform.inverse_adjoint,
+                                               p.lmda * p.mu, L=L, B=B, J_min=J, eta=1)
+    m = px.mcmc.SKROCK(op, reg, p)
+    assert np.allclose(m.mus, g["mus"], rtol=1e-13) and np.allclose(m.nus, g["nus"], rtol=1e-13) and np.allclose(m.ks, g["ks"], rtol=1e-13)
+    m5 = px.mcmc.SKROCK(op, reg, px.mcmc.PxMCMCParams(s=5, verbosity=0, nsamples=1))
+    assert np.allclose(m5.mus, g["mus5"], rtol=1e-13) and np.allclose(m5.nus, g["nus5"], rtol=1e-13)
+    assert rel_l2(reg.T, g["T"]) < 1e-14
+    assert np.isclose(reg.prior(g["X"]), g["prior"], rtol=1e-12)
+    assert rel_l2(op.forward(g["X"]), g["preds"]) < TOL
+    assert rel_l2(op.calc_gradg(g["preds"]), g["gradg"]) < TOL
+    assert rel_l2(m._gradlogpi(g["X"]), g["gradlogpi"]) < TOL
+    np.random.seed(31)
+    assert rel_l2(m.chain_step(g["X"]), g["Xn"]) < TOL
+
+
+def test_samplers_smoke_identity_operators(px):
+    """reference tests/test_mcmc.py: each sampler runs with IdentityTransform + Identity + L1"""
+    rng = np.random.default_rng(0)
+    data = rng.standard_normal(190)
+    for setting in ("analysis", "synthesis"):
+        for sig in (0.1, np.full(190, 0.1)):
+            t = px.transforms.IdentityTransform()
+            op = px.forward.ForwardOperator(data, sig, setting, t, px.measurements.Identity(190, 190), nparams=190)
+            reg = px.prior.L1(setting, t.inverse, t.inverse_adjoint, 1)
+            prm = px.mcmc.PxMCMCParams(nsamples=20, nburn=5, ngap=2, verbosity=0, s=5)
+            for cls in (px.mcmc.MYULA, px.mcmc.PxMALA, px.mcmc.SKROCK):
+                algo = cls(op, reg, prm)
+                algo.run()
+                algo = cls(op, reg, prm)
+                algo.run(data.copy())
+                with pytest.raises(Exception):
+                    cls(op, reg, prm).run(data[:5])
+                with pytest.raises(TypeError):
+                    cls(op, reg, prm).run([1.0] * 190)
+
+
+def test_multichain_device_noise(px):
+    """batched chains with Philox noise: chains differ, statistics sane, batch == plan batch"""
+    L, B, J, nb = 16, 2, 2, 4
+    rng = np.random.default_rng(4)
+    data = px.sht.inverse(rng.standard_normal(L * L) + 0j, L).ravel()
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.1, "synthesis", L, B, J, nchains=nb)
+    p = px.mcmc.PxMCMCParams(nsamples=3, nburn=0, ngap=2, delta=1e-6, lmda=1e-6, verbosity=0)
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda, L=L, B=B, J_min=J)
+    m = px.mcmc.MYULA(op, reg, p, noise="device", nchains=nb, seed=7)
+    m.run(np.zeros(op.nparams))
+    assert m.chain.shape == (nb, 3, op.nparams)
+    assert np.all(np.isfinite(m.chain))
+    assert not np.allclose(m.chain[0], m.chain[1])
+    # identical seed => identical chains (counter-based generator)
+    m2 = px.mcmc.MYULA(op, reg, p, noise="device", nchains=nb, seed=7)
+    m2.run(np.zeros(op.nparams))
+    assert np.array_equal(m.chain, m2.chain)
+    # first increment is sqrt(2 delta) * N(0,1) to leading order
+    z = m.chain[:, 0, :].ravel() / np.sqrt(2e-6)
+    assert abs(z.std() - np.sqrt(1.0)) < 0.2
