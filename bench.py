@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the proximal-Langevin hot path (BASELINE.json metric:
+"MYULA iterations/s at L=256 (per chain and x chains)").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one MYULA iteration (mcmc.py:158-164 of the reference: data-fidelity
+gradient through Psi^dagger, fused soft-threshold prox + Langevin update with
+Philox noise, new predictions through Psi) of `--chains` independent chains per
+GPU, wavelet-synthesis operator at L=256, B=1.5, J_min=2 (398 342 complex
+coefficients and 130 816 complex pixels per chain), synthetic complex map.
+Chains are independent units: weak scaling, no data-path collective.
+
+Prints ONE JSON line (see DESIGN.md "Measurement" for every field).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_DEF, B_DEF, JMIN_DEF = 256, 1.5, 2
+METRIC = "MYULA chain-iterations/s at L=256 (x chains)"
+UNIT = "chain-iterations/s"
+
+
+def bandlimits(L, B, J_min):
+    J = int(np.ceil(np.log(L) / np.log(B)))
+    out = [min(int(np.ceil(B ** J_min)), L)]
+    for j in range(J_min, J + 1):
+        out.append(min(int(np.ceil(B ** (j + 1))), L))
+    return out
+
+
+def algorithmic_flops_per_chain_iteration(L, B, J_min):
+    """F_it = 2 F_Psi = 8 (L^3 + sum_scales L_j^3) FP64 flops (FFT flops excluded)."""
+    return 8.0 * (L ** 3 + sum(b ** 3 for b in bandlimits(L, B, J_min)))
+
+
+def synthetic_flm(L, seed=20240):
+    rng = np.random.default_rng(seed)
+    flm = np.zeros(L * L, dtype=complex)
+    for el in range(L):
+        amp = (1.0 + el) ** -1.25  # C_l = (1+l)^-2.5
+        flm[el * el + el] = amp * rng.standard_normal()
+        m = np.arange(1, el + 1)
+        a = amp * (rng.standard_normal(el) + 1j * rng.standard_normal(el)) / np.sqrt(2)
+        flm[el * el + el + m] = a
+        flm[el * el + el - m] = (-1.0) ** m * np.conj(a)
+    return flm
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit())}
+
+
+# ---------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU oracle restatement of the reference path
+# ---------------------------------------------------------------------------------------
+def _oracle_one_iteration(args):
+    L, B, J_min, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        ctx = None
+    from oracle import pxmcmc_ref as R
+    from oracle import ssht_ref
+
+    rng = np.random.default_rng(seed)
+    t = R.WaveletTransform(L, B, J_min)
+    data = ssht_ref.inverse(synthetic_flm(L), L, 0).ravel()
+    data = data / np.sqrt(np.mean(np.abs(data) ** 2))
+    op = R.ForwardOperator(data, 1.0, "synthesis", t, R.IdentityMeasurement(data.size, data.size), t.ncoefs)
+    prior = R.S2WaveletsL1("synthesis", t.inverse, t.inverse_adjoint, 1e-6, L, B, J_min)
+    X = rng.laplace(size=t.ncoefs)
+    preds = op.forward(X)
+    t0 = time.perf_counter()
+    R.myula_iteration(op, prior, 1e-6, 1e-6, X, preds, rng.standard_normal(t.ncoefs))
+    dt = time.perf_counter() - t0
+    if ctx is not None:
+        ctx.unregister() if hasattr(ctx, "unregister") else None
+    return dt
+
+
+def cpu_reference_throughput(L, B, J_min, procs, steps):
+    """`steps` rounds of `procs` independent chain-iterations run one per host core"""
+    import multiprocessing as mp
+
+    times = []
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for s in range(steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_one_iteration, [(L, B, J_min, 1000 * s + i) for i in range(procs)])
+            times.append(time.perf_counter() - t0)
+    # the timed map includes building each worker's inputs; use the workers' own timers instead
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # the CPU leg is O(L^3) numpy: bound the sample so that the run ends within minutes
+    L = args.ref_L
+    procs = max(1, min(os.cpu_count() or 1, args.ref_procs))
+    import multiprocessing as mp
+
+    steps = max(1, min(args.steps, 2))
+    t_iter = []
+    with mp.get_context("spawn").Pool(procs) as pool:
+        for s in range(args.warmup and 1 or 0):
+            pool.map(_oracle_one_iteration, [(L, args.B, args.J_min, i) for i in range(procs)])
+        t0 = time.perf_counter()
+        for s in range(steps):
+            t_iter += pool.map(_oracle_one_iteration, [(L, args.B, args.J_min, 100 * s + i) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    mean_it = float(np.mean(t_iter))
+    value = procs / mean_it  # procs chains advance one iteration every mean_it seconds
+    scale = (algorithmic_flops_per_chain_iteration(args.L, args.B, args.J_min) /
+             algorithmic_flops_per_chain_iteration(L, args.B, args.J_min))
+    sample = (f"{steps} x {procs} chain-iterations of the numpy oracle (CPU restatement of the reference path), one per core, "
+              f"at L={L}" + ("" if L == args.L else f"; value scaled by the O(L^3) flop ratio {scale:.1f} to L={args.L}"))
+    value_at_L = value / scale
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value_at_L, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * mean_it * scale, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"MYULA L={args.L} B={args.B} J_min={args.J_min} synthesis, S2_Wavelets_L1, CPU oracle port"},
+        "cpu_baseline": {"value": value_at_L, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value_at_L, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from pxmcmc_b200 import _lib, device as D, sht
+    from pxmcmc_b200.forward import SphericalWaveletTransformOperator
+    from pxmcmc_b200.mcmc import MYULA, PxMCMCParams
+    from pxmcmc_b200.prior import S2_Wavelets_L1
+    import ctypes as C
+
+    L, B, J_min, nch = args.L, args.B, args.J_min, args.chains
+    data = sht.inverse(synthetic_flm(L), L).ravel()
+    data = data / np.sqrt(np.mean(np.abs(data) ** 2))  # complex, as on the reference's HEALPix path
+    op = SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J_min, nchains=nch)
+    prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, track=[])
+    reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J_min)
+    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234 + rank)
+    ncoef, npix = op.nparams, L * (2 * L - 1)
+    rng = np.random.default_rng(7 + rank)
+    X = D.to_dev_c(rng.laplace(size=(nch, ncoef)))
+    P = D.to_dev_c(op.forward(X))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput -----------------------------------------------------
+    for _ in range(args.warmup):
+        X, P = m.iterate(X, P)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.lib.pxm_launch_count()
+    _lib.check(_lib.lib.pxm_profile_begin(16 * args.steps + 64))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        X, P = m.iterate(X, P)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    ms_kind = (C.c_double * 3)()
+    cnt_kind = (C.c_longlong * 3)()
+    _lib.check(_lib.lib.pxm_profile_end(ms_kind, cnt_kind))
+    launches = _lib.lib.pxm_launch_count() - l0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    finite = bool(torch.isfinite(torch.view_as_real(X)).all().item())
+
+    # ---- FP64 peak for the roofline: cuBLAS DGEMM measured right here ------------------------
+    def dgemm_peak():
+        n = 6144
+        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+        torch.matmul(a, b)
+        best = 1e9
+        for _ in range(4):
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            torch.matmul(a, b)
+            s1.record()
+            torch.cuda.synchronize()
+            best = min(best, s0.elapsed_time(s1))
+        return 2.0 * n ** 3 / best / 1e9  # TFLOP/s
+
+    # ---- end-to-end through host buffers (pinned), rank-local ----------------------------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    Xh = torch.empty((nch, ncoef), dtype=torch.complex128).pin_memory()
+    Ph = torch.empty((nch, npix), dtype=torch.complex128).pin_memory()
+    Xh.copy_(X.cpu())
+    Ph.copy_(P.cpu())
+    Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
+    m.iterate_host(Xh, Ph, Xo, Po)  # warm-up
+    barrier()
+    w0 = torch.cuda.Event(enable_timing=True)
+    w1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    w0.record()
+    for _ in range(e2e_steps):
+        m.iterate_host(Xh, Ph, Xo, Po)
+        Xh, Xo = Xo, Xh
+        Ph, Po = Po, Ph
+    w1.record()
+    torch.cuda.synchronize()
+    e2e_s = max(w0.elapsed_time(w1) / 1e3, time.perf_counter() - t0)
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = (ncoef + npix) * nch * 16
+    d2h = (ncoef + npix) * nch * 16
+
+    if rank == 0:
+        peak = dgemm_peak()
+        flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
+        leg_ms, leg_n = ms_kind[0], cnt_kind[0]
+        achieved = flops_step * args.steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": world * nch * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"MYULA L={L} B={B} J_min={J_min} synthesis, Identity measurement, S2_Wavelets_L1, "
+                                   f"{nch} independent chains per GPU (config 5 of BASELINE.json; per-chain it/s = value/(n_gpus*chains))",
+                       "chains_per_gpu": nch, "ncoefs": ncoef, "npix": npix, "noise": "Philox4x32-10 in-kernel",
+                       "l2_note": f"per-step working set {(ncoef + npix) * nch * 16 * 3 / 2**20:.0f} MiB of state + "
+                                  f"{op.transform._plan(nch).table_bytes / 2**20:.0f} MiB of Legendre tables exceeds the 126 MB L2"},
+            "per_chain_iterations_per_s": args.steps / (ms / 1e3),
+            "gpu_launches": int(launches),
+            "finite": finite,
+            "stage_ms_per_step": {"legendre": leg_ms / args.steps, "ring_fft": ms_kind[1] / args.steps,
+                                  "elementwise": ms_kind[2] / args.steps},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)",
+                         "launches_timed": int(leg_n),
+                         "algorithmic_flops_per_launch": flops_step / 4,
+                         "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
+            "e2e": {"value": world * nch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host"},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            t_it = _oracle_one_iteration((args.ref_L, B, J_min, 0))
+            scale = algorithmic_flops_per_chain_iteration(L, B, J_min) / algorithmic_flops_per_chain_iteration(args.ref_L, B, J_min)
+            line["cpu_baseline"] = {
+                "value": 1.0 / (t_it * scale), "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"1 chain-iteration of the numpy oracle at L={args.ref_L} ({t_it:.1f} s on one core)"
+                          + ("" if args.ref_L == L else f", scaled by the O(L^3) flop ratio {scale:.1f} to L={L}")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chains", type=int, default=64, help="independent chains per GPU")
+    ap.add_argument("--L", type=int, default=L_DEF)
+    ap.add_argument("--B", type=float, default=B_DEF)
+    ap.add_argument("--J_min", type=int, default=JMIN_DEF)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--ref-L", type=int, default=256, help="bandlimit of the bounded CPU sample")
+    ap.add_argument("--ref-procs", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,16 @@ int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* s
 int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
                  int nrows, long long ncols, long long nchains, void* stream);
 
+/* ---- measurement aids (bench.py) ---------------------------------------------
+ * pxm_profile_begin/end bracket a region in which every library call records a
+ * CUDA-event pair on its launching stream; end() returns the summed device time
+ * and the number of timed calls per kernel class: 0 Legendre contraction,
+ * 1 ring FFT, 2 elementwise/reduction/sparse.  pxm_launch_count: kernels
+ * launched by the library since load. */
+int pxm_profile_begin(int max_events);
+int pxm_profile_end(double* ms_by_kind, long long* count_by_kind);
+long long pxm_launch_count(void);
+
 /* ---- debugging aids (tests only) ---------------------------------------------- */
 int pxm_debug_set_naive(int on); /* route Legendre contractions through the plain kernel */
 int pxm_debug_wigner_row_host(int grid_L, int ring, int m, int spin, int lmax, double* out); /* host, no GPU */

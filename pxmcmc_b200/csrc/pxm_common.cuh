@@ -33,6 +33,14 @@ void pxm_set_error(const std::string& msg);
     }                                                                                    \
   } while (0)
 
+// every kernel launch of the library goes through this (launch counter for bench.py's gpu_launches)
+extern long long g_pxm_launches;
+#define PXM_LAUNCHED()           \
+  do {                           \
+    ++g_pxm_launches;            \
+    PXM_CUDA(cudaGetLastError()); \
+  } while (0)
+
 #define PXM_REQUIRE(cond, msg)                     \
   do {                                             \
     if (!(cond)) {                                 \

@@ -410,7 +410,7 @@ int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, 
     k_soft_c<<<grid_for(total), 256, 0, st>>>((const cplx*)x, Tv, Ts, (cplx*)out, n, total);
   else
     k_soft_r<<<grid_for(total), 256, 0, st>>>((const double*)x, Tv, Ts, (double*)out, n, total);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -440,7 +440,7 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
   p.stream0 = stream0;
   if (!p.total) return PXM_OK;
   k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -449,7 +449,7 @@ int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* 
   const size_t total = n * nchains;
   if (!total) return PXM_OK;
   k_resid<<<grid_for(total), 256, 0, st>>>((const cplx*)preds, (const cplx*)data, (const cplx*)ic, (cplx*)out, n, total);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -473,9 +473,9 @@ int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, con
   if (!nchains) return PXM_OK;
   dim3 grid(PXM_REDUCE_PARTS, (unsigned)nchains);
   k_reduce_stage1<<<grid, 256, 0, st>>>(p);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   k_reduce_stage2<<<(unsigned)nchains, 256, 0, st>>>((const cplx*)partial, PXM_REDUCE_PARTS, (cplx*)out);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -494,7 +494,7 @@ int pxm_launch_lincomb(int nx, const void* const* xs, const double* as, const do
   p.total = total;
   if (!total) return PXM_OK;
   k_lincomb<<<grid_for(total), 256, 0, st>>>(p);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -507,7 +507,7 @@ int pxm_launch_gather(int scatter, const void* in, const int* idx, const double*
     k_scatter_w<<<grid_for(total), 256, 0, st>>>((const cplx*)in, idx, w, (cplx*)out, nsel, nfull, total);
   else
     k_gather_w<<<grid_for(total), 256, 0, st>>>((const cplx*)in, idx, w, (cplx*)out, nsel, nfull, total);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -526,14 +526,14 @@ int pxm_launch_lm_convert(int to_internal, void* flm, double* H, const unsigned 
   const size_t total = (size_t)L * L * nchains;
   if (!total) return PXM_OK;
   k_lm_convert<<<grid_for(total), 256, 0, st>>>(p);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
 int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st) {
   if (!total) return PXM_OK;
   k_r2c<<<grid_for(total), 256, 0, st>>>(x, (cplx*)out, total);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -542,7 +542,7 @@ int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* val
   if (!nrows || !nchains) return PXM_OK;
   dim3 grid((unsigned)((nrows * 32 + 255) / 256), (unsigned)nchains);
   k_csr_spmv<<<grid, 256, 0, st>>>(indptr, indices, vals, (const cplx*)x, (cplx*)y, nrows, ncols);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -552,6 +552,6 @@ int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, doub
   if (!total) return PXM_OK;
   k_gradlogpi<<<grid_for(total), 256, 0, st>>>((const cplx*)X, (const cplx*)prox, Tv, Ts, (const cplx*)gradg, lmda,
                                                 (cplx*)out, n, total);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }

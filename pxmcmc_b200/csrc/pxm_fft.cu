@@ -6,10 +6,18 @@
 // Replaces the FFTW calls inside ssht (reference call sites:
 // /root/reference/pxmcmc/transforms.py:95-98, pxmcmc/measurements.py:223-239).
 // Odd, often prime lengths (511, 389, 259, 173, ...) => Bluestein chirp-z with a
-// power-of-two length M >= 2n-1 done entirely in shared memory: radix-4(/2)
-// decimation-in-frequency forward, pointwise product with the precomputed filter
-// spectrum (kept in the kernel's own digit-reversed order, so no reordering pass
-// exists anywhere), decimation-in-time inverse.
+// power-of-two length M >= 2n-1, entirely on-chip:
+//   * in-place radix-16 passes (one leading radix-2/4/8 pass when log2 M is not a
+//     multiple of 4); every thread holds its 16 points in registers, shared
+//     memory is only the exchange medium between passes and is padded by one
+//     element per 16 so that both the strided and the contiguous access patterns
+//     are bank-conflict free;
+//   * decimation in frequency forward, decimation in time inverse, so the
+//     spectrum is only ever seen in the kernel's own digit-reversed order (the
+//     filter spectrum is precomputed in that order: no reordering pass exists);
+//   * the last forward pass, the product with the filter spectrum and the first
+//     inverse pass act on the same 16 contiguous points and are fused in
+//     registers.
 #include "pxm_common.cuh"
 
 namespace {
@@ -24,77 +32,172 @@ __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
 }
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ cplx cmuli(cplx a) { return make_double2(-a.y, a.x); }    // * i
-__device__ __forceinline__ cplx cmulni(cplx a) { return make_double2(a.y, -a.x); }   // * -i
-
-// In-place forward FFT (e^{-i}) of `nr` rings of length M held at s[r*M + i];
-// output in the digit-reversed order defined by this very pass sequence.
-__device__ void fft_forward_dif(cplx* s, int nr, int M, int logM, const cplx* __restrict__ tw) {
-  int Ls = M;
-  if (logM & 1) {
-    const int h = M >> 1;
-    for (int idx = threadIdx.x; idx < nr * h; idx += blockDim.x) {
-      const int r = idx / h, j = idx - r * h;
-      cplx* p = s + r * M;
-      const cplx x0 = p[j], x1 = p[j + h];
-      p[j] = cadd(x0, x1);
-      p[j + h] = cmul(csub(x0, x1), tw[j]);
-    }
-    Ls = h;
-    __syncthreads();
-  }
-  for (; Ls >= 4; Ls >>= 2) {
-    const int q4 = Ls >> 2, nb = M >> 2, tstep = M / Ls;
-    for (int idx = threadIdx.x; idx < nr * nb; idx += blockDim.x) {
-      const int r = idx / nb, b = idx - r * nb;
-      const int blk = b / q4, j = b - blk * q4;
-      cplx* p = s + r * M + blk * Ls + j;
-      const cplx x0 = p[0], x1 = p[q4], x2 = p[2 * q4], x3 = p[3 * q4];
-      const cplx a02 = cadd(x0, x2), s02 = csub(x0, x2), a13 = cadd(x1, x3), s13 = csub(x1, x3);
-      const cplx y0 = cadd(a02, a13);
-      const cplx y2 = csub(a02, a13);
-      const cplx y1 = cadd(s02, cmulni(s13));  // x0 - i x1 - x2 + i x3
-      const cplx y3 = cadd(s02, cmuli(s13));   // x0 + i x1 - x2 - i x3
-      p[0] = y0;
-      p[q4] = cmul(y1, tw[j * tstep]);
-      p[2 * q4] = cmul(y2, tw[2 * j * tstep]);
-      p[3 * q4] = cmul(y3, tw[3 * j * tstep]);
-    }
-    __syncthreads();
-  }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ cplx rot90(cplx a) {
+  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+// multiply by exp(-+ i pi/4)
+template <bool INV>
+__device__ __forceinline__ cplx rot45(cplx a) {
+  const double h = 0.70710678118654752440;
+  return INV ? make_double2(h * (a.x - a.y), h * (a.x + a.y)) : make_double2(h * (a.x + a.y), h * (a.y - a.x));
+}
+template <bool INV>
+__device__ __forceinline__ cplx twc(cplx a, double c, double s) {  // a * (c -+ i s)
+  return INV ? make_double2(a.x * c - a.y * s, a.x * s + a.y * c) : make_double2(a.x * c + a.y * s, a.y * c - a.x * s);
 }
 
-// exact inverse of fft_forward_dif up to the factor M (unnormalised)
-__device__ void fft_inverse_dit(cplx* s, int nr, int M, int logM, const cplx* __restrict__ tw) {
-  for (int Ls = 4; Ls <= ((logM & 1) ? (M >> 1) : M); Ls <<= 2) {
-    const int q4 = Ls >> 2, nb = M >> 2, tstep = M / Ls;
-    for (int idx = threadIdx.x; idx < nr * nb; idx += blockDim.x) {
-      const int r = idx / nb, b = idx - r * nb;
-      const int blk = b / q4, j = b - blk * q4;
-      cplx* p = s + r * M + blk * Ls + j;
-      const cplx y0 = p[0];
-      const cplx y1 = cmulc(p[q4], tw[j * tstep]);
-      const cplx y2 = cmulc(p[2 * q4], tw[2 * j * tstep]);
-      const cplx y3 = cmulc(p[3 * q4], tw[3 * j * tstep]);
-      const cplx a02 = cadd(y0, y2), s02 = csub(y0, y2), a13 = cadd(y1, y3), s13 = csub(y1, y3);
-      p[0] = cadd(a02, a13);
-      p[2 * q4] = csub(a02, a13);
-      p[q4] = cadd(s02, cmuli(s13));       // y0 + i y1 - y2 - i y3
-      p[3 * q4] = cadd(s02, cmulni(s13));  // y0 - i y1 - y2 + i y3
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+
+// ---- small DFTs in registers: y_q = sum_r x_r exp(-+ 2 pi i r q / R), natural order in and out
+template <bool INV>
+__device__ __forceinline__ void dft2(cplx& a, cplx& b) {
+  const cplx t = a;
+  a = cadd(t, b);
+  b = csub(t, b);
+}
+template <bool INV>
+__device__ __forceinline__ void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
+  const cplx a02 = cadd(x0, x2), s02 = csub(x0, x2), a13 = cadd(x1, x3), s13 = rot90<INV>(csub(x1, x3));
+  x0 = cadd(a02, a13);
+  x2 = csub(a02, a13);
+  x1 = cadd(s02, s13);
+  x3 = csub(s02, s13);
+}
+template <bool INV>
+__device__ __forceinline__ void dft8(cplx* x) {
+  // 8 = 2 x 4: r = 4 r1 + r2 (r1<2, r2<4), q = q1 + 2 q2
+  dft2<INV>(x[0], x[4]);
+  dft2<INV>(x[1], x[5]);
+  dft2<INV>(x[2], x[6]);
+  dft2<INV>(x[3], x[7]);
+  // twiddles w8^(r2 q1), q1 = 1 lives in x[4+r2]
+  x[5] = rot45<INV>(x[5]);
+  x[6] = rot90<INV>(x[6]);
+  x[7] = rot90<INV>(rot45<INV>(x[7]));
+  dft4<INV>(x[0], x[1], x[2], x[3]);  // q1 = 0 -> outputs q = 2 q2
+  dft4<INV>(x[4], x[5], x[6], x[7]);  // q1 = 1 -> outputs q = 1 + 2 q2
+  // reorder to natural q: currently x[q2] = X[2 q2], x[4+q2] = X[1+2 q2]
+  const cplx t1 = x[1], t2 = x[2], t3 = x[3], t4 = x[4], t5 = x[5], t6 = x[6];
+  x[1] = t4;
+  x[2] = t1;
+  x[3] = t5;
+  x[4] = t2;
+  x[5] = t6;
+  x[6] = t3;
+}
+template <bool INV>
+__device__ __forceinline__ void dft16(cplx* x) {
+  // 16 = 4 x 4: r = 4 r1 + r2, q = q1 + 4 q2
+  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos, sin(pi/8)
+  const double h = 0.70710678118654752440;
+#pragma unroll
+  for (int r2 = 0; r2 < 4; ++r2) dft4<INV>(x[r2], x[4 + r2], x[8 + r2], x[12 + r2]);
+  // now x[4 q1 + r2] = t[r2][q1]; multiply by w16^(r2 q1)
+  x[5] = twc<INV>(x[5], c1, s1);     // k=1
+  x[6] = twc<INV>(x[6], h, h);       // k=2
+  x[7] = twc<INV>(x[7], s1, c1);     // k=3
+  x[9] = twc<INV>(x[9], h, h);       // k=2
+  x[10] = rot90<INV>(x[10]);         // k=4
+  x[11] = twc<INV>(x[11], -h, h);    // k=6
+  x[13] = twc<INV>(x[13], s1, c1);   // k=3
+  x[14] = twc<INV>(x[14], -h, h);    // k=6
+  x[15] = twc<INV>(x[15], -c1, -s1); // k=9
+#pragma unroll
+  for (int q1 = 0; q1 < 4; ++q1) dft4<INV>(x[4 * q1], x[4 * q1 + 1], x[4 * q1 + 2], x[4 * q1 + 3]);
+  // x[4 q1 + q2] = X[q1 + 4 q2] -> transpose to natural order
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = a + 1; b < 4; ++b) {
+      const cplx t = x[4 * a + b];
+      x[4 * a + b] = x[4 * b + a];
+      x[4 * b + a] = t;
     }
-    __syncthreads();
-  }
-  if (logM & 1) {
-    const int h = M >> 1;
-    for (int idx = threadIdx.x; idx < nr * h; idx += blockDim.x) {
-      const int r = idx / h, j = idx - r * h;
-      cplx* p = s + r * M;
-      const cplx y0 = p[j], y1 = cmulc(p[j + h], tw[j]);
-      p[j] = cadd(y0, y1);
-      p[j + h] = csub(y0, y1);
+}
+template <int R, bool INV>
+__device__ __forceinline__ void dftR(cplx* x) {
+  if (R == 2) dft2<INV>(x[0], x[1]);
+  if (R == 4) dft4<INV>(x[0], x[1], x[2], x[3]);
+  if (R == 8) dft8<INV>(x);
+  if (R == 16) dft16<INV>(x);
+}
+
+// One in-place pass over `nr` rings (padded stride MP): sub-transform length 2^lgLs,
+// radix R.  Forward (DIF): butterfly then twiddle; inverse (DIT): conj-twiddle then butterfly.
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass(cplx* s, int nr, int M, int MP, int lgLs, const cplx* __restrict__ tw) {
+  constexpr int lgR = R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4;
+  const int lgS = lgLs - lgR, S = 1 << lgS, nbf = M >> lgR, tstep = M >> lgLs;
+  for (int idx = threadIdx.x; idx < nr * nbf; idx += blockDim.x) {
+    const int r = idx / nbf, b = idx - r * nbf;
+    const int blk = b >> lgS, j = b & (S - 1);
+    cplx* p = s + r * MP;
+    const int base = (blk << lgLs) + j;
+    cplx x[R];
+#pragma unroll
+    for (int k = 0; k < R; ++k) x[k] = p[padi(base + (k << lgS))];
+    if (INV && lgS > 0) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) x[k] = cmulc(x[k], tw[(j * k * tstep) & (M - 1)]);
     }
-    __syncthreads();
+    dftR<R, INV>(x);
+    if (!INV && lgS > 0) {
+#pragma unroll
+      for (int k = 1; k < R; ++k) x[k] = cmul(x[k], tw[(j * k * tstep) & (M - 1)]);
+    }
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[padi(base + (k << lgS))] = x[k];
   }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int first_radix_log(int logM) { return logM & 3; }  // 0 -> only radix-16 passes
+
+// forward passes except the last (Ls = 16) one
+__device__ void fft_forward_head(cplx* s, int nr, int M, int MP, int logM, const cplx* __restrict__ tw) {
+  int lgLs = logM;
+  const int f = first_radix_log(logM);
+  if (f == 1) {
+    fft_pass<2, false>(s, nr, M, MP, lgLs, tw);
+    lgLs -= 1;
+  } else if (f == 2) {
+    fft_pass<4, false>(s, nr, M, MP, lgLs, tw);
+    lgLs -= 2;
+  } else if (f == 3) {
+    fft_pass<8, false>(s, nr, M, MP, lgLs, tw);
+    lgLs -= 3;
+  }
+  for (; lgLs > 4; lgLs -= 4) fft_pass<16, false>(s, nr, M, MP, lgLs, tw);
+}
+// inverse passes except the first (Ls = 16) one
+__device__ void fft_inverse_tail(cplx* s, int nr, int M, int MP, int logM, const cplx* __restrict__ tw) {
+  const int f = first_radix_log(logM);
+  const int top16 = logM - f;  // largest Ls handled by radix-16 passes
+  for (int lgLs = 8; lgLs <= top16; lgLs += 4) fft_pass<16, true>(s, nr, M, MP, lgLs, tw);
+  if (f == 1) fft_pass<2, true>(s, nr, M, MP, logM, tw);
+  if (f == 2) fft_pass<4, true>(s, nr, M, MP, logM, tw);
+  if (f == 3) fft_pass<8, true>(s, nr, M, MP, logM, tw);
+}
+// middle: last forward pass (contiguous 16 points, no twiddles) x filter spectrum x first inverse pass
+__device__ void fft_middle(cplx* s, int nr, int M, int MP, const cplx* __restrict__ bhat) {
+  const int nbf = M >> 4;
+  for (int idx = threadIdx.x; idx < nr * nbf; idx += blockDim.x) {
+    const int r = idx / nbf, b = idx - r * nbf;
+    cplx* p = s + r * MP + b * 17;  // padi(16 b + k) = 17 b + k
+    const cplx* bh = bhat + b * 16;
+    cplx x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = p[k];
+    dft16<false>(x);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = cmul(x[k], bh[k]);
+    dft16<true>(x);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) p[k] = x[k];
+  }
+  __syncthreads();
 }
 
 // ---- table setup -------------------------------------------------------------
@@ -115,23 +218,26 @@ __global__ void fft_fill_tables_kernel(const PxmFftGroup* groups, int ngroups, c
   }
 }
 
+// filter spectrum in the digit-reversed order produced by the forward passes
 __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cplx* arena) {
   extern __shared__ __align__(16) unsigned char fsm[];
   cplx* s = reinterpret_cast<cplx*>(fsm);
   const PxmFftGroup gr = groups[blockIdx.x];
+  const int M = gr.M, MP = M + (M >> 4);
   const cplx* chirp = arena + gr.chirp_off;
-  for (int i = threadIdx.x; i < gr.M; i += blockDim.x) s[i] = make_double2(0.0, 0.0);
+  for (int i = threadIdx.x; i < MP; i += blockDim.x) s[i] = make_double2(0.0, 0.0);
   __syncthreads();
   for (int j = threadIdx.x; j < gr.n; j += blockDim.x) {
     const cplx c = chirp[j];
     const cplx b = make_double2(c.x, -c.y);
-    s[j] = b;
-    if (j > 0) s[gr.M - j] = b;
+    s[padi(j)] = b;
+    if (j > 0) s[padi(M - j)] = b;
   }
   __syncthreads();
-  fft_forward_dif(s, 1, gr.M, gr.logM, arena + gr.tw_off);
+  fft_forward_head(s, 1, M, MP, gr.logM, arena + gr.tw_off);
+  fft_pass<16, false>(s, 1, M, MP, 4, arena + gr.tw_off);
   cplx* bhat = arena + gr.bhat_off;
-  for (int i = threadIdx.x; i < gr.M; i += blockDim.x) bhat[i] = s[i];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) bhat[i] = s[padi(i)];
 }
 
 // ---- the ring transform ---------------------------------------------------------
@@ -149,72 +255,79 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
   const int chain = blockIdx.y;
   const int t0 = ((int)blockIdx.x - gr.cta_begin) * gr.rings_per_cta;
   const int nr = min(gr.rings_per_cta, gr.rings - t0);
-  const int n = gr.n, M = gr.M, ell = gr.ell;
+  const int n = gr.n, M = gr.M, ell = gr.ell, lgM = gr.logM;
+  const int MP = M + (M >> 4);
   const cplx* chirp = arena + gr.chirp_off;
   const cplx* bhat = arena + gr.bhat_off;
   const cplx* tw = arena + gr.tw_off;
   cplx* mypix = pix + (size_t)chain * pix_chain_stride + gr.pix_off;
+  const int colbase = gr.paired ? chain * 4 : chain * 2;
 
   // 1. load, pre-multiply by the chirp, zero-pad
-  for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
-    const int r = idx / M, j = idx - r * M;
-    cplx v = make_double2(0.0, 0.0);
-    if (j < n) {
-      const int t = t0 + r;
-      if (DIR == 0) {
-        v = mypix[(size_t)t * n + j];
-      } else {
+  if (DIR == 0) {
+    for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
+      const int r = idx >> lgM, j = idx & (M - 1);
+      cplx v = make_double2(0.0, 0.0);
+      if (j < n) v = cmul(mypix[(size_t)(t0 + r) * n + j], chirp[j]);
+      s[r * MP + padi(j)] = v;
+    }
+  } else {
+    // gather F_m[t]: the rings of one k4 row-group are adjacent doubles (t%4) -> loop rings fastest
+    for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
+      const int r = idx % nr, j = idx / nr;
+      cplx v = make_double2(0.0, 0.0);
+      if (j < n) {
+        const int t = t0 + r;
         const int m = (j < ell) ? j : j - n;
         size_t base;
         double sg = 1.0;
         if (gr.paired) {
           const int am = m < 0 ? -m : m;
-          base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, chain * 4 + (m < 0 ? 2 : 0), nld);
+          base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, colbase + (m < 0 ? 2 : 0), nld);
           if (m < 0 && (am & 1)) sg = -1.0;
         } else {
-          base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, chain * 2, nld);
+          base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, colbase, nld);
         }
         // conj on load: x_p = conj( DFT( conj(F) ) )
-        v = make_double2(sg * F[base], -sg * F[base + 4]);
+        v = cmul(make_double2(sg * F[base], -sg * F[base + 4]), chirp[j]);
       }
-      v = cmul(v, chirp[j]);
+      s[r * MP + padi(j)] = v;
     }
-    s[idx] = v;
   }
   __syncthreads();
   // 2. circular convolution with the chirp filter
-  fft_forward_dif(s, nr, M, gr.logM, tw);
-  for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
-    const int j = idx & (M - 1);
-    s[idx] = cmul(s[idx], bhat[j]);
-  }
-  __syncthreads();
-  fft_inverse_dit(s, nr, M, gr.logM, tw);
+  fft_forward_head(s, nr, M, MP, lgM, tw);
+  fft_middle(s, nr, M, MP, bhat);
+  fft_inverse_tail(s, nr, M, MP, lgM, tw);
   // 3. post-multiply, scale, scatter
   const double sc = gr.scale / (double)M;
-  for (int idx = threadIdx.x; idx < nr * n; idx += blockDim.x) {
-    const int r = idx / n, k = idx - r * n;
-    const int t = t0 + r;
-    cplx v = cmul(s[r * M + k], chirp[k]);
-    v.x *= sc;
-    v.y *= sc;
-    if (DIR == 0) {
+  if (DIR == 0) {
+    for (int idx = threadIdx.x; idx < nr * n; idx += blockDim.x) {
+      const int r = idx % nr, k = idx / nr;
+      const int t = t0 + r;
+      cplx v = cmul(s[r * MP + padi(k)], chirp[k]);
+      v.x *= sc;
+      v.y *= sc;
       const int m = (k < ell) ? k : k - n;
       size_t base;
       if (gr.paired) {
         const int am = m < 0 ? -m : m;
-        base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, chain * 4 + (m < 0 ? 2 : 0), nld);
+        base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, colbase + (m < 0 ? 2 : 0), nld);
         if (m < 0 && (am & 1)) {
           v.x = -v.x;
           v.y = -v.y;
         }
       } else {
-        base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, chain * 2, nld);
+        base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, colbase, nld);
       }
       F[base] = v.x;
       F[base + 4] = v.y;  // next column in the k4-interleaved layout
-    } else {
-      mypix[(size_t)t * n + k] = make_double2(v.x, -v.y);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < nr * n; idx += blockDim.x) {
+      const int r = idx / n, k = idx - r * n;
+      cplx v = cmul(s[r * MP + padi(k)], chirp[k]);
+      mypix[(size_t)(t0 + r) * n + k] = make_double2(v.x * sc, -v.y * sc);
     }
   }
 }
@@ -234,11 +347,11 @@ int pxm_fft_choose_M(int n, int* logM) {
 int pxm_fft_rings_per_cta(int M) {
   int r = 4096 / M;
   if (r < 1) r = 1;
-  if (r > 4) r = 4;
+  if (r > 16) r = 16;
   return r;
 }
 
-constexpr int PXM_FFT_SMEM = 4096 * 16;  // 64 KB: up to 4096 complex points per CTA
+constexpr int PXM_FFT_SMEM = (4096 + 256) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
 
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
                          cudaStream_t stream) {
@@ -256,9 +369,9 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     }
   }
   fft_fill_tables_kernel<<<ngroups, 256, 0, stream>>>(d_groups, ngroups, (cplx*)d_arena);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   fft_fill_bhat_kernel<<<ngroups, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, (cplx*)d_arena);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -274,6 +387,6 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, int ngroups, int ctas_p
   else
     pxm_ring_fft_kernel<1><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, (cplx*)pix, pix_chain_stride, F,
                                                                  nld, (const cplx*)d_arena);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }

@@ -253,7 +253,7 @@ int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* 
   }
   dim3 grid(nitems, nld / BN);
   kern<<<grid, 256, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   return PXM_OK;
 }
 
@@ -289,7 +289,7 @@ int pxm_legendre_launch(int orient, const double* tab, const double* b, double* 
       pxm_legendre_naive_kernel<0><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
     else
       pxm_legendre_naive_kernel<1><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
-    PXM_CUDA(cudaGetLastError());
+    PXM_LAUNCHED();
     return PXM_OK;
   }
   if (orient == 0) return launch_orient<0>(tab, b, c, items, segs, nitems, nld, stream);

@@ -22,6 +22,32 @@ static thread_local std::string g_err;
 void pxm_set_error(const std::string& msg) { g_err = msg; }
 static int g_naive = 0;
 int pxm_debug_naive() { return g_naive; }
+long long g_pxm_launches = 0;
+
+// ---- optional per-kernel-class device timing (CUDA events on the launching stream) ----
+// kinds: 0 Legendre contraction, 1 ring FFT, 2 elementwise/reduction/sparse
+namespace {
+struct ProfEv {
+  cudaEvent_t e0, e1;
+  int kind;
+};
+bool g_prof_on = false;
+std::vector<ProfEv> g_prof_pool;
+size_t g_prof_used = 0;
+struct ProfScope {
+  cudaStream_t st;
+  ProfEv* ev = nullptr;
+  ProfScope(int kind, cudaStream_t s) : st(s) {
+    if (!g_prof_on || g_prof_used >= g_prof_pool.size()) return;
+    ev = &g_prof_pool[g_prof_used++];
+    ev->kind = kind;
+    cudaEventRecord(ev->e0, st);
+  }
+  ~ProfScope() {
+    if (ev) cudaEventRecord(ev->e1, st);
+  }
+};
+}  // namespace
 
 namespace {
 
@@ -327,6 +353,41 @@ extern "C" {
 
 const char* pxm_last_error(void) { return g_err.c_str(); }
 
+int pxm_profile_begin(int max_events) {
+  for (auto& e : g_prof_pool) {
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  g_prof_pool.assign((size_t)std::max(max_events, 0), ProfEv());
+  for (auto& e : g_prof_pool) {
+    PXM_CUDA(cudaEventCreate(&e.e0));
+    PXM_CUDA(cudaEventCreate(&e.e1));
+  }
+  g_prof_used = 0;
+  g_prof_on = true;
+  return PXM_OK;
+}
+
+int pxm_profile_end(double* ms_by_kind, long long* count_by_kind) {
+  g_prof_on = false;
+  PXM_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < 3; ++k) {
+    ms_by_kind[k] = 0.0;
+    count_by_kind[k] = 0;
+  }
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, g_prof_pool[i].e0, g_prof_pool[i].e1) == cudaSuccess) {
+      ms_by_kind[g_prof_pool[i].kind] += ms;
+      count_by_kind[g_prof_pool[i].kind] += 1;
+    }
+  }
+  g_prof_used = 0;
+  return PXM_OK;
+}
+
+long long pxm_launch_count(void) { return g_pxm_launches; }
+
 int pxm_debug_set_naive(int on) {
   g_naive = on;
   return PXM_OK;
@@ -416,18 +477,18 @@ static int sht_run(pxm_sht_plan* p, int which, void* d_flm, void* d_f, int nb, c
   if (which == 0 || which == 3) {  // harmonic -> pixel
     PXM_TRY(pxm_launch_lm_convert(1, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
     Stage& S = which == 0 ? p->s_lam : p->s_w;
-    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
-                                st, naive));
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+                                st, naive)); }
     FftStage& F = which == 0 ? p->fft_out_unit : p->fft_out_norm;
-    PXM_TRY(pxm_fft_launch(1, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
-                           p->ffttab.d_arena, nb, st));
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, st)); }
   } else {  // pixel -> harmonic
     FftStage& F = which == 2 ? p->fft_in_unit : p->fft_in_norm;
-    PXM_TRY(pxm_fft_launch(0, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
-                           p->ffttab.d_arena, nb, st));
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, st)); }
     Stage& S = which == 2 ? p->a_lam : p->a_w;
-    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
-                                st, naive));
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+                                st, naive)); }
     PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
   }
   return PXM_OK;
@@ -660,23 +721,23 @@ static int wav_run(pxm_wav_plan* p, int which, void* d_coef, void* d_pix, int nb
   const size_t npix = (size_t)p->L * (2 * p->L - 1);
   const bool coef_to_pix = (which == 0 || which == 3);
   if (coef_to_pix) {
-    PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
-                           d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
-    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_multi.d_items.d, D.a_multi.d_segs.d,
-                                (int)D.a_multi.items.size(), p->nld, st, naive));
-    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_full.d_items.d, D.s_full.d_segs.d,
-                                (int)D.s_full.items.size(), p->nld, st, naive));
-    PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
-                           d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
+                           d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                                (int)D.a_multi.items.size(), p->nld, st, naive)); }
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_full.d_items.d, D.s_full.d_segs.d,
+                                (int)D.s_full.items.size(), p->nld, st, naive)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
+                           d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
   } else {
-    PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
-                           npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
-    PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_full.d_items.d, D.a_full.d_segs.d,
-                                (int)D.a_full.items.size(), p->nld, st, naive));
-    PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_multi.d_items.d, D.s_multi.d_segs.d,
-                                (int)D.s_multi.items.size(), p->nld, st, naive));
-    PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, (int)D.fft_scales_out.groups.size(),
-                           D.fft_scales_out.ctas, d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st));
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
+                           npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_full.d_items.d, D.a_full.d_segs.d,
+                                (int)D.a_full.items.size(), p->nld, st, naive)); }
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+                                (int)D.s_multi.items.size(), p->nld, st, naive)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, (int)D.fft_scales_out.groups.size(),
+                           D.fft_scales_out.ctas, d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
   }
   return PXM_OK;
 }
@@ -699,6 +760,7 @@ int pxm_wav_analysis_adjoint(pxm_wav_plan* p, const void* d_coef, void* d_pix, i
 // =========================================================================
 int pxm_soft(int is_complex, const void* d_x, const double* d_T, double T_scalar, void* d_out, long long n,
              long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_soft(is_complex, d_x, d_T, T_scalar, d_out, (size_t)n, (size_t)nchains, (cudaStream_t)stream);
 }
 
@@ -706,12 +768,14 @@ int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, c
                      const double* d_w_re, const double* d_w_im, void* d_Xout, void* d_prox_out, long long n,
                      long long nchains, double delta, double lmda, int noise_mode, unsigned long long seed,
                      unsigned long long step, unsigned int stream0, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, d_w_re, d_w_im, d_Xout, d_prox_out, (size_t)n,
                           (size_t)nchains, delta, lmda, noise_mode, seed, step, stream0, (cudaStream_t)stream);
 }
 
 int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,
                      long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_resid(d_preds, d_data, d_invcov, d_out, (size_t)n, (size_t)nchains, (cudaStream_t)stream);
 }
 
@@ -719,6 +783,7 @@ int pxm_reduce_scratch_elems(void) { return 148; }
 
 int pxm_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w, double delta,
                double lmda, long long n, long long nchains, void* d_partial, void* d_out, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   PXM_REQUIRE(kind >= 0 && kind <= 2, "reduce kind");
   return pxm_launch_reduce(kind, a, b, c, d, w, delta, lmda, (size_t)n, (size_t)nchains, d_partial, d_out,
                            (cudaStream_t)stream);
@@ -726,33 +791,39 @@ int pxm_reduce(int kind, const void* a, const void* b, const void* c, const void
 
 int pxm_lincomb(int nx, const void* const* d_xs, const double* coefs, const double* d_z, double cz, double c0,
                 void* d_out, long long total, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   PXM_REQUIRE(nx >= 0 && nx <= 4, "lincomb supports up to 4 terms");
   return pxm_launch_lincomb(nx, d_xs, coefs, d_z, cz, c0, d_out, (size_t)total, (cudaStream_t)stream);
 }
 
 int pxm_gradlogpi(const void* d_X, const void* d_prox, const double* d_T, double T_scalar, const void* d_gradg,
                   double lmda, void* d_out, long long n, long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_gradlogpi(d_X, d_prox, d_T, T_scalar, d_gradg, lmda, d_out, (size_t)n, (size_t)nchains,
                               (cudaStream_t)stream);
 }
 
 int pxm_masked_gather(const void* d_full, const int* d_idx, const double* d_w, void* d_sel, long long nsel,
                       long long nfull, long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_gather(0, d_full, d_idx, d_w, d_sel, (size_t)nsel, (size_t)nfull, (size_t)nchains,
                            (cudaStream_t)stream);
 }
 int pxm_masked_scatter(const void* d_sel, const int* d_idx, const double* d_w, void* d_full, long long nsel,
                        long long nfull, long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_gather(1, d_sel, d_idx, d_w, d_full, (size_t)nsel, (size_t)nfull, (size_t)nchains,
                            (cudaStream_t)stream);
 }
 
 int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_r2c(d_x, d_out, (size_t)total, (cudaStream_t)stream);
 }
 
 int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
                  int nrows, long long ncols, long long nchains, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_csr_spmv(d_indptr, d_indices, d_vals, d_x, d_y, nrows, (size_t)ncols, (size_t)nchains,
                              (cudaStream_t)stream);
 }

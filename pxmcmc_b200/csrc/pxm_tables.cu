@@ -179,7 +179,7 @@ int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_
   const long long total = (long long)T.nslots * T.rings;
   k_wigner_tiles<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_tab, ds.d, T.nslots, T.rings, T.grid_L, T.lmax,
                                                                    T.spin, d_g);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   PXM_CUDA(cudaStreamSynchronize(st));
   ds.release();
   return PXM_OK;
@@ -201,11 +201,11 @@ int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cu
   PXM_CUDA(cudaMalloc(&d_Q, sizeof(double) * qsz * 2));
   PXM_CUDA(cudaMemsetAsync(d_Q, 0, sizeof(double) * qsz * 2, st));
   k_quad_weights<<<(nf + 127) / 128, 128, 0, st>>>(d_wr, Lf);
-  PXM_CUDA(cudaGetLastError());
+  PXM_LAUNCHED();
   for (int par = 0; par < 2; ++par) {
     const long long tot = (long long)Lf * ell;
     k_build_Q<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(d_Q + par * qsz, d_wr, ell, Lf, par, nldq);
-    PXM_CUDA(cudaGetLastError());
+    PXM_LAUNCHED();
   }
   // process slots in chunks to bound the temporary fine-grid tables
   const size_t budget = (size_t)96 << 20;  // doubles (768 MB) for fine tables + C
@@ -292,7 +292,7 @@ int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cu
     PXM_TRY(dco.upload(c_off));
     dim3 grid(64, F.nslots);
     k_c_to_tiles<<<grid, 256, 0, st>>>(d_C, dco.d, dfs.d, F.nslots, ell, nldq, d_g, d_tab);
-    PXM_CUDA(cudaGetLastError());
+    PXM_LAUNCHED();
     PXM_CUDA(cudaStreamSynchronize(st));
     di.release();
     dsg.release();

@@ -257,12 +257,8 @@ class MYULA(PxMCMC):
         i = 0
         j = 0
         X_curr, curr_preds = self._initial_sample(start_point)
-        fused = self._fused_prox() is not None
         while j < self.nsamples:
-            gradg = D.to_dev_c(self._gradg_dev(curr_preds))
-            proxf = None if fused else self._proxf_dev(X_curr)
-            X_curr = self._propose_dev(X_curr, proxf, gradg)
-            curr_preds = D.to_dev_c(self._forward_dev(X_curr))
+            X_curr, curr_preds = self.iterate(X_curr, curr_preds)
             if i >= self.nburn:
                 if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
                     logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
@@ -277,6 +273,33 @@ class MYULA(PxMCMC):
             i += 1
         self._final_state = (X_curr, curr_preds)
         print("\nDONE")
+
+    def iterate(self, X_curr, curr_preds):
+        """One pass of the loop body (pxmcmc/mcmc.py:158-164) on device tensors
+        [nchains, .]: gradg -> prox -> proposal -> new predictions."""
+        gradg = D.to_dev_c(self._gradg_dev(curr_preds))
+        proxf = None if self._fused_prox() is not None else self._proxf_dev(X_curr)
+        X_new = self._propose_dev(X_curr, proxf, gradg)
+        return X_new, D.to_dev_c(self._forward_dev(X_new))
+
+    def iterate_host(self, X_host, preds_host, X_out=None, preds_out=None):
+        """The same iteration through HOST buffers (pinned torch CPU tensors or numpy
+        arrays [nchains, .]): copies the state in, runs the kernels, copies the new
+        state and predictions back.  This is the end-to-end path bench.py times."""
+        dv = D.dev()
+        xh = X_host if D.is_dev(X_host) else torch.from_numpy(np.ascontiguousarray(X_host, dtype=np.complex128))
+        ph = preds_host if D.is_dev(preds_host) else torch.from_numpy(np.ascontiguousarray(preds_host, dtype=np.complex128))
+        Xd = xh.to(dv, non_blocking=True)
+        Pd = ph.to(dv, non_blocking=True)
+        if Xd.dim() == 1:
+            Xd, Pd = Xd.unsqueeze(0), Pd.unsqueeze(0)
+        Xn, Pn = self.iterate(Xd, Pd)
+        if X_out is not None:
+            X_out.copy_(Xn.reshape(X_out.shape), non_blocking=True)
+            preds_out.copy_(Pn.reshape(preds_out.shape), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return X_out, preds_out
+        return D.to_host(Xn), D.to_host(Pn)
 
     def chain_step(self, X, proxf, gradg):
         """One proposal from (X, prox(X), gradg) (pxmcmc/mcmc.py:185-201)."""
