@@ -194,7 +194,8 @@ def run_ours(args):
     op = SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J_min, nchains=nch)
     prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, track=[])
     reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J_min)
-    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234 + rank)
+    from pxmcmc_b200.sharding import philox_stream0
+    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234, stream0=philox_stream0(nch * world, world, rank))
     ncoef, npix = op.nparams, L * (2 * L - 1)
     rng = np.random.default_rng(7 + rank)
     X = D.to_dev_c(rng.laplace(size=(nch, ncoef)))

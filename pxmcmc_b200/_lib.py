@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpxmcmc_b200.so")
+LIB_PATH = os.environ.get("PXM_LIB", os.path.join(_HERE, "libpxmcmc_b200.so"))
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -113,7 +113,7 @@ struct PxmFftGroup {
   int cta_begin;    // first CTA (within one chain) of this group
   int nslots;       // ell (paired +-m, spin 0) or 2*ell-1
   int paired;       // 1: slot = |m|, 4 columns per chain; 0: slot = m+ell-1, 2 columns per chain
-  int pad;
+  int pad;          // log2(rings_per_cta)
   double scale;     // applied to every output
   unsigned long long pix_off;       // complex elements: start of this map inside one chain's pixel vector
   unsigned long long f_off;         // doubles: start of this grid's ring-Fourier array

@@ -124,31 +124,53 @@ __device__ __forceinline__ void dftR(cplx* x) {
   if (R == 16) dft16<INV>(x);
 }
 
-// One in-place pass over `nr` rings (padded stride MP): sub-transform length 2^lgLs,
-// radix R.  Forward (DIF): butterfly then twiddle; inverse (DIT): conj-twiddle then butterfly.
+// One in-place pass over 2^lgnr rings (padded stride MP): sub-transform length 2^lgLs,
+// radix R, element stride S = Ls/R >= 16 (so the padded address is affine in k).
+// Forward (DIF): butterfly then twiddle; inverse (DIT): conj-twiddle then butterfly.
 template <int R, bool INV>
-__device__ __forceinline__ void fft_pass(cplx* s, int nr, int M, int MP, int lgLs, const cplx* __restrict__ tw) {
+__device__ __forceinline__ void fft_pass(cplx* s, int lgnr, int lgM, int MP, int lgLs, const cplx* __restrict__ tw) {
   constexpr int lgR = R == 2 ? 1 : R == 4 ? 2 : R == 8 ? 3 : 4;
-  const int lgS = lgLs - lgR, S = 1 << lgS, nbf = M >> lgR, tstep = M >> lgLs;
-  for (int idx = threadIdx.x; idx < nr * nbf; idx += blockDim.x) {
-    const int r = idx / nbf, b = idx - r * nbf;
+  const int lgS = lgLs - lgR, S = 1 << lgS, lgnbf = lgM - lgR, tstep = 1 << (lgM - lgLs);
+  const int stride = S + (S >> 4);
+  const int total = 1 << (lgnr + lgnbf);
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx >> lgnbf, b = idx & ((1 << lgnbf) - 1);
     const int blk = b >> lgS, j = b & (S - 1);
-    cplx* p = s + r * MP;
-    const int base = (blk << lgLs) + j;
+    cplx* p = s + r * MP + padi((blk << lgLs) + j);
     cplx x[R];
 #pragma unroll
-    for (int k = 0; k < R; ++k) x[k] = p[padi(base + (k << lgS))];
-    if (INV && lgS > 0) {
+    for (int k = 0; k < R; ++k) x[k] = p[k * stride];
+    // twiddles w^k, k < R, from ONE table load; the powers are formed on the fly in
+    // two interleaved chains (even / odd exponents, <= 8 products deep => a few ulp),
+    // which keeps the L1TEX pipe free for the shared-memory exchange
+    if (INV) {
+      cplx w1 = tw[j * tstep];
+      w1.y = -w1.y;
+      const cplx w2 = cmul(w1, w1);
+      cplx wo = w1, we = w2;
 #pragma unroll
-      for (int k = 1; k < R; ++k) x[k] = cmulc(x[k], tw[(j * k * tstep) & (M - 1)]);
+      for (int k = 1; k < R; k += 2) {
+        x[k] = cmul(x[k], wo);
+        if (k + 1 < R) x[k + 1] = cmul(x[k + 1], we);
+        wo = cmul(wo, w2);
+        we = cmul(we, w2);
+      }
+      dftR<R, INV>(x);
+    } else {
+      dftR<R, INV>(x);
+      const cplx w1 = tw[j * tstep];
+      const cplx w2 = cmul(w1, w1);
+      cplx wo = w1, we = w2;
+#pragma unroll
+      for (int k = 1; k < R; k += 2) {
+        x[k] = cmul(x[k], wo);
+        if (k + 1 < R) x[k + 1] = cmul(x[k + 1], we);
+        wo = cmul(wo, w2);
+        we = cmul(we, w2);
+      }
     }
-    dftR<R, INV>(x);
-    if (!INV && lgS > 0) {
 #pragma unroll
-      for (int k = 1; k < R; ++k) x[k] = cmul(x[k], tw[(j * k * tstep) & (M - 1)]);
-    }
-#pragma unroll
-    for (int k = 0; k < R; ++k) p[padi(base + (k << lgS))] = x[k];
+    for (int k = 0; k < R; ++k) p[k * stride] = x[k];
   }
   __syncthreads();
 }
@@ -156,44 +178,48 @@ __device__ __forceinline__ void fft_pass(cplx* s, int nr, int M, int MP, int lgL
 __device__ __forceinline__ int first_radix_log(int logM) { return logM & 3; }  // 0 -> only radix-16 passes
 
 // forward passes except the last (Ls = 16) one
-__device__ void fft_forward_head(cplx* s, int nr, int M, int MP, int logM, const cplx* __restrict__ tw) {
-  int lgLs = logM;
-  const int f = first_radix_log(logM);
+__device__ void fft_forward_head(cplx* s, int lgnr, int lgM, int MP, const cplx* __restrict__ tw) {
+  int lgLs = lgM;
+  const int f = first_radix_log(lgM);
   if (f == 1) {
-    fft_pass<2, false>(s, nr, M, MP, lgLs, tw);
+    fft_pass<2, false>(s, lgnr, lgM, MP, lgLs, tw);
     lgLs -= 1;
   } else if (f == 2) {
-    fft_pass<4, false>(s, nr, M, MP, lgLs, tw);
+    fft_pass<4, false>(s, lgnr, lgM, MP, lgLs, tw);
     lgLs -= 2;
   } else if (f == 3) {
-    fft_pass<8, false>(s, nr, M, MP, lgLs, tw);
+    fft_pass<8, false>(s, lgnr, lgM, MP, lgLs, tw);
     lgLs -= 3;
   }
-  for (; lgLs > 4; lgLs -= 4) fft_pass<16, false>(s, nr, M, MP, lgLs, tw);
+  for (; lgLs > 4; lgLs -= 4) fft_pass<16, false>(s, lgnr, lgM, MP, lgLs, tw);
 }
 // inverse passes except the first (Ls = 16) one
-__device__ void fft_inverse_tail(cplx* s, int nr, int M, int MP, int logM, const cplx* __restrict__ tw) {
-  const int f = first_radix_log(logM);
-  const int top16 = logM - f;  // largest Ls handled by radix-16 passes
-  for (int lgLs = 8; lgLs <= top16; lgLs += 4) fft_pass<16, true>(s, nr, M, MP, lgLs, tw);
-  if (f == 1) fft_pass<2, true>(s, nr, M, MP, logM, tw);
-  if (f == 2) fft_pass<4, true>(s, nr, M, MP, logM, tw);
-  if (f == 3) fft_pass<8, true>(s, nr, M, MP, logM, tw);
+__device__ void fft_inverse_tail(cplx* s, int lgnr, int lgM, int MP, const cplx* __restrict__ tw) {
+  const int f = first_radix_log(lgM);
+  const int top16 = lgM - f;  // largest Ls handled by radix-16 passes
+  for (int lgLs = 8; lgLs <= top16; lgLs += 4) fft_pass<16, true>(s, lgnr, lgM, MP, lgLs, tw);
+  if (f == 1) fft_pass<2, true>(s, lgnr, lgM, MP, lgM, tw);
+  if (f == 2) fft_pass<4, true>(s, lgnr, lgM, MP, lgM, tw);
+  if (f == 3) fft_pass<8, true>(s, lgnr, lgM, MP, lgM, tw);
 }
-// middle: last forward pass (contiguous 16 points, no twiddles) x filter spectrum x first inverse pass
-__device__ void fft_middle(cplx* s, int nr, int M, int MP, const cplx* __restrict__ bhat) {
-  const int nbf = M >> 4;
-  for (int idx = threadIdx.x; idx < nr * nbf; idx += blockDim.x) {
-    const int r = idx / nbf, b = idx - r * nbf;
+// middle: last forward pass (contiguous 16 points, no twiddles) x filter spectrum x first inverse
+// pass; bhat == nullptr: plain last forward pass (used to build the filter spectrum itself)
+__device__ void fft_middle(cplx* s, int lgnr, int lgM, int MP, const cplx* __restrict__ bhat) {
+  const int lgnbf = lgM - 4, nbf = 1 << lgnbf;
+  const int total = 1 << (lgnr + lgnbf);
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx >> lgnbf, b = idx & (nbf - 1);
     cplx* p = s + r * MP + b * 17;  // padi(16 b + k) = 17 b + k
-    const cplx* bh = bhat + b * 16;
     cplx x[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) x[k] = p[k];
     dft16<false>(x);
+    if (bhat) {
+      const cplx* bh = bhat + b;  // filter spectrum stored [k][b]: coalesced across the lanes
 #pragma unroll
-    for (int k = 0; k < 16; ++k) x[k] = cmul(x[k], bh[k]);
-    dft16<true>(x);
+      for (int k = 0; k < 16; ++k) x[k] = cmul(x[k], bh[k << lgnbf]);
+      dft16<true>(x);
+    }
 #pragma unroll
     for (int k = 0; k < 16; ++k) p[k] = x[k];
   }
@@ -223,7 +249,7 @@ __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cpl
   extern __shared__ __align__(16) unsigned char fsm[];
   cplx* s = reinterpret_cast<cplx*>(fsm);
   const PxmFftGroup gr = groups[blockIdx.x];
-  const int M = gr.M, MP = M + (M >> 4);
+  const int M = gr.M, MP = M + (M >> 4) + 2;
   const cplx* chirp = arena + gr.chirp_off;
   for (int i = threadIdx.x; i < MP; i += blockDim.x) s[i] = make_double2(0.0, 0.0);
   __syncthreads();
@@ -234,17 +260,21 @@ __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cpl
     if (j > 0) s[padi(M - j)] = b;
   }
   __syncthreads();
-  fft_forward_head(s, 1, M, MP, gr.logM, arena + gr.tw_off);
-  fft_pass<16, false>(s, 1, M, MP, 4, arena + gr.tw_off);
+  fft_forward_head(s, 0, gr.logM, MP, arena + gr.tw_off);
+  fft_middle(s, 0, gr.logM, MP, nullptr);
   cplx* bhat = arena + gr.bhat_off;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) bhat[i] = s[padi(i)];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) bhat[(i & 15) * (M >> 4) + (i >> 4)] = s[padi(i)];
 }
 
 // ---- the ring transform ---------------------------------------------------------
 // DIR 0: pixels -> ring coefficients  F_m[t] = scale * sum_p f[t,p] e^{-i m phi_p}
 // DIR 1: ring coefficients -> pixels  f[t,p] = scale * sum_m F_m[t] e^{+i m phi_p}
+// A CTA owns 2^lgr consecutive rings (a whole number of k4 row-groups when >= 4).
+#ifndef PXM_FFT_MINB
+#define PXM_FFT_MINB 3
+#endif
 template <int DIR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PXM_FFT_MINB)
 pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* __restrict__ pix,
                     size_t pix_chain_stride, double* __restrict__ F, int nld, const cplx* __restrict__ arena) {
   extern __shared__ __align__(16) unsigned char fsm[];
@@ -253,81 +283,97 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
   while (gi + 1 < ngroups && (int)blockIdx.x >= groups[gi + 1].cta_begin) ++gi;
   const PxmFftGroup gr = groups[gi];
   const int chain = blockIdx.y;
-  const int t0 = ((int)blockIdx.x - gr.cta_begin) * gr.rings_per_cta;
-  const int nr = min(gr.rings_per_cta, gr.rings - t0);
-  const int n = gr.n, M = gr.M, ell = gr.ell, lgM = gr.logM;
-  const int MP = M + (M >> 4);
+  const int lgr = gr.pad;  // log2(rings per CTA)
+  const int t0 = ((int)blockIdx.x - gr.cta_begin) << lgr;
+  const int n = gr.n, M = gr.M, ell = gr.ell, lgM = gr.logM, rings = gr.rings;
+  const int MP = M + (M >> 4) + 2;  // +2: the rings of one row-group land in different banks
   const cplx* chirp = arena + gr.chirp_off;
   const cplx* bhat = arena + gr.bhat_off;
   const cplx* tw = arena + gr.tw_off;
   cplx* mypix = pix + (size_t)chain * pix_chain_stride + gr.pix_off;
-  const int colbase = gr.paired ? chain * 4 : chain * 2;
+  // gather / scatter of the k4-interleaved ring array: a thread keeps ONE ring (ring index fastest
+  // across the lanes: the 4 rings of a row-group are adjacent doubles) and walks over m
+  const int rr = threadIdx.x & ((1 << lgr) - 1);
+  const int j0 = threadIdx.x >> lgr, jstep = blockDim.x >> lgr;
+  const int tr = t0 + rr;
+  const bool tvalid = tr < rings;
+  const size_t frow = gr.f_off + ((size_t)(tr >> 2) * (size_t)nld + (size_t)(gr.paired ? chain * 4 : chain * 2)) * 4 +
+                      (size_t)(tr & 3);
+  const size_t sstride = gr.slot_stride;
 
   // 1. load, pre-multiply by the chirp, zero-pad
   if (DIR == 0) {
-    for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
+    const int total = 1 << (lgr + lgM);
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
       const int r = idx >> lgM, j = idx & (M - 1);
       cplx v = make_double2(0.0, 0.0);
-      if (j < n) v = cmul(mypix[(size_t)(t0 + r) * n + j], chirp[j]);
+      if (j < n && t0 + r < rings) v = cmul(mypix[(size_t)(t0 + r) * n + j], chirp[j]);
       s[r * MP + padi(j)] = v;
     }
   } else {
-    // gather F_m[t]: the rings of one k4 row-group are adjacent doubles (t%4) -> loop rings fastest
-    for (int idx = threadIdx.x; idx < nr * M; idx += blockDim.x) {
-      const int r = idx % nr, j = idx / nr;
+    cplx* srow = s + rr * MP;
+#pragma unroll 4
+    for (int j = j0; j < M; j += jstep) {
       cplx v = make_double2(0.0, 0.0);
-      if (j < n) {
-        const int t = t0 + r;
+      if (j < n && tvalid) {
         const int m = (j < ell) ? j : j - n;
         size_t base;
         double sg = 1.0;
         if (gr.paired) {
           const int am = m < 0 ? -m : m;
-          base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, colbase + (m < 0 ? 2 : 0), nld);
+          base = frow + (size_t)am * sstride + (m < 0 ? 8 : 0);
           if (m < 0 && (am & 1)) sg = -1.0;
         } else {
-          base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, colbase, nld);
+          base = frow + (size_t)(m + ell - 1) * sstride;
         }
         // conj on load: x_p = conj( DFT( conj(F) ) )
         v = cmul(make_double2(sg * F[base], -sg * F[base + 4]), chirp[j]);
       }
-      s[r * MP + padi(j)] = v;
+      srow[padi(j)] = v;
     }
   }
   __syncthreads();
   // 2. circular convolution with the chirp filter
-  fft_forward_head(s, nr, M, MP, lgM, tw);
-  fft_middle(s, nr, M, MP, bhat);
-  fft_inverse_tail(s, nr, M, MP, lgM, tw);
+  fft_forward_head(s, lgr, lgM, MP, tw);
+  fft_middle(s, lgr, lgM, MP, bhat);
+  fft_inverse_tail(s, lgr, lgM, MP, tw);
   // 3. post-multiply, scale, scatter
   const double sc = gr.scale / (double)M;
   if (DIR == 0) {
-    for (int idx = threadIdx.x; idx < nr * n; idx += blockDim.x) {
-      const int r = idx % nr, k = idx / nr;
-      const int t = t0 + r;
-      cplx v = cmul(s[r * MP + padi(k)], chirp[k]);
-      v.x *= sc;
-      v.y *= sc;
-      const int m = (k < ell) ? k : k - n;
-      size_t base;
-      if (gr.paired) {
-        const int am = m < 0 ? -m : m;
-        base = gr.f_off + (size_t)am * gr.slot_stride + pxm_il_index(t, colbase + (m < 0 ? 2 : 0), nld);
-        if (m < 0 && (am & 1)) {
-          v.x = -v.x;
-          v.y = -v.y;
+    if (tvalid) {
+      const cplx* srow = s + rr * MP;
+#pragma unroll 2
+      for (int k = j0; k < n; k += jstep) {
+        cplx v = cmul(srow[padi(k)], chirp[k]);
+        v.x *= sc;
+        v.y *= sc;
+        const int m = (k < ell) ? k : k - n;
+        size_t base;
+        if (gr.paired) {
+          const int am = m < 0 ? -m : m;
+          base = frow + (size_t)am * sstride + (m < 0 ? 8 : 0);
+          if (m < 0 && (am & 1)) {
+            v.x = -v.x;
+            v.y = -v.y;
+          }
+        } else {
+          base = frow + (size_t)(m + ell - 1) * sstride;
         }
-      } else {
-        base = gr.f_off + (size_t)(m + ell - 1) * gr.slot_stride + pxm_il_index(t, colbase, nld);
+        F[base] = v.x;
+        F[base + 4] = v.y;  // next column in the k4-interleaved layout
       }
-      F[base] = v.x;
-      F[base + 4] = v.y;  // next column in the k4-interleaved layout
     }
   } else {
-    for (int idx = threadIdx.x; idx < nr * n; idx += blockDim.x) {
-      const int r = idx / n, k = idx - r * n;
-      cplx v = cmul(s[r * MP + padi(k)], chirp[k]);
-      mypix[(size_t)(t0 + r) * n + k] = make_double2(v.x * sc, -v.y * sc);
+    const int nr = min(1 << lgr, rings - t0);
+    for (int r = 0; r < nr; ++r) {
+      const cplx* srow = s + r * MP;
+      cplx* prow = mypix + (size_t)(t0 + r) * n;
+#pragma unroll 2
+      for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const cplx v = cmul(srow[padi(k)], chirp[k]);
+        prow[k] = make_double2(v.x * sc, -v.y * sc);
+      }
     }
   }
 }
@@ -344,14 +390,14 @@ int pxm_fft_choose_M(int n, int* logM) {
   return M;
 }
 
-int pxm_fft_rings_per_cta(int M) {
-  int r = 4096 / M;
-  if (r < 1) r = 1;
-  if (r > 16) r = 16;
-  return r;
+// log2 of the rings one CTA transforms (4096 points per CTA, at most 16 rings)
+int pxm_fft_rings_per_cta_log(int M) {
+  int lg = 0;
+  while ((M << (lg + 1)) <= 4096 && lg < 4) ++lg;
+  return lg;
 }
 
-constexpr int PXM_FFT_SMEM = (4096 + 256) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
+constexpr int PXM_FFT_SMEM = (4096 + 256 + 32) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
 
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
                          cudaStream_t stream) {

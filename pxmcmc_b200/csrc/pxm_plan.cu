@@ -177,7 +177,8 @@ struct FftTables {
 void add_fft_group(FftStage& S, FftTables& tabs, const RingBuf& R, ull pix_off, double scale) {
   PxmFftGroup g = tabs.get(R.ell);
   g.rings = R.ell;
-  g.rings_per_cta = pxm_fft_rings_per_cta(g.M);
+  g.pad = pxm_fft_rings_per_cta_log(g.M);  // log2(rings per CTA)
+  g.rings_per_cta = 1 << g.pad;
   g.cta_begin = S.ctas;
   g.nslots = R.nslots;
   g.paired = R.paired ? 1 : 0;

@@ -52,7 +52,7 @@ int pxm_legendre_pad_columns(int ncols);
 int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
                         const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive);
 int pxm_fft_choose_M(int n, int* logM);
-int pxm_fft_rings_per_cta(int M);
+int pxm_fft_rings_per_cta_log(int M);
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
                          cudaStream_t stream);
 int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, int ngroups, int ctas_per_chain, void* pix,

@@ -60,7 +60,7 @@ def _cplx_lt(a, b):
 class PxMCMC:
     """Common machinery (pxmcmc/mcmc.py:46-140)."""
 
-    def __init__(self, forward, prior, mcmcparams=PxMCMCParams(), *, noise="host", nchains=1, seed=0):
+    def __init__(self, forward, prior, mcmcparams=PxMCMCParams(), *, noise="host", nchains=1, seed=0, stream0=0):
         self.forward = forward
         self.prior = prior
         for attr in mcmcparams.__dict__.keys():
@@ -70,6 +70,7 @@ class PxMCMC:
         self.noise = noise
         self.nchains = int(nchains)
         self.seed = int(seed)
+        self.stream0 = int(stream0)  # global index of this sampler's first chain (Philox stream id)
         self._step_counter = 0
         self._initialise_tracking_arrays()
 
@@ -249,7 +250,8 @@ class MYULA(PxMCMC):
         else:
             self._step_counter += 1
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
-                                     noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter)
+                                     noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter,
+                                     stream0=self.stream0)
         return out
 
     def run(self, start_point=None):
