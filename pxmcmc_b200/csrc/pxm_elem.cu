@@ -147,6 +147,34 @@ __global__ void k_myula_update(MyulaArgs p) {
   }
 }
 
+// Philox real-noise variant: one Box-Muller pair serves two consecutive coefficients, so a
+// thread updates elements (2p, 2p+1) of one chain (halves the transcendental work; the noise
+// stream is identical to the per-element kernel: element e uses normal (e&1) of pair e>>1)
+__global__ void k_myula_update_pair(MyulaArgs p) {
+  const size_t npairs = (p.n + 1) >> 1;
+  const size_t nchains = p.total / p.n;
+  const size_t tot = npairs * nchains;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t chain = q / npairs, pr = q - chain * npairs;
+    double z[2];
+    philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, pr, &z[0], &z[1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const size_t e = 2 * pr + h;
+      if (e >= p.n) break;
+      const size_t i = chain * p.n + e;
+      const cplx x = p.X[i];
+      const cplx px = p.prox ? p.prox[i] : soft_c(x, p.Tv ? p.Tv[e] : p.Ts);
+      if (p.prox_out) p.prox_out[i] = px;
+      const cplx g = p.gradg[i];
+      cplx o;
+      o.x = ((p.a * x.x + p.b * px.x) - p.delta * g.x) + p.sq2d * z[h];
+      o.y = ((p.a * x.y + p.b * px.y) - p.delta * g.y) + p.sq2d * 0.0;
+      p.Xout[i] = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // data-fidelity residual (/root/reference/pxmcmc/forward.py:66-69):
 //   r = invcov (.) (preds - data), invcov diagonal, possibly complex (:80-82)
@@ -439,7 +467,10 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
   p.step = step;
   p.stream0 = stream0;
   if (!p.total) return PXM_OK;
-  k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
+  if (noise_mode == 2)
+    k_myula_update_pair<<<grid_for((p.total + 1) / 2), 256, 0, st>>>(p);
+  else
+    k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
   PXM_LAUNCHED();
   return PXM_OK;
 }

@@ -56,92 +56,104 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
                : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int LEG_CONSUMER_WARPS = 8;
+constexpr int LEG_THREADS = (LEG_CONSUMER_WARPS + 1) * 32;  // + one TMA producer warp
+
 template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
 struct LegCfg {
   static constexpr int BM = 64;
-  static constexpr int BK = ORIENT == 0 ? 16 : 32;
-  static constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;
-  static constexpr int NT_M = BM / TILE_ROWS;
-  static constexpr int A_STAGE = NT_M * PXM_TILE_DOUBLES;
+  static constexpr int BK = 16;                             // k rows per pipeline stage
+  static constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;  // output rows covered by one table tile
+  static constexpr int NT_M = BM / TILE_ROWS;              // 2 full tiles (S) or 4 half tiles (A) per stage
+  static constexpr int A_PIECE = ORIENT == 0 ? PXM_TILE_DOUBLES : PXM_TILE_DOUBLES / 2;
+  static constexpr int A_STAGE = NT_M * A_PIECE;            // 1024 doubles = 8 KB
   static constexpr int B_STAGE = BK * BN;
   static constexpr int WM = BM / WARPS_M;
   static constexpr int WN = BN / WARPS_N;
   static constexpr int MI = WM / 8;
   static constexpr int NI = WN / 8;
   static constexpr size_t SMEM = 128 + (size_t)STAGES * (A_STAGE + B_STAGE) * sizeof(double);
-  static_assert(WARPS_M * WARPS_N == 8, "8 warps");
+  static_assert(WARPS_M * WARPS_N == LEG_CONSUMER_WARPS, "8 consumer warps");
   static_assert(MI >= 1 && NI >= 1, "warp tile");
+  static_assert(2 * STAGES * 8 <= 128, "barrier area");
 };
 
+// ORIENT 0: a k-stage is one 16-degree block: NT_M = 2 full 32x16 tiles (rows = rings).
+// ORIENT 1: a k-stage is HALF a ring block (16 rings): 4 half tiles (rows = degrees); the
+//           descriptor's nk counts ring blocks, i.e. two stages each.
 template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(LEG_THREADS, 2)
 pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ bmat,
                     double* __restrict__ cmat, const PxmLegItem* __restrict__ items,
                     const PxmLegSeg* __restrict__ segs, int nld) {
   using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* empty = full + STAGES;
   double* sA = reinterpret_cast<double*>(smem_raw + 128);
   double* sB = sA + STAGES * C::A_STAGE;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, q = lane & 3;
-  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   const PxmLegItem item = items[blockIdx.x];
   const int n0 = blockIdx.y * BN;
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], LEG_CONSUMER_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncthreads();
 
-  // ---- producer cursor (thread 0 only) -----------------------------------
-  int pseg = 0, pk = 0, pit = 0;
-  int total = 0;
-  for (int s = 0; s < item.seg_count; ++s) total += segs[item.seg_begin + s].nk;
-
-  auto produce = [&]() {
-    // skip empty segments
-    while (pseg < item.seg_count && pk >= segs[item.seg_begin + pseg].nk) {
-      ++pseg;
-      pk = 0;
-    }
-    if (pseg >= item.seg_count) return;
-    const PxmLegSeg sg = segs[item.seg_begin + pseg];
-    const int slot = pit % STAGES;
-    uint64_t* bar = &full[slot];
-    const uint32_t bytes = (uint32_t)(sg.nmt * PXM_TILE_DOUBLES * 8 + C::BK * BN * 8);
-    mbar_expect_tx(bar, bytes);
-    double* dstA = sA + slot * C::A_STAGE + sg.mt0 * PXM_TILE_DOUBLES;
-    const double* srcA = tab + sg.a_off + (size_t)pk * (size_t)sg.a_kstride;
-    if (sg.a_mstride == PXM_TILE_DOUBLES) {
-      bulk_g2s(dstA, srcA, (uint32_t)(sg.nmt * PXM_TILE_DOUBLES * 8), bar);
-    } else {
-      for (int j = 0; j < sg.nmt; ++j)
-        bulk_g2s(dstA + j * PXM_TILE_DOUBLES, srcA + (size_t)j * (size_t)sg.a_mstride,
-                 PXM_TILE_DOUBLES * 8, bar);
-    }
-    double* dstB = sB + slot * C::B_STAGE;
-    const double* srcB = bmat + sg.b_off + ((size_t)pk * (C::BK / 4) * (size_t)nld + (size_t)n0) * 4;
-    if (BN == nld) {
-      bulk_g2s(dstB, srcB, (uint32_t)(C::BK * BN * 8), bar);
-    } else {
+  if (warp == LEG_CONSUMER_WARPS) {
+    // ===================== TMA producer warp (one elected lane) =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int s = 0; s < item.seg_count; ++s) {
+        const PxmLegSeg sg = segs[item.seg_begin + s];
+        const int nst = ORIENT == 0 ? sg.nk : 2 * sg.nk;
+        const uint32_t bytes = (uint32_t)(sg.nmt * C::A_PIECE * 8 + C::BK * BN * 8);
+        for (int k = 0; k < nst; ++k, ++it) {
+          const int slot = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty[slot], (uint32_t)(((it / STAGES) - 1) & 1));
+          uint64_t* bar = &full[slot];
+          mbar_expect_tx(bar, bytes);
+          double* dstA = sA + slot * C::A_STAGE + sg.mt0 * C::A_PIECE;
+          if (ORIENT == 0) {
+            const double* srcA = tab + sg.a_off + (size_t)k * (size_t)sg.a_kstride;
+            for (int j = 0; j < sg.nmt; ++j)
+              bulk_g2s(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
+          } else {
+            const double* srcA = tab + sg.a_off + (size_t)(k >> 1) * (size_t)sg.a_kstride + (k & 1) * C::A_PIECE;
+            for (int j = 0; j < sg.nmt; ++j)
+              bulk_g2s(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
+          }
+          double* dstB = sB + slot * C::B_STAGE;
+          const double* srcB = bmat + sg.b_off + ((size_t)k * (C::BK / 4) * (size_t)nld + (size_t)n0) * 4;
+          if (BN == nld) {
+            bulk_g2s(dstB, srcB, (uint32_t)(C::BK * BN * 8), bar);
+          } else {
 #pragma unroll
-      for (int rg = 0; rg < C::BK / 4; ++rg)
-        bulk_g2s(dstB + rg * BN * 4, srcB + (size_t)rg * (size_t)nld * 4, BN * 32, bar);
+            for (int rg = 0; rg < C::BK / 4; ++rg)
+              bulk_g2s(dstB + rg * BN * 4, srcB + (size_t)rg * (size_t)nld * 4, BN * 32, bar);
+          }
+        }
+      }
     }
-    ++pk;
-    ++pit;
-  };
-
-  if (tid == 0) {
-    for (int s = 0; s < STAGES - 1 && s < total; ++s) produce();
+    return;
   }
 
+  // ================================ consumer warps ================================
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
   double acc[C::MI][C::NI][2];
 #pragma unroll
   for (int mi = 0; mi < C::MI; ++mi)
@@ -150,7 +162,7 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
 
   int it = 0;
   for (int s = 0; s < item.seg_count; ++s) {
-    const int seg_nk = segs[item.seg_begin + s].nk;
+    const int seg_nst = (ORIENT == 0 ? 1 : 2) * segs[item.seg_begin + s].nk;
     const int seg_mt0 = segs[item.seg_begin + s].mt0;
     const int seg_mt1 = seg_mt0 + segs[item.seg_begin + s].nmt;
     bool mv[C::MI];
@@ -159,8 +171,7 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
       const int tl = (wm * C::WM + mi * 8) / C::TILE_ROWS;
       mv[mi] = (tl >= seg_mt0) && (tl < seg_mt1);
     }
-    for (int k = 0; k < seg_nk; ++k, ++it) {
-      if (tid == 0 && pit < total) produce();
+    for (int k = 0; k < seg_nst; ++k, ++it) {
       const int slot = it % STAGES;
       mbar_wait(&full[slot], (uint32_t)((it / STAGES) & 1));
       const double* a_s = sA + slot * C::A_STAGE;
@@ -173,10 +184,10 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
           const int row = wm * C::WM + mi * 8 + g;
           if (ORIENT == 0) {
             const int tl = row >> 5, r = row & 31;
-            a[mi] = a_s[tl * PXM_TILE_DOUBLES + r * PXM_TILE_L + (((kk ^ (r & 3)) << 2) | q)];
+            a[mi] = a_s[tl * C::A_PIECE + r * PXM_TILE_L + (((kk ^ (r & 3)) << 2) | q)];
           } else {
             const int tl = row >> 4, c = row & 15, r = kk * 4 + q;
-            a[mi] = a_s[tl * PXM_TILE_DOUBLES + r * PXM_TILE_L + (c ^ (q << 2))];
+            a[mi] = a_s[tl * C::A_PIECE + r * PXM_TILE_L + (c ^ (q << 2))];
           }
         }
 #pragma unroll
@@ -189,7 +200,8 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
           }
         }
       }
-      __syncthreads();  // everyone done with `slot` before thread 0 refills it next iteration
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[slot]);  // this warp is done with the slot
     }
   }
 
@@ -252,19 +264,31 @@ int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* 
     configured = true;
   }
   dim3 grid(nitems, nld / BN);
-  kern<<<grid, 256, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
+  kern<<<grid, LEG_THREADS, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
   PXM_LAUNCHED();
   return PXM_OK;
 }
 
+// warp layouts: contraction over l (ORIENT 0) splits rows x columns 2x4; contraction over rings
+// (ORIENT 1) gives every warp all 64 degrees (1x8), so that segments whose l-support covers only
+// part of the tile (wavelet scales) keep all eight warps equally busy
 template <int ORIENT>
 int launch_orient(const double* tab, const double* b, double* c, const PxmLegItem* items, const PxmLegSeg* segs,
                   int nitems, int nld, cudaStream_t stream) {
-  if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
-  if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
-  if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
-  if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
-  if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, (ORIENT == 0 ? 6 : 4)>(tab, b, c, items, segs, nitems, nld, stream);
+  constexpr int ST = 4;
+  if (ORIENT == 0) {
+    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, ST>(tab, b, c, items, segs, nitems, nld, stream);
+  } else {
+    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 64) return launch_cfg<ORIENT, 64, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, ST>(tab, b, c, items, segs, nitems, nld, stream);
+  }
   pxm_set_error("legendre: unsupported column count " + std::to_string(nld));
   return PXM_ERR_ARG;
 }
