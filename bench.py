@@ -279,6 +279,10 @@ def run_ours(args):
 
     if rank == 0:
         peak = dgemm_peak()
+        try:
+            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:  # noqa: BLE001
+            hbm_peak = 6650.0  # fallback stated in B200_PROFILING.md
         flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
         leg_ms, leg_n = ms_kind[0], cnt_kind[0]
         achieved = flops_step * args.steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else None
@@ -297,11 +301,23 @@ def run_ours(args):
             "stage_ms_per_step": {"legendre": leg_ms / args.steps, "ring_fft": ms_kind[1] / args.steps,
                                   "elementwise": ms_kind[2] / args.steps},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read+write per launch, mean of the 4 launches of one step, from the ncu --set full
+                         # capture profiles/kernels_r1b_metrics.txt (only valid for the default workload)
+                         "traffic": 0.649e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
                          "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)",
                          "launches_timed": int(leg_n),
                          "algorithmic_flops_per_launch": flops_step / 4,
                          "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
+            # second-largest (by time: largest) kernel, reported the same way: HBM class per SURVEY 8(d);
+            # algorithmic bytes = pixels/coefficients in + ring coefficients out = 32 B x (ncoef+npix) per Psi per chain
+            "roofline_fft": {"bound": "hbm", "kernel": "pxm_ring_fft_kernel (4 launches per step)",
+                             "achieved": 2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] > 0 else None,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": (2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 / hbm_peak) if ms_kind[1] > 0 else None,
+                             "traffic": 0.470e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
+                             "note": "DRAM traffic equals the algorithmic bytes; the kernel is bound on chip (L1TEX data pipe 72-80 %, "
+                                     "FP64 pipe 35 %), see profiles/kernels_r1b_metrics.txt"},
             "e2e": {"value": world * nch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host"},
