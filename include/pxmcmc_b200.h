@@ -67,6 +67,42 @@ int pxm_wav_analysis_adjoint(pxm_wav_plan* plan, const void* d_coef, void* d_pix
  * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);
 
+/* ---- m-sharded plans: one chain, bandlimit too large or too slow for one GPU ---
+ * (no counterpart in the reference, which is single-process)
+ * One process per GPU, `world` <= 8 ranks on one NVLink/NVSwitch node.  Rank r
+ * owns the azimuthal orders |m| with pxm_shard_owner_of_m(|m|) == r (harmonic
+ * space, Legendre tables: 1/world of the memory) and, of every ring grid, the
+ * rows [t0, t1) of pxm_*_plan_local_rows (pixel / coefficient space: every
+ * pixel-side pointer of the transform calls then addresses those LOCAL rows
+ * only, scale maps concatenated in the usual order).  flm arrays keep their
+ * full length; a rank reads and writes only the orders it owns (others: 0).
+ * The theta<->m transposition is fused into the Legendre contractions: the
+ * contraction over l stores each 64-ring output tile straight into the ring
+ * buffer of the rank owning those rings, the contraction over rings pulls ring
+ * blocks from their owners with the same bulk copies it uses locally; a
+ * flag-based peer barrier separates the local and the peer-access phases.
+ * Set-up: create -> exchange pxm_*_plan_workspace addresses (same process:
+ * directly; other processes: pxm_ipc_export / pxm_ipc_open) -> attach.  All
+ * ranks must issue the same sequence of transform calls. */
+int pxm_sht_plan_create_sharded(int L, int spin, int max_batch, int rank, int world, pxm_sht_plan** out);
+int pxm_wav_plan_create_sharded(int L, double B, int J_min, int max_batch, int rank, int world, pxm_wav_plan** out);
+int pxm_sht_plan_prepare(pxm_sht_plan* plan); /* build all tables now (mandatory before a sharded plan is used) */
+int pxm_wav_plan_prepare(pxm_wav_plan* plan);
+void* pxm_sht_plan_workspace(pxm_sht_plan* plan, size_t* bytes);
+void* pxm_wav_plan_workspace(pxm_wav_plan* plan, size_t* bytes);
+int pxm_sht_plan_attach(pxm_sht_plan* plan, void* const* peer_workspaces /* [world]; own entry ignored */);
+int pxm_wav_plan_attach(pxm_wav_plan* plan, void* const* peer_workspaces);
+int pxm_sht_plan_local_rows(const pxm_sht_plan* plan, int* t0, int* t1);
+int pxm_wav_plan_local_rows(const pxm_wav_plan* plan, int* t0, int* t1 /* [nscales_total + 1], last = pixel map */,
+                            long long* ncoefs_local, long long* npix_local);
+int pxm_sht_plan_barrier_status(pxm_sht_plan* plan, long long* failed_epoch /* 0 = no time-out */);
+int pxm_wav_plan_barrier_status(pxm_wav_plan* plan, long long* failed_epoch);
+int pxm_shard_owner_of_m(int abs_m, int world);                                        /* host only */
+int pxm_shard_ring_range(int ell, int rot, int rank, int world, int* t0, int* t1);      /* host only */
+int pxm_ipc_export(const void* d_ptr, void* handle64);
+int pxm_ipc_open(const void* handle64, void** d_ptr);
+int pxm_ipc_close(void* d_ptr);
+
 /* ---- fused elementwise passes ---------------------------------------------
  * pxm_soft: utils.soft (pxmcmc/utils.py:55-67); T vector (d_T, length n) or scalar. */
 int pxm_soft(int is_complex, const void* d_x, const double* d_T, double T_scalar, void* d_out, long long n,

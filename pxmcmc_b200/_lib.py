@@ -37,6 +37,23 @@ SIGNATURES = {
     "pxm_wav_analysis": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_analysis_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wavelet_tiling": (_i, [_i, _d, _i, _vp, _vp, C.POINTER(_i)]),
+    "pxm_sht_plan_create_sharded": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "pxm_wav_plan_create_sharded": (_i, [_i, _d, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "pxm_sht_plan_prepare": (_i, [_vp]),
+    "pxm_wav_plan_prepare": (_i, [_vp]),
+    "pxm_sht_plan_workspace": (_vp, [_vp, C.POINTER(C.c_size_t)]),
+    "pxm_wav_plan_workspace": (_vp, [_vp, C.POINTER(C.c_size_t)]),
+    "pxm_sht_plan_attach": (_i, [_vp, C.POINTER(_vp)]),
+    "pxm_wav_plan_attach": (_i, [_vp, C.POINTER(_vp)]),
+    "pxm_sht_plan_local_rows": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
+    "pxm_wav_plan_local_rows": (_i, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(_ll), C.POINTER(_ll)]),
+    "pxm_sht_plan_barrier_status": (_i, [_vp, C.POINTER(_ll)]),
+    "pxm_wav_plan_barrier_status": (_i, [_vp, C.POINTER(_ll)]),
+    "pxm_shard_owner_of_m": (_i, [_i, _i]),
+    "pxm_shard_ring_range": (_i, [_i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "pxm_ipc_export": (_i, [_vp, _vp]),
+    "pxm_ipc_open": (_i, [_vp, C.POINTER(_vp)]),
+    "pxm_ipc_close": (_i, [_vp]),
     "pxm_soft": (_i, [_i, _vp, _vp, _d, _vp, _ll, _ll, _vp]),
     "pxm_myula_update": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _ll, _ll, _d, _d, _i, _u64, _u64, _u32, _vp]),
     "pxm_resid_invcov": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _vp]),

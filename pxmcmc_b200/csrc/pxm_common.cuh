@@ -91,7 +91,7 @@ struct PxmLegSeg {
   int mt0;                   // first M-direction tile present (others are implicit zeros)
   int nmt;                   // number of M-direction tiles present
   int nk;                    // number of k-stages
-  int pad;
+  int src;                   // rank whose workspace holds this segment's data operand (0 when not sharded)
 };
 
 struct PxmLegItem {
@@ -100,6 +100,17 @@ struct PxmLegItem {
   int seg_count;
   int nmt_out;  // number of M-direction tiles to store
   int cost;     // k-stages x tiles, for ordering
+  int dst;      // rank whose workspace receives the output tile (0 when not sharded)
+  int pad;
+};
+
+// Workspaces of the ranks of an m-sharded plan (peer-mapped device memory, NVLink):
+// the contraction over l PUSHES its output tile into the ring buffer of the rank that
+// owns those rings, the contraction over rings PULLS ring blocks from their owners with
+// the same cp.async.bulk copies it uses locally.  Unsharded plans use p[0] only.
+constexpr int PXM_MAX_PEERS = 8;
+struct PxmPeers {
+  double* p[PXM_MAX_PEERS];
 };
 
 // descriptors of the ring FFT ---------------------------------------------------
@@ -108,14 +119,16 @@ struct PxmFftGroup {
   int n;            // 2*ell-1 samples per ring
   int M;            // power-of-two Bluestein length >= 2n-1
   int logM;
-  int rings;        // number of rings (ell)
+  int rings;        // end of this rank's ring range (ell when not sharded)
   int rings_per_cta;
   int cta_begin;    // first CTA (within one chain) of this group
   int nslots;       // ell (paired +-m, spin 0) or 2*ell-1
   int paired;       // 1: slot = |m|, 4 columns per chain; 0: slot = m+ell-1, 2 columns per chain
   int pad;          // log2(rings_per_cta)
+  int ring0;        // first ring this rank transforms (`rings` is the end, exclusive); 0 when not sharded
+  int pad2;
   double scale;     // applied to every output
-  unsigned long long pix_off;       // complex elements: start of this map inside one chain's pixel vector
+  unsigned long long pix_off;       // complex elements: start of this map's LOCAL rows inside one chain's pixel vector
   unsigned long long f_off;         // doubles: start of this grid's ring-Fourier array
   unsigned long long slot_stride;   // doubles between m-slots
   unsigned long long chirp_off;     // complex elements into the twiddle arena: c_j = exp(-i pi j^2/n), n entries

@@ -352,6 +352,7 @@ struct LmArgs {
   double* H;          // internal
   const unsigned long long* slot_off;  // per slot
   const double* gl;   // may be null
+  const unsigned char* own;  // may be null; per slot: does this rank own the azimuthal order (m-sharded plans)
   int L, paired, nld, nchains, to_internal;
 };
 __global__ void k_lm_convert(LmArgs p) {
@@ -375,6 +376,10 @@ __global__ void k_lm_convert(LmArgs p) {
     } else {
       slot = m + p.L - 1;
       col = chain * 2;
+    }
+    if (p.own && !p.own[slot]) {  // another rank's order: nothing to load, zero on the way out
+      if (!p.to_internal) p.flm[i] = make_double2(0.0, 0.0);
+      continue;
     }
     const size_t base = p.slot_off[slot] + pxm_il_index(l - am, col, p.nld);
     const double gl = p.gl ? p.gl[l] : 1.0;
@@ -542,9 +547,17 @@ int pxm_launch_gather(int scatter, const void* in, const int* idx, const double*
   return PXM_OK;
 }
 
+int pxm_elem_preload() {
+  cudaFuncAttributes a;
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_lm_convert));
+  return PXM_OK;
+}
+
 int pxm_launch_lm_convert(int to_internal, void* flm, double* H, const unsigned long long* d_slot_off,
-                          const double* d_gl, int L, int paired, int nld, int nchains, cudaStream_t st) {
+                          const unsigned char* d_own, const double* d_gl, int L, int paired, int nld, int nchains,
+                          cudaStream_t st) {
   LmArgs p;
+  p.own = d_own;
   p.flm = (cplx*)flm;
   p.H = H;
   p.slot_off = d_slot_off;

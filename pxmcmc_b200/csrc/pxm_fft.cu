@@ -270,6 +270,7 @@ __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cpl
 // DIR 0: pixels -> ring coefficients  F_m[t] = scale * sum_p f[t,p] e^{-i m phi_p}
 // DIR 1: ring coefficients -> pixels  f[t,p] = scale * sum_m F_m[t] e^{+i m phi_p}
 // A CTA owns 2^lgr consecutive rings (a whole number of k4 row-groups when >= 4).
+// m-sharded plans: a rank transforms only the rings [ring0, rings) it owns; its pixel vector holds those rows.
 #ifndef PXM_FFT_MINB
 #define PXM_FFT_MINB 3
 #endif
@@ -284,7 +285,7 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
   const PxmFftGroup gr = groups[gi];
   const int chain = blockIdx.y;
   const int lgr = gr.pad;  // log2(rings per CTA)
-  const int t0 = ((int)blockIdx.x - gr.cta_begin) << lgr;
+  const int t0 = gr.ring0 + (((int)blockIdx.x - gr.cta_begin) << lgr);  // global ring index
   const int n = gr.n, M = gr.M, ell = gr.ell, lgM = gr.logM, rings = gr.rings;
   const int MP = M + (M >> 4) + 2;  // +2: the rings of one row-group land in different banks
   const cplx* chirp = arena + gr.chirp_off;
@@ -308,7 +309,7 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
       const int r = idx >> lgM, j = idx & (M - 1);
       cplx v = make_double2(0.0, 0.0);
-      if (j < n && t0 + r < rings) v = cmul(mypix[(size_t)(t0 + r) * n + j], chirp[j]);
+      if (j < n && t0 + r < rings) v = cmul(mypix[(size_t)(t0 + r - gr.ring0) * n + j], chirp[j]);
       s[r * MP + padi(j)] = v;
     }
   } else {
@@ -368,7 +369,7 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
     const int nr = min(1 << lgr, rings - t0);
     for (int r = 0; r < nr; ++r) {
       const cplx* srow = s + r * MP;
-      cplx* prow = mypix + (size_t)(t0 + r) * n;
+      cplx* prow = mypix + (size_t)(t0 + r - gr.ring0) * n;
 #pragma unroll 2
       for (int k = threadIdx.x; k < n; k += blockDim.x) {
         const cplx v = cmul(srow[padi(k)], chirp[k]);
@@ -408,6 +409,7 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT_SMEM));
     configured = true;
   }
+  if (ngroups <= 0) return PXM_OK;  // a rank of an m-sharded plan that owns no ring
   for (int i = 0; i < ngroups; ++i) {
     if (h_groups[i].M > 4096) {
       pxm_set_error("ring FFT: bandlimit too large (Bluestein length > 4096, i.e. L > 1024)");

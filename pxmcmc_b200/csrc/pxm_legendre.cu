@@ -87,8 +87,8 @@ struct LegCfg {
 //           descriptor's nk counts ring blocks, i.e. two stages each.
 template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
 __global__ void __launch_bounds__(LEG_THREADS, 2)
-pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ bmat,
-                    double* __restrict__ cmat, const PxmLegItem* __restrict__ items,
+pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmPeers bpeers,
+                    const __grid_constant__ PxmPeers cpeers, const PxmLegItem* __restrict__ items,
                     const PxmLegSeg* __restrict__ segs, int nld) {
   using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -137,7 +137,8 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
               bulk_g2s(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
           }
           double* dstB = sB + slot * C::B_STAGE;
-          const double* srcB = bmat + sg.b_off + ((size_t)k * (C::BK / 4) * (size_t)nld + (size_t)n0) * 4;
+          // m-sharded plans: the ring block may live in a peer's workspace (pulled over NVLink)
+          const double* srcB = bpeers.p[sg.src] + sg.b_off + ((size_t)k * (C::BK / 4) * (size_t)nld + (size_t)n0) * 4;
           if (BN == nld) {
             bulk_g2s(dstB, srcB, (uint32_t)(C::BK * BN * 8), bar);
           } else {
@@ -205,7 +206,8 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
     }
   }
 
-  // ---- epilogue: k4-interleaved store ---------------------------------------
+  // ---- epilogue: k4-interleaved store (into the owner of these rows: a peer when m-sharded) ----
+  double* __restrict__ cmat = cpeers.p[item.dst];
 #pragma unroll
   for (int mi = 0; mi < C::MI; ++mi) {
     const int row = wm * C::WM + mi * 8 + g;
@@ -223,12 +225,13 @@ pxm_legendre_kernel(const double* __restrict__ tab, const double* __restrict__ b
 // aid for the GPU tests (localises a fault to the tensor-core kernel or to the
 // tables/descriptors); never selected by the product path.
 template <int ORIENT>
-__global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const double* __restrict__ bmat,
-                                          double* __restrict__ cmat, const PxmLegItem* __restrict__ items,
-                                          const PxmLegSeg* __restrict__ segs, int nld) {
+__global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const PxmPeers bpeers, const PxmPeers cpeers,
+                                          const PxmLegItem* __restrict__ items, const PxmLegSeg* __restrict__ segs,
+                                          int nld) {
   constexpr int BK = ORIENT == 0 ? 16 : 32;
   constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;
   const PxmLegItem item = items[blockIdx.x];
+  double* cmat = cpeers.p[item.dst];
   const int row = threadIdx.x & 63;
   for (int col = blockIdx.y * blockDim.x / 64 + (threadIdx.x >> 6); col < nld; col += gridDim.y * (blockDim.x / 64)) {
     const int tl = row / TILE_ROWS;
@@ -236,6 +239,7 @@ __global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const 
     double acc = 0.0;
     for (int s = 0; s < item.seg_count; ++s) {
       const PxmLegSeg sg = segs[item.seg_begin + s];
+      const double* bmat = bpeers.p[sg.src];
       if (tl < sg.mt0 || tl >= sg.mt0 + sg.nmt) continue;
       for (int k = 0; k < sg.nk; ++k) {
         const double* tile = tab + sg.a_off + (size_t)k * sg.a_kstride + (size_t)(tl - sg.mt0) * sg.a_mstride;
@@ -254,7 +258,7 @@ __global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const 
 }
 
 template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
-int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* items, const PxmLegSeg* segs,
+int launch_cfg(const double* tab, const PxmPeers& b, const PxmPeers& c, const PxmLegItem* items, const PxmLegSeg* segs,
                int nitems, int nld, cudaStream_t stream) {
   using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
   static bool configured = false;
@@ -263,6 +267,7 @@ int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* 
     PXM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
+  if (nitems == 0) return PXM_OK;  // preload only (pxm_legendre_preload)
   dim3 grid(nitems, nld / BN);
   kern<<<grid, LEG_THREADS, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
   PXM_LAUNCHED();
@@ -273,8 +278,8 @@ int launch_cfg(const double* tab, const double* b, double* c, const PxmLegItem* 
 // (ORIENT 1) gives every warp all 64 degrees (1x8), so that segments whose l-support covers only
 // part of the tile (wavelet scales) keep all eight warps equally busy
 template <int ORIENT>
-int launch_orient(const double* tab, const double* b, double* c, const PxmLegItem* items, const PxmLegSeg* segs,
-                  int nitems, int nld, cudaStream_t stream) {
+int launch_orient(const double* tab, const PxmPeers& b, const PxmPeers& c, const PxmLegItem* items,
+                  const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream) {
   constexpr int ST = 4;
   if (ORIENT == 0) {
     if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
@@ -304,8 +309,33 @@ int pxm_legendre_pad_columns(int ncols) {
   return pxm_round_up(ncols, 128);
 }
 
+int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
+                              const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
+                              cudaStream_t stream, int naive);
+
 int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
                         const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive) {
+  PxmPeers bp = {}, cp = {};
+  bp.p[0] = const_cast<double*>(b);
+  cp.p[0] = c;
+  return pxm_legendre_launch_peers(orient, tab, bp, cp, items, segs, nitems, nld, stream, naive);
+}
+
+// Load and configure the kernels a plan with `nld` columns will launch (CUDA loads kernels
+// lazily, and a first-use load may synchronise the device -- fatal while a peer barrier spins).
+int pxm_legendre_preload(int nld) {
+  PxmPeers z = {};
+  PXM_TRY(launch_orient<0>(nullptr, z, z, nullptr, nullptr, 0, nld, 0));
+  PXM_TRY(launch_orient<1>(nullptr, z, z, nullptr, nullptr, 0, nld, 0));
+  cudaFuncAttributes a;
+  PXM_CUDA(cudaFuncGetAttributes(&a, pxm_legendre_naive_kernel<0>));
+  PXM_CUDA(cudaFuncGetAttributes(&a, pxm_legendre_naive_kernel<1>));
+  return PXM_OK;
+}
+
+int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
+                              const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
+                              cudaStream_t stream, int naive) {
   if (nitems <= 0) return PXM_OK;
   if (naive) {
     dim3 grid(nitems, 4);

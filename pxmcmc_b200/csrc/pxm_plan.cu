@@ -8,6 +8,7 @@
 // with stages dropped at the harmonic-space boundary of the pyssht-level calls.
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -53,10 +54,21 @@ namespace {
 
 typedef unsigned long long ull;
 
+// first doubles of every workspace: barrier flags of an m-sharded plan (one 64-bit epoch per
+// peer) and, at word PXM_WS_ERR, the barrier's time-out flag
+constexpr ull PXM_WS_RESERVED = 512;
+constexpr int PXM_WS_ERR = 64;
+
+struct Shard {
+  int rank = 0, world = 1;
+};
+
 struct RingBuf {
   int ell = 0;
   bool paired = true;
   int nslots = 0;
+  int rot = 0;          // rotation of the ring-block ownership (scale index)
+  int t0 = 0, t1 = 0;   // rings owned by this rank
   ull off = 0;          // doubles into the workspace
   ull slot_stride = 0;  // doubles
   int slot_of(int m) const { return paired ? std::abs(m) : m + ell - 1; }
@@ -72,9 +84,11 @@ struct HarmBuf {
   int slot_of(int m) const { return paired ? std::abs(m) : m + L - 1; }
 };
 
-void make_ring(RingBuf& R, int ell, bool paired, int nld, ull& cursor) {
+void make_ring(RingBuf& R, int ell, bool paired, int nld, ull& cursor, const Shard& sh = Shard(), int rot = 0) {
   R.ell = ell;
   R.paired = paired;
+  R.rot = rot;
+  pxm_ring_range(ell, rot, sh.rank, sh.world, &R.t0, &R.t1);
   R.nslots = paired ? ell : 2 * ell - 1;
   R.slot_stride = (ull)pxm_round_up(ell, 32) * nld;
   R.off = cursor;
@@ -175,8 +189,10 @@ struct FftTables {
 };
 
 void add_fft_group(FftStage& S, FftTables& tabs, const RingBuf& R, ull pix_off, double scale) {
+  if (R.t1 <= R.t0) return;  // this rank owns no ring of the grid
   PxmFftGroup g = tabs.get(R.ell);
-  g.rings = R.ell;
+  g.rings = R.t1;
+  g.ring0 = R.t0;
   g.pad = pxm_fft_rings_per_cta_log(g.M);  // log2(rings per CTA)
   g.rings_per_cta = 1 << g.pad;
   g.cta_begin = S.ctas;
@@ -186,14 +202,15 @@ void add_fft_group(FftStage& S, FftTables& tabs, const RingBuf& R, ull pix_off, 
   g.pix_off = pix_off;
   g.f_off = R.off;
   g.slot_stride = R.slot_stride;
-  S.ctas += pxm_ceil_div(R.ell, g.rings_per_cta);
+  S.ctas += pxm_ceil_div(R.t1 - R.t0, g.rings_per_cta);
   S.groups.push_back(g);
 }
 
 int slot_index(const PxmTableLayout& T, int m) { return T.paired ? std::abs(m) : m + T.lmax - 1; }
 
 // contraction over l:  ring buffer R  <-  table T  x  harmonic buffer H
-void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf& R, int nld) {
+void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf& R, int nld,
+                   const Shard& sh = Shard()) {
   const PxmTableLayout& T = tr.T;
   S.orient = 0;
   for (int s = 0; s < T.nslots; ++s) {
@@ -209,12 +226,14 @@ void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf
       sg.nmt = std::min(2, T.ntb - 2 * i);
       sg.nk = T.nlb[s];
       sg.b_off = H.slot_off[hs] + (ull)T.lb0[s] * PXM_TILE_L * nld;
+      sg.src = sh.rank;  // harmonic coefficients of an owned order are local
       PxmLegItem it = {};
       it.c_off = R.off + (ull)rs * R.slot_stride + (ull)(64 * i) * nld;
       it.seg_begin = (int)S.segs.size();
       it.seg_count = 1;
       it.nmt_out = sg.nmt;
       it.cost = sg.nk * sg.nmt;
+      it.dst = pxm_owner_of_ring_block(R.ell, i, R.rot, sh.world);  // pushed to the owner of these 64 rings
       S.segs.push_back(sg);
       S.items.push_back(it);
     }
@@ -227,12 +246,14 @@ struct ASource {
 };
 
 // contraction over rings:  harmonic buffer H  <-  sum over sources  table^T x ring buffer
-void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H, int nld) {
+void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H, int nld,
+                   const Shard& sh = Shard()) {
   S.orient = 1;
   const int ns = (int)H.slot_off.size();
   for (int hs = 0; hs < ns; ++hs) {
     const int m = H.paired ? hs : hs - (H.L - 1);
     const int am = std::abs(m);
+    if (pxm_owner_of_m(am, sh.world) != sh.rank) continue;
     const int nlbH = pxm_ceil_div(H.L - am, PXM_TILE_L);
     for (int lt = 0; 4 * lt < nlbH; ++lt) {
       PxmLegItem it = {};
@@ -245,18 +266,27 @@ void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H,
         if (T.nlb[s] == 0) continue;
         const int lbA = std::max(4 * lt, T.lb0[s]), lbB = std::min(4 * lt + 4, T.lb0[s] + T.nlb[s]);
         if (lbA >= lbB) continue;
-        PxmLegSeg sg = {};
-        sg.a_off = T.tile_off[s] + (ull)(lbA - T.lb0[s]) * PXM_TILE_DOUBLES;
-        sg.a_kstride = T.nlb[s] * PXM_TILE_DOUBLES;
-        sg.a_mstride = PXM_TILE_DOUBLES;
-        sg.mt0 = lbA - 4 * lt;
-        sg.nmt = lbB - lbA;
-        sg.nk = T.ntb;
-        sg.b_off = src.R->off + (ull)src.R->slot_of(m) * src.R->slot_stride;
-        it.cost += sg.nk * sg.nmt;
-        S.segs.push_back(sg);
+        // one segment per rank that owns part of the source rings (pulled from that rank's workspace)
+        for (int q = 0; q < sh.world; ++q) {
+          int qt0, qt1;
+          pxm_ring_range(src.R->ell, src.R->rot, q, sh.world, &qt0, &qt1);
+          if (qt1 <= qt0) continue;
+          const int tb0 = qt0 / PXM_TILE_T, tb1 = pxm_ceil_div(qt1, PXM_TILE_T);
+          PxmLegSeg sg = {};
+          sg.a_kstride = T.nlb[s] * PXM_TILE_DOUBLES;
+          sg.a_off = T.tile_off[s] + (ull)(lbA - T.lb0[s]) * PXM_TILE_DOUBLES + (ull)tb0 * sg.a_kstride;
+          sg.a_mstride = PXM_TILE_DOUBLES;
+          sg.mt0 = lbA - 4 * lt;
+          sg.nmt = lbB - lbA;
+          sg.nk = tb1 - tb0;
+          sg.b_off = src.R->off + (ull)src.R->slot_of(m) * src.R->slot_stride + (ull)tb0 * PXM_TILE_T * nld;
+          sg.src = q;
+          it.cost += sg.nk * sg.nmt;
+          S.segs.push_back(sg);
+        }
       }
       it.seg_count = (int)S.segs.size() - it.seg_begin;
+      it.dst = sh.rank;  // harmonic coefficients of an owned order stay local
       it.c_off = H.slot_off[hs] + (ull)(64 * lt) * nld;
       it.nmt_out = std::min(4, nlbH - 4 * lt);
       S.items.push_back(it);
@@ -323,12 +353,81 @@ Tiling make_tiling(int L, double B, int J_min) {
 
 }  // namespace
 
+// ---------------------------------------------------------------- peer barrier
+// All ranks of an m-sharded plan meet here between a phase that touches only local memory (ring
+// FFTs, elementwise) and a phase that pushes to / pulls from peer workspaces (the contractions).
+// One 64-bit epoch per (rank, peer) in the reserved head of every workspace; release/acquire at
+// system scope over NVLink.  A time-out (a peer that never arrives) sets the error word instead
+// of hanging the GPU.
+__global__ void k_peer_barrier(PxmPeers peers, int rank, int world, ull epoch) {
+  const int q = threadIdx.x;
+  if (q >= world) return;
+  ull* remote = reinterpret_cast<ull*>(peers.p[q]) + rank;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+  const ull* mine = reinterpret_cast<const ull*>(peers.p[rank]) + q;
+  const long long t_start = clock64();
+  for (;;) {
+    ull v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t_start > 20000000000LL) {  // ~10 s
+      reinterpret_cast<ull*>(peers.p[rank])[PXM_WS_ERR] = epoch;
+      break;
+    }
+    __nanosleep(100);
+  }
+}
+
+struct PeerSet {
+  Shard sh;
+  PxmPeers peers = {};
+  ull epoch = 0;
+  bool attached = false;
+  int barrier(cudaStream_t st) {
+    if (sh.world <= 1) return PXM_OK;
+    if (!attached) {
+      pxm_set_error("m-sharded plan used before pxm_*_plan_attach");
+      return PXM_ERR_ARG;
+    }
+    ++epoch;
+    k_peer_barrier<<<1, 32, 0, st>>>(peers, sh.rank, sh.world, epoch);
+    PXM_LAUNCHED();
+    return PXM_OK;
+  }
+  int attach(double* own, void* const* ws) {
+    for (int q = 0; q < sh.world; ++q) peers.p[q] = (q == sh.rank) ? own : static_cast<double*>(ws[q]);
+    for (int q = 0; q < sh.world; ++q)
+      if (!peers.p[q]) {
+        pxm_set_error("attach: null peer workspace");
+        return PXM_ERR_ARG;
+      }
+    attached = true;
+    return PXM_OK;
+  }
+  int status(long long* failed_epoch) const {
+    ull v = 0;
+    PXM_CUDA(cudaMemcpy(&v, reinterpret_cast<const ull*>(peers.p[sh.rank]) + PXM_WS_ERR, 8, cudaMemcpyDeviceToHost));
+    *failed_epoch = (long long)v;
+    return PXM_OK;
+  }
+};
+
+int check_shard(int rank, int world) {
+  PXM_REQUIRE(world >= 1 && world <= PXM_MAX_PEERS, "world size must be in [1, 8]");
+  PXM_REQUIRE(rank >= 0 && rank < world, "rank out of range");
+  return PXM_OK;
+}
+
 // =========================================================================
 //                               SHT plan
 // =========================================================================
 struct pxm_sht_plan {
   int L = 0, spin = 0, nb = 0, nld = 0;
   bool paired = true;
+  PeerSet ps;
+  size_t ws_bytes = 0;
+  PxmDevVec<unsigned char> d_own;  // per harmonic slot: 1 when this rank owns the azimuthal order
   TableRef lam, w;
   double* d_tab = nullptr;
   double* d_ws = nullptr;
@@ -411,6 +510,11 @@ int pxm_init(int device) {
 }
 
 int pxm_sht_plan_create(int L, int spin, int max_batch, pxm_sht_plan** out) {
+  return pxm_sht_plan_create_sharded(L, spin, max_batch, 0, 1, out);
+}
+
+int pxm_sht_plan_create_sharded(int L, int spin, int max_batch, int rank, int world, pxm_sht_plan** out) {
+  PXM_TRY(check_shard(rank, world));
   PXM_REQUIRE(L >= 1 && L <= 1024, "L must be in [1, 1024]");
   PXM_REQUIRE(std::abs(spin) < L || L == 1, "|spin| must be < L");
   PXM_REQUIRE(max_batch >= 1, "max_batch >= 1");
@@ -420,21 +524,35 @@ int pxm_sht_plan_create(int L, int spin, int max_batch, pxm_sht_plan** out) {
   p->nb = max_batch;
   p->paired = (spin == 0);
   p->nld = pxm_legendre_pad_columns((p->paired ? 4 : 2) * max_batch);
+  p->ps.sh.rank = rank;
+  p->ps.sh.world = world;
+  const Shard& sh = p->ps.sh;
   ull tcur = 0;
-  pxm_make_table_layout(p->lam.T, L, L, L, spin, 0, L, tcur);
+  pxm_make_table_layout(p->lam.T, L, L, L, spin, 0, L, tcur, rank, world);
   tcur += p->lam.T.doubles;
   p->lam.family = 0;
-  pxm_make_table_layout(p->w.T, L, L, L, spin, 0, L, tcur);
+  pxm_make_table_layout(p->w.T, L, L, L, spin, 0, L, tcur, rank, world);
   tcur += p->w.T.doubles;
   p->w.family = 1;
   PXM_CUDA(cudaMalloc(&p->d_tab, std::max<ull>(tcur, 1) * 8));
   PXM_CUDA(cudaMemset(p->d_tab, 0, std::max<ull>(tcur, 1) * 8));
-  ull wcur = 0;
-  make_ring(p->R, L, p->paired, p->nld, wcur);
+  ull wcur = PXM_WS_RESERVED;
+  make_ring(p->R, L, p->paired, p->nld, wcur, sh, 0);
   make_harm(p->H, L, p->paired, p->nld, wcur);
   PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
   PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
+  p->ws_bytes = wcur * 8;
+  p->ps.peers.p[0] = p->d_ws;
+  if (world == 1) p->ps.attached = true;
   PXM_TRY(p->H.d_slot_off.upload(p->H.slot_off));
+  {
+    std::vector<unsigned char> own(p->H.slot_off.size());
+    for (size_t s = 0; s < own.size(); ++s) {
+      const int am = p->paired ? (int)s : std::abs((int)s - (L - 1));
+      own[s] = pxm_owner_of_m(am, world) == rank;
+    }
+    PXM_TRY(p->d_own.upload(own));
+  }
   const double inv_n = 1.0 / (2 * L - 1);
   add_fft_group(p->fft_in_unit, p->ffttab, p->R, 0, 1.0);
   add_fft_group(p->fft_in_norm, p->ffttab, p->R, 0, inv_n);
@@ -443,10 +561,10 @@ int pxm_sht_plan_create(int L, int spin, int max_batch, pxm_sht_plan** out) {
   PXM_TRY(p->ffttab.finalize(0));
   for (FftStage* f : {&p->fft_in_unit, &p->fft_in_norm, &p->fft_out_unit, &p->fft_out_norm})
     PXM_TRY(f->d_groups.upload(f->groups));
-  build_s_items(p->s_lam, p->lam, p->H, p->R, p->nld);
-  build_s_items(p->s_w, p->w, p->H, p->R, p->nld);
-  build_a_items(p->a_lam, {{&p->lam, &p->R}}, p->H, p->nld);
-  build_a_items(p->a_w, {{&p->w, &p->R}}, p->H, p->nld);
+  build_s_items(p->s_lam, p->lam, p->H, p->R, p->nld, sh);
+  build_s_items(p->s_w, p->w, p->H, p->R, p->nld, sh);
+  build_a_items(p->a_lam, {{&p->lam, &p->R}}, p->H, p->nld, sh);
+  build_a_items(p->a_w, {{&p->w, &p->R}}, p->H, p->nld, sh);
   for (Stage* s : {&p->s_lam, &p->s_w, &p->a_lam, &p->a_w}) PXM_TRY(s->upload());
   *out = p.release();
   return PXM_OK;
@@ -458,6 +576,7 @@ int pxm_sht_plan_destroy(pxm_sht_plan* p) {
   for (FftStage* f : {&p->fft_in_unit, &p->fft_in_norm, &p->fft_out_unit, &p->fft_out_norm}) f->release();
   p->ffttab.release();
   p->H.d_slot_off.release();
+  p->d_own.release();
   if (p->d_tab) cudaFree(p->d_tab);
   if (p->d_ws) cudaFree(p->d_ws);
   delete p;
@@ -471,15 +590,20 @@ static int sht_run(pxm_sht_plan* p, int which, void* d_flm, void* d_f, int nb, c
   PXM_REQUIRE(p != nullptr, "null plan");
   PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t npix = (size_t)p->L * (2 * p->L - 1);
+  // pixel vectors hold the rows of the rings this rank owns (all of them when not sharded)
+  const size_t npix = (size_t)(p->R.t1 - p->R.t0) * (2 * p->L - 1);
   TableRef& tr = (which == 0 || which == 2) ? p->lam : p->w;
   PXM_TRY(p->ensure(tr));
   const int naive = pxm_debug_naive();
+  const PxmPeers& pe = p->ps.peers;
+  const unsigned char* own = p->ps.sh.world > 1 ? p->d_own.d : nullptr;
   if (which == 0 || which == 3) {  // harmonic -> pixel
-    PXM_TRY(pxm_launch_lm_convert(1, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
+    PXM_TRY(pxm_launch_lm_convert(1, d_flm, p->d_ws, p->H.d_slot_off.d, own, d_gl, p->L, p->paired, p->nld, nb, st));
     Stage& S = which == 0 ? p->s_lam : p->s_w;
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+    PXM_TRY(p->ps.barrier(st));  // peers are done reading the ring buffers this stage overwrites
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
                                 st, naive)); }
+    PXM_TRY(p->ps.barrier(st));  // every rank's tiles have landed
     FftStage& F = which == 0 ? p->fft_out_unit : p->fft_out_norm;
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
                            p->ffttab.d_arena, nb, st)); }
@@ -488,9 +612,11 @@ static int sht_run(pxm_sht_plan* p, int which, void* d_flm, void* d_f, int nb, c
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
                            p->ffttab.d_arena, nb, st)); }
     Stage& S = which == 2 ? p->a_lam : p->a_w;
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
+    PXM_TRY(p->ps.barrier(st));  // every rank's ring coefficients are in place
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
                                 st, naive)); }
-    PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, d_gl, p->L, p->paired, p->nld, nb, st));
+    PXM_TRY(p->ps.barrier(st));  // peers are done pulling from this rank's ring buffer
+    PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, own, d_gl, p->L, p->paired, p->nld, nb, st));
   }
   return PXM_OK;
 }
@@ -531,8 +657,11 @@ struct pxm_wav_plan {
   int L = 0, J_min = 0, nb = 0, nld = 0, nscales_total = 0;
   double B = 0;
   Tiling til;
-  std::vector<ull> coef_off;  // complex offset of every scale map inside the coefficient vector
-  ull ncoefs = 0, nscal = 0;
+  PeerSet ps;
+  size_t ws_bytes = 0;
+  std::vector<ull> coef_off;  // complex offset of every scale map's LOCAL rows inside the local coefficient vector
+  ull ncoefs = 0, nscal = 0;  // global sizes
+  ull ncoefs_local = 0, npix_local = 0;
   double* d_tab = nullptr;
   double* d_ws = nullptr;
   ull tab_doubles = 0;
@@ -570,6 +699,11 @@ struct pxm_wav_plan {
 extern "C" {
 
 int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan** out) {
+  return pxm_wav_plan_create_sharded(L, B, J_min, max_batch, 0, 1, out);
+}
+
+int pxm_wav_plan_create_sharded(int L, double B, int J_min, int max_batch, int rank, int world, pxm_wav_plan** out) {
+  PXM_TRY(check_shard(rank, world));
   PXM_REQUIRE(L >= 2 && L <= 1024, "L must be in [2, 1024]");
   PXM_REQUIRE(B > 1.0, "B must be > 1");
   PXM_REQUIRE(J_min >= 0, "J_min >= 0");
@@ -584,13 +718,20 @@ int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan*
   PXM_REQUIRE(p->til.J >= J_min, "J_min larger than J_max");
   const int S = (int)p->til.bandlimits.size();
   p->nscales_total = S;
-  ull c = 0;
+  p->ps.sh.rank = rank;
+  p->ps.sh.world = world;
+  const Shard& sh = p->ps.sh;
+  ull c = 0, cl = 0;
   for (int i = 0; i < S; ++i) {
-    p->coef_off.push_back(c);
+    p->coef_off.push_back(cl);
     const ull Lj = p->til.bandlimits[i];
     c += Lj * (2 * Lj - 1);
+    int t0, t1;
+    pxm_ring_range((int)Lj, i + 1, rank, world, &t0, &t1);
+    cl += (ull)(t1 - t0) * (2 * Lj - 1);
   }
   p->ncoefs = c;
+  p->ncoefs_local = cl;
   p->nscal = (ull)p->til.bandlimits[0] * (2 * p->til.bandlimits[0] - 1);
 
   // ---- table layouts ----------------------------------------------------------
@@ -599,7 +740,7 @@ int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan*
   auto add_table = [&](TableRef& tr, int fam, int ell, int lo, int hi, const std::vector<double>& g) {
     tr.family = fam;
     tr.g = g;
-    pxm_make_table_layout(tr.T, ell, ell, ell, 0, lo, hi, tcur);
+    pxm_make_table_layout(tr.T, ell, ell, ell, 0, lo, hi, tcur, rank, world);
     tcur += tr.T.doubles;
   };
   std::vector<double> ones;
@@ -633,13 +774,17 @@ int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan*
   PXM_CUDA(cudaMemset(p->d_tab, 0, std::max<ull>(tcur, 1) * 8));
 
   // ---- workspace ------------------------------------------------------------------
-  ull wcur = 0;
-  make_ring(p->Rfull, L, true, p->nld, wcur);
+  ull wcur = PXM_WS_RESERVED;
+  make_ring(p->Rfull, L, true, p->nld, wcur, sh, 0);
   p->Rsc.resize(S);
-  for (int i = 0; i < S; ++i) make_ring(p->Rsc[i], p->til.bandlimits[i], true, p->nld, wcur);
+  for (int i = 0; i < S; ++i) make_ring(p->Rsc[i], p->til.bandlimits[i], true, p->nld, wcur, sh, i + 1);
   make_harm(p->H, L, true, p->nld, wcur);
   PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
   PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
+  p->ws_bytes = wcur * 8;
+  p->ps.peers.p[0] = p->d_ws;
+  if (world == 1) p->ps.attached = true;
+  p->npix_local = (ull)(p->Rfull.t1 - p->Rfull.t0) * (2 * L - 1);
 
   // ---- stages -----------------------------------------------------------------------
   const double inv_nL = 1.0 / (2 * L - 1);
@@ -655,10 +800,10 @@ int pxm_wav_plan_create(int L, double B, int J_min, int max_batch, pxm_wav_plan*
     add_fft_group(D->fft_full_out, p->ffttab, p->Rfull, 0, is_syn ? 1.0 : inv_nL);
     std::vector<ASource> srcs;
     for (int i = 0; i < S; ++i) srcs.push_back({&D->scales[i], &p->Rsc[i]});
-    build_a_items(D->a_multi, srcs, p->H, p->nld);
-    build_s_items(D->s_full, D->full, p->H, p->Rfull, p->nld);
-    build_a_items(D->a_full, {{&D->full, &p->Rfull}}, p->H, p->nld);
-    for (int i = 0; i < S; ++i) build_s_items(D->s_multi, D->scales[i], p->H, p->Rsc[i], p->nld);
+    build_a_items(D->a_multi, srcs, p->H, p->nld, sh);
+    build_s_items(D->s_full, D->full, p->H, p->Rfull, p->nld, sh);
+    build_a_items(D->a_full, {{&D->full, &p->Rfull}}, p->H, p->nld, sh);
+    for (int i = 0; i < S; ++i) build_s_items(D->s_multi, D->scales[i], p->H, p->Rsc[i], p->nld, sh);
     for (Stage* s : {&D->a_multi, &D->s_full, &D->a_full, &D->s_multi}) PXM_TRY(s->upload());
   }
   PXM_TRY(p->ffttab.finalize(0));
@@ -719,26 +864,33 @@ static int wav_run(pxm_wav_plan* p, int which, void* d_coef, void* d_pix, int nb
   WavDirection& D = (which < 2) ? p->syn : p->ana;
   PXM_TRY(p->ensure(D));
   const int naive = pxm_debug_naive();
-  const size_t npix = (size_t)p->L * (2 * p->L - 1);
+  // local sizes: the rows of the rings this rank owns (everything when not sharded)
+  const size_t npix = (size_t)p->npix_local, ncoef = (size_t)p->ncoefs_local;
+  const PxmPeers& pe = p->ps.peers;
   const bool coef_to_pix = (which == 0 || which == 3);
+  // m-sharded: [local ring FFTs] | barrier | [pull rings -> own m's ; push own m's -> ring owners] | barrier | [local ring FFTs]
   if (coef_to_pix) {
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
-                           d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                           d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    PXM_TRY(p->ps.barrier(st));
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_multi.d_items.d, D.a_multi.d_segs.d,
                                 (int)D.a_multi.items.size(), p->nld, st, naive)); }
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_full.d_items.d, D.s_full.d_segs.d,
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_full.d_items.d, D.s_full.d_segs.d,
                                 (int)D.s_full.items.size(), p->nld, st, naive)); }
+    PXM_TRY(p->ps.barrier(st));
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
                            d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
   } else {
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
                            npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, D.a_full.d_items.d, D.a_full.d_segs.d,
+    PXM_TRY(p->ps.barrier(st));
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_full.d_items.d, D.a_full.d_segs.d,
                                 (int)D.a_full.items.size(), p->nld, st, naive)); }
-    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+    { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
                                 (int)D.s_multi.items.size(), p->nld, st, naive)); }
+    PXM_TRY(p->ps.barrier(st));
     { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, (int)D.fft_scales_out.groups.size(),
-                           D.fft_scales_out.ctas, d_coef, p->ncoefs, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+                           D.fft_scales_out.ctas, d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
   }
   return PXM_OK;
 }
@@ -754,6 +906,101 @@ int pxm_wav_analysis(pxm_wav_plan* p, const void* d_pix, void* d_coef, int nbatc
 }
 int pxm_wav_analysis_adjoint(pxm_wav_plan* p, const void* d_coef, void* d_pix, int nbatch, void* stream) {
   return wav_run(p, 3, const_cast<void*>(d_coef), d_pix, nbatch, stream);
+}
+
+// =========================================================================
+//          m-sharded plans: workspace exchange, local layout, IPC
+// =========================================================================
+void* pxm_sht_plan_workspace(pxm_sht_plan* p, size_t* bytes) {
+  if (bytes) *bytes = p->ws_bytes;
+  return p->d_ws;
+}
+void* pxm_wav_plan_workspace(pxm_wav_plan* p, size_t* bytes) {
+  if (bytes) *bytes = p->ws_bytes;
+  return p->d_ws;
+}
+// Build every Legendre table now instead of on first use.  Required for m-sharded plans (the
+// table generator allocates/frees scratch memory, which synchronises the device and must not
+// happen while a peer barrier is spinning); optional otherwise.
+static int preload_kernels(int nld) {
+  cudaFuncAttributes a;
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_peer_barrier));
+  PXM_TRY(pxm_legendre_preload(nld));
+  PXM_TRY(pxm_elem_preload());
+  return PXM_OK;
+}
+int pxm_sht_plan_prepare(pxm_sht_plan* p) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_TRY(preload_kernels(p->nld));
+  PXM_TRY(p->ensure(p->lam));
+  PXM_TRY(p->ensure(p->w));
+  PXM_CUDA(cudaDeviceSynchronize());
+  return PXM_OK;
+}
+int pxm_wav_plan_prepare(pxm_wav_plan* p) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_TRY(preload_kernels(p->nld));
+  PXM_TRY(p->ensure(p->syn));
+  PXM_TRY(p->ensure(p->ana));
+  PXM_CUDA(cudaDeviceSynchronize());
+  return PXM_OK;
+}
+int pxm_sht_plan_attach(pxm_sht_plan* p, void* const* peer_ws) {
+  PXM_REQUIRE(p && peer_ws, "attach: null argument");
+  return p->ps.attach(p->d_ws, peer_ws);
+}
+int pxm_wav_plan_attach(pxm_wav_plan* p, void* const* peer_ws) {
+  PXM_REQUIRE(p && peer_ws, "attach: null argument");
+  return p->ps.attach(p->d_ws, peer_ws);
+}
+int pxm_sht_plan_barrier_status(pxm_sht_plan* p, long long* failed_epoch) { return p->ps.status(failed_epoch); }
+int pxm_wav_plan_barrier_status(pxm_wav_plan* p, long long* failed_epoch) { return p->ps.status(failed_epoch); }
+
+int pxm_sht_plan_local_rows(const pxm_sht_plan* p, int* t0, int* t1) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  *t0 = p->R.t0;
+  *t1 = p->R.t1;
+  return PXM_OK;
+}
+// t0/t1[i], i < nscales_total: rows of scale map i; t0/t1[nscales_total]: rows of the pixel map
+int pxm_wav_plan_local_rows(const pxm_wav_plan* p, int* t0, int* t1, long long* ncoefs_local, long long* npix_local) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  for (int i = 0; i < p->nscales_total; ++i) {
+    t0[i] = p->Rsc[i].t0;
+    t1[i] = p->Rsc[i].t1;
+  }
+  t0[p->nscales_total] = p->Rfull.t0;
+  t1[p->nscales_total] = p->Rfull.t1;
+  if (ncoefs_local) *ncoefs_local = (long long)p->ncoefs_local;
+  if (npix_local) *npix_local = (long long)p->npix_local;
+  return PXM_OK;
+}
+
+// host-only views of the partition (what tests/test_host_cpu.py checks without a GPU)
+int pxm_shard_owner_of_m(int abs_m, int world) { return pxm_owner_of_m(abs_m, world); }
+int pxm_shard_ring_range(int ell, int rot, int rank, int world, int* t0, int* t1) {
+  PXM_REQUIRE(world >= 1 && world <= PXM_MAX_PEERS && rank >= 0 && rank < world && ell >= 1, "shard arguments");
+  pxm_ring_range(ell, rot, rank, world, t0, t1);
+  return PXM_OK;
+}
+
+// CUDA IPC: how the ranks (one process per GPU) learn each other's workspace addresses
+int pxm_ipc_export(const void* d_ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  PXM_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+  memcpy(handle64, &h, 64);
+  return PXM_OK;
+}
+int pxm_ipc_open(const void* handle64, void** d_ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  PXM_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return PXM_OK;
+}
+int pxm_ipc_close(void* d_ptr) {
+  PXM_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return PXM_OK;
 }
 
 // =========================================================================

@@ -42,8 +42,41 @@ struct PxmTableLayout {
   size_t doubles = 0;
 };
 
+// m-sharding: azimuthal orders are dealt to the ranks in a snake so that the
+// triangular work (L - |m|) balances; +m and -m always share an owner.
+inline int pxm_owner_of_m(int am, int world) {
+  if (world <= 1) return 0;
+  const int k = am % (2 * world);
+  return k < world ? k : 2 * world - 1 - k;
+}
+// theta-sharding: rings are owned in blocks of 64 (one output tile of the contraction over l).
+// Grids with fewer blocks than ranks are spread with a stride and rotated by `rot` (the scale
+// index) so that the small wavelet scales do not all land on rank 0.
+inline int pxm_owner_of_ring_block(int ell, int blk, int rot, int world) {
+  if (world <= 1) return 0;
+  const int nb = (ell + 63) / 64;
+  if (nb >= world) return (int)(((long long)blk * world) / nb);
+  return (blk * (world / nb) + rot) % world;
+}
+inline void pxm_ring_range(int ell, int rot, int rank, int world, int* t0, int* t1) {
+  const int nb = (ell + 63) / 64;
+  int first = -1, last = -1;
+  for (int b = 0; b < nb; ++b)
+    if (pxm_owner_of_ring_block(ell, b, rot, world) == rank) {
+      if (first < 0) first = b;
+      last = b;
+    }
+  if (first < 0) {
+    *t0 = *t1 = 0;
+    return;
+  }
+  *t0 = 64 * first;
+  *t1 = 64 * (last + 1) < ell ? 64 * (last + 1) : ell;
+}
+
+// slots whose |m| is owned by another rank get no tiles (rank = 0, world = 1: everything)
 void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, int spin, int l_lo, int l_hi,
-                           unsigned long long base_off);
+                           unsigned long long base_off, int rank = 0, int world = 1);
 int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
 int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
 
@@ -51,6 +84,11 @@ int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cu
 int pxm_legendre_pad_columns(int ncols);
 int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
                         const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive);
+int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
+                              const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
+                              cudaStream_t stream, int naive);
+int pxm_legendre_preload(int nld);
+int pxm_elem_preload();
 int pxm_fft_choose_M(int n, int* logM);
 int pxm_fft_rings_per_cta_log(int M);
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
@@ -75,7 +113,8 @@ int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, doub
 int pxm_launch_gather(int scatter, const void* in, const int* idx, const double* w, void* out, size_t nsel,
                       size_t nfull, size_t nchains, cudaStream_t st);
 int pxm_launch_lm_convert(int to_internal, void* flm, double* H, const unsigned long long* d_slot_off,
-                          const double* d_gl, int L, int paired, int nld, int nchains, cudaStream_t st);
+                          const unsigned char* d_own, const double* d_gl, int L, int paired, int nld, int nchains,
+                          cudaStream_t st);
 int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st);
 int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* vals, const void* x, void* y, int nrows,
                         size_t ncols, size_t nchains, cudaStream_t st);

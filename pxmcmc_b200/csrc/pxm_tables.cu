@@ -126,7 +126,7 @@ __global__ void k_c_to_tiles(const double* __restrict__ C, const unsigned long l
 }  // namespace
 
 void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, int spin, int l_lo, int l_hi,
-                           unsigned long long base_off) {
+                           unsigned long long base_off, int rank, int world) {
   T.grid_L = grid_L;
   T.rings = rings;
   T.lmax = lmax;
@@ -150,7 +150,7 @@ void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, i
     const int am = std::abs(T.slot_m[s]);
     const int first = std::max(std::max(am, as), T.l_lo), last = T.l_hi;
     T.tile_off[s] = off;
-    if (first >= last) continue;
+    if (first >= last || pxm_owner_of_m(am, world) != rank) continue;
     T.lb0[s] = (first - am) / PXM_TILE_L;
     T.nlb[s] = (last - 1 - am) / PXM_TILE_L + 1 - T.lb0[s];
     off += (unsigned long long)T.ntb * T.nlb[s] * PXM_TILE_DOUBLES;
@@ -231,7 +231,8 @@ int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cu
     while (s1 < T.nslots) {
       const int am = std::abs(T.slot_m[s1]);
       const int first = std::max(am, as);
-      const int nlb = first < ell ? (ell - 1 - am) / PXM_TILE_L + 1 : 0;
+      // slots without tiles (outside the kernel's l-support, or owned by another rank) are skipped
+      const int nlb = (first < ell && T.nlb[s1] > 0) ? (ell - 1 - am) / PXM_TILE_L + 1 : 0;
       const size_t fd = (size_t)F.ntb * nlb * PXM_TILE_DOUBLES;
       const size_t cd = (size_t)pxm_round_up(std::max(ell - am, 1), 64) * nldq;
       if (s1 > s0 && need + fd + cd > budget) break;
@@ -268,13 +269,15 @@ int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cu
         sg.mt0 = 0;
         sg.nmt = std::min(4, F.nlb[i] - lt * 4);
         sg.nk = F.ntb;
-        sg.pad = 0;
+        sg.src = 0;
         PxmLegItem it;
         it.c_off = c_off[i] + (unsigned long long)(lt * 64) * nldq;
         it.seg_begin = (int)segs.size();
         it.seg_count = 1;
         it.nmt_out = sg.nmt;
         it.cost = sg.nk * sg.nmt;
+        it.dst = 0;
+        it.pad = 0;
         segs.push_back(sg);
         items.push_back(it);
       }

@@ -1,0 +1,159 @@
+"""GPU tests of the m-sharded transforms.
+
+* `SimulatedRanks`: all ranks of a sharded plan live in ONE process on ONE GPU (one
+  stream per rank) -- the same kernels, peer-pointer tables, push/pull contractions
+  and flag barrier as the multi-process path, so the driver's single-GPU
+  `pytest -m gpu` covers it.  Reference values: the CPU oracle at small L, the
+  unsharded plan (itself pinned to the oracle/fixtures in test_gpu_parity.py) at
+  bandlimits with several 64-ring blocks.
+* `test_two_processes_*`: real one-process-per-GPU run over CUDA IPC + NVLink,
+  skipped when fewer than two GPUs are visible (run with `gpurun --gpus 2`).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10  # relative L2, FP64 (BASELINE.json north_star)
+
+
+@pytest.fixture(scope="module")
+def ms():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pxmcmc_b200 import msharded
+
+    return msharded
+
+
+def _dev(x):
+    from pxmcmc_b200 import device as D
+
+    return D.to_dev_c(x)
+
+
+def _host(t):
+    return t.detach().cpu().numpy()
+
+
+def _rand_c(rng, n):
+    return rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_wavelet_small_L_against_oracle(ms, world):
+    L, B, J = 20, 2.0, 1
+    rng = np.random.default_rng(5)
+    sim = ms.SimulatedRanks(world, lambda r, w: ms.ShardedWaveletPlan(L, B, J, r, w))
+    p0 = sim.plans[0]
+    coef = _rand_c(rng, p0.ncoefs)
+    pix = _rand_c(rng, L * (2 * L - 1))
+    from oracle import pxmcmc_ref as R
+
+    t = R.WaveletTransform(L, B, J)
+    expect = {"synthesis": t.inverse(coef), "synthesis_adjoint": t.inverse_adjoint(pix),
+              "analysis": t.forward(pix), "analysis_adjoint": t.forward_adjoint(coef)}
+    for name, full_in, in_lay, out_lay in [
+        ("synthesis", coef, "coef_layout", "pix_layout"),
+        ("synthesis_adjoint", pix, "pix_layout", "coef_layout"),
+        ("analysis", pix, "pix_layout", "coef_layout"),
+        ("analysis_adjoint", coef, "coef_layout", "pix_layout"),
+    ]:
+        ins = [_dev(getattr(p, in_lay).to_local(full_in)) for p in sim.plans]
+        outs = sim.run(name, ins)
+        full = np.zeros(getattr(p0, out_lay).n_full, dtype=complex)
+        for p, o in zip(sim.plans, outs):
+            getattr(p, out_lay).scatter_into(full, _host(o))
+        assert rel_l2(full, expect[name]) < TOL, name
+
+
+@pytest.mark.parametrize("world,L,B", [(2, 136, 2.0), (4, 200, 1.7), (8, 136, 2.0)])
+def test_wavelet_multiblock_against_unsharded(ms, world, L, B):
+    from pxmcmc_b200 import device as D
+
+    J = 2
+    rng = np.random.default_rng(11)
+    whole = D.WaveletPlan.get(L, B, J, 1)
+    sim = ms.SimulatedRanks(world, lambda r, w: ms.ShardedWaveletPlan(L, B, J, r, w))
+    p0 = sim.plans[0]
+    assert p0.ncoefs == whole.ncoefs
+    # every rank owns 1/world of the tables (up to the snake's granularity)
+    tb = [p.table_bytes for p in sim.plans]
+    assert max(tb) < 0.75 * whole.table_bytes
+    coef = _rand_c(rng, p0.ncoefs)
+    pix = _rand_c(rng, L * (2 * L - 1))
+    for name, full_in, in_lay, out_lay in [
+        ("synthesis", coef, "coef_layout", "pix_layout"),
+        ("synthesis_adjoint", pix, "pix_layout", "coef_layout"),
+        ("analysis", pix, "pix_layout", "coef_layout"),
+        ("analysis_adjoint", coef, "coef_layout", "pix_layout"),
+    ]:
+        expect = _host(getattr(whole, name)(_dev(full_in)))
+        # twice: the second call checks that the ring buffers are safely reused across calls
+        for _ in range(2):
+            ins = [_dev(getattr(p, in_lay).to_local(full_in)) for p in sim.plans]
+            outs = sim.run(name, ins)
+        full = np.zeros(getattr(p0, out_lay).n_full, dtype=complex)
+        for p, o in zip(sim.plans, outs):
+            getattr(p, out_lay).scatter_into(full, _host(o))
+        assert rel_l2(full, expect) < 1e-13, name
+
+
+@pytest.mark.parametrize("spin", [0, 2])
+@pytest.mark.parametrize("world,L", [(2, 24), (4, 150)])
+def test_sht_sharded(ms, spin, world, L):
+    from oracle import ssht_ref
+    from pxmcmc_b200 import device as D
+
+    rng = np.random.default_rng(3)
+    sim = ms.SimulatedRanks(world, lambda r, w: ms.ShardedShtPlan(L, spin, r, w))
+    flm = _rand_c(rng, L * L)
+    for el in range(abs(spin)):
+        flm[el * el:(el + 1) * (el + 1)] = 0
+    f = _rand_c(rng, L * (2 * L - 1))
+    whole = D.ShtPlan.get(L, spin, 1)
+    gl = D.to_dev_f(rng.standard_normal(L))
+    masks = [ms.flm_owner_mask(L, r, world) for r in range(world)]
+    assert np.array_equal(np.sum(masks, axis=0), np.ones(L * L))  # every order has exactly one owner
+    for name, harmonic_in in [("inverse", True), ("forward_adjoint", True), ("forward", False), ("inverse_adjoint", False)]:
+        for g in (None, gl):
+            if L <= 32 and g is None:
+                fn = getattr(ssht_ref, name)
+                expect = np.asarray(fn(flm if harmonic_in else f.reshape(L, 2 * L - 1), L, spin)).ravel()
+                tol = TOL
+            else:
+                expect = _host(getattr(whole, name)(_dev(flm if harmonic_in else f), gl=g))
+                tol = 1e-13
+            if harmonic_in:
+                # a rank is only required to hold its own orders: poison the rest
+                ins = [_dev(np.where(mk, flm, np.nan + 0j)) for mk in masks]
+                outs = sim.run(name, ins, gl=g)
+                full = np.zeros(L * (2 * L - 1), dtype=complex)
+                for p, o in zip(sim.plans, outs):
+                    p.pix_layout.scatter_into(full, _host(o))
+            else:
+                ins = [_dev(p.pix_layout.to_local(f)) for p in sim.plans]
+                outs = [_host(o) for o in sim.run(name, ins, gl=g)]
+                for mk, o in zip(masks, outs):
+                    assert not np.any(o[~mk])  # orders of other ranks read as zero
+                full = np.sum(outs, axis=0)
+            assert rel_l2(full, expect) < tol, (name, g is not None)
+
+
+def test_two_processes_over_nvlink():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "scripts", "msharded_check.py"), "--L", "136", "--B", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MSHARDED OK" in r.stdout
