@@ -547,9 +547,23 @@ int pxm_launch_gather(int scatter, const void* in, const int* idx, const double*
   return PXM_OK;
 }
 
+// force-load every kernel of this file (see pxm_legendre_preload)
 int pxm_elem_preload() {
   cudaFuncAttributes a;
   PXM_CUDA(cudaFuncGetAttributes(&a, k_lm_convert));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_soft_c));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_soft_r));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update_pair));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_resid));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage1));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage2));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_gradlogpi));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_lincomb));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_gather_w));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_scatter_w));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_r2c));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_csr_spmv));
   return PXM_OK;
 }
 

@@ -113,12 +113,15 @@ class PxMCMC:
 
     def _logpi_dev(self, Xd, Pd):
         """per-chain (logPi, L2, prior) as host numpy arrays (complex, complex, real)"""
+        red = getattr(self.forward, "_pxm_allreduce", None)  # m-sharded operator: partial sums per rank
         if getattr(self.forward, "_diag", None) is not None:
             data_d, ic_d = self.forward._upload()
-            L2 = D.to_host(D.reduce_dev(1, Pd, b=data_d, c=ic_d))
+            L2d = D.reduce_dev(1, Pd, b=data_d, c=ic_d)
+            L2 = D.to_host(red(L2d) if red else L2d)
         else:
             L2 = np.array([self._host_L2(D.to_host(Pd[c])) for c in range(Pd.shape[0])])
-        pr = D.to_host(self._prior_dev(Xd))
+        prd = self._prior_dev(Xd)
+        pr = D.to_host(red(prd) if red else prd)
         return -self.mu * pr - L2, L2, pr
 
     def _host_L2(self, preds):

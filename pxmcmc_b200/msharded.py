@@ -228,29 +228,146 @@ class ShardedShtPlan(_ShardedBase):
 # barrier -- where only a single GPU is available (the driver's `pytest -m gpu`).
 # ----------------------------------------------------------------------------
 class SimulatedRanks:
-    def __init__(self, world, make_plan):
-        """make_plan(rank, world) -> a sharded plan created with exchange=None"""
+    def __init__(self, world, *factories):
+        """factories: make_plan(rank, world) -> a sharded plan created with exchange=None.
+        `plan_sets[k][r]` is rank r's plan from factory k; `plans` = `plan_sets[0]`."""
         self.world = world
-        self.plans = [make_plan(r, world) for r in range(world)]
-        ptrs = [p.ws_ptr for p in self.plans]
-        for p in self.plans:
-            p.attach_pointers(ptrs)
+        self.plan_sets = []
+        for make_plan in factories:
+            plans = [make_plan(r, world) for r in range(world)]
+            ptrs = [p.ws_ptr for p in plans]
+            for p in plans:
+                p.attach_pointers(ptrs)
+            self.plan_sets.append(plans)
+        self.plans = self.plan_sets[0]
         self.streams = [torch.cuda.Stream() for _ in range(world)]
         torch.cuda.synchronize()
 
-    def run(self, method, inputs, **kw):
-        """calls plan.<method>(inputs[r]) for every rank, each on its own stream, and
-        returns the per-rank outputs after all of them have finished"""
+    def map(self, fn):
+        """fn(rank) is called for every rank with that rank's stream current; it must only
+        enqueue work (no host synchronisation: the other ranks' kernels are not queued yet).
+        Returns the per-rank results after every stream has drained."""
         outs = []
         cur = torch.cuda.current_stream()
-        for r, (p, st) in enumerate(zip(self.plans, self.streams)):
+        for r, st in enumerate(self.streams):
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                outs.append(getattr(p, method)(inputs[r], **kw))
+                outs.append(fn(r))
         for st in self.streams:
             cur.wait_stream(st)
         torch.cuda.synchronize()
-        for p in self.plans:
-            if not p.barrier_ok():
-                raise RuntimeError("peer barrier timed out")
+        for plans in self.plan_sets:
+            for p in plans:
+                if not p.barrier_ok():
+                    raise RuntimeError("peer barrier timed out")
         return outs
+
+    def run(self, method, inputs, **kw):
+        """plan.<method>(inputs[r]) for every rank of the first plan set"""
+        return self.map(lambda r: getattr(self.plans[r], method)(inputs[r], **kw))
+
+
+# ----------------------------------------------------------------------------
+# sharded counterparts of the reference-facing classes: same method names, LOCAL
+# vectors.  They plug into pxmcmc_b200.forward.ForwardOperator and the samplers of
+# pxmcmc_b200.mcmc unchanged (which only see vectors of the local length).
+# ----------------------------------------------------------------------------
+class ShardedSphericalWaveletTransform:
+    """`SphericalWaveletTransform` (pxmcmc/transforms.py:59-166) of one rank: `inverse`,
+    `inverse_adjoint`, `forward`, `forward_adjoint` on local coefficient / pixel vectors."""
+
+    _pxm_native = True
+
+    def __init__(self, L, B, J_min, rank, world, exchange=None, nchains=1, plan=None):
+        self.plan = plan if plan is not None else ShardedWaveletPlan(L, B, J_min, rank, world, nbatch=nchains, exchange=exchange)
+        self.L, self.B, self.J_min = L, B, J_min
+        self.bandlimits = list(self.plan.bandlimits)
+        self.ncoefs = self.plan.ncoefs_local          # local sizes: what the sampler sees
+        self.ncoefs_global = self.plan.ncoefs
+        self.coef_layout, self.pix_layout = self.plan.coef_layout, self.plan.pix_layout
+
+    def _apply(self, name, X):
+        return D.like_input(getattr(self.plan, name)(D.to_dev_c(X)), X)
+
+    def forward(self, X):
+        return self._apply("analysis", X)
+
+    def inverse(self, X):
+        return self._apply("synthesis", X)
+
+    def inverse_adjoint(self, X):
+        return self._apply("synthesis_adjoint", X)
+
+    def forward_adjoint(self, X):
+        return self._apply("analysis_adjoint", X)
+
+
+class ShardedWeakLensing:
+    """`WeakLensing` (pxmcmc/measurements.py:185-304) of one rank: convergence rows in,
+    masked + covariance-weighted shear of the same rows out, and the adjoint chain.
+    The harmonic coefficients in between stay m-sharded; the kappa->gamma kernel is the
+    per-degree multiplier of the spin-2 transform."""
+
+    _pxm_native = True
+
+    def __init__(self, L, rank, world, mask=None, ngal=None, exchange=None, plans=None):
+        from .measurements import WeakLensing
+
+        host = WeakLensing(L, mask=mask, ngal=ngal)  # host-side set-up only (mask, inv_cov, kernel)
+        self.L, self.rank, self.world = L, rank, world
+        self.s0, self.s2 = plans if plans is not None else (
+            ShardedShtPlan(L, 0, rank, world, exchange=exchange), ShardedShtPlan(L, 2, rank, world, exchange=exchange))
+        self.pix_layout = self.s0.pix_layout
+        (t0, t1), n = self.pix_layout.rows[0], 2 * L - 1
+        local_mask = host.mask[t0:t1].ravel()
+        self.npix = self.pix_layout.n_local
+        self.ndata = int(local_mask.sum())
+        # position of the local data inside the reference's full data vector (C-order boolean gather)
+        before = int(host.mask[:t0].sum())
+        self.data_index = before + np.arange(self.ndata, dtype=np.int64)
+        self.ndata_global = int(host.mask.sum())
+        self.inv_cov = np.asarray(host.inv_cov)[self.data_index]
+        dv = D.dev()
+        self._idx = torch.from_numpy(np.flatnonzero(local_mask).astype(np.int32)).to(dv)
+        self._w = D.to_dev_f(self.inv_cov)
+        self._gl = D.to_dev_f(host._kernel_per_l())
+
+    def forward(self, kappa):
+        x = D.to_dev_c(kappa)
+        klm = self.s0.forward(x)
+        gamma = self.s2.inverse(klm, gl=self._gl)
+        return D.like_input(D.gather_dev(gamma, self._idx, self._w, self.ndata), kappa)
+
+    def adjoint(self, gamma):
+        y = D.to_dev_c(gamma)
+        g = D.scatter_dev(y, self._idx, self._w, self.npix)
+        glm = self.s2.inverse_adjoint(g, gl=self._gl)
+        return D.like_input(self.s0.forward_adjoint(glm), gamma)
+
+
+def sharded_s2_wavelets_l1(transform, T, L, B, J_min, cls=None, **kw):
+    """The reference's `S2_Wavelets_L1` (or a subclass) restricted to this rank's
+    coefficients: thresholds and prior weights are the full vectors gathered at the
+    local positions, so prox and Langevin update are element-for-element those of the
+    unsharded sampler."""
+    from . import prior as P
+
+    full = (cls or P.S2_Wavelets_L1)("synthesis", transform.inverse, transform.inverse_adjoint, T, L, B, J_min, **kw)
+    idx = transform.coef_layout.index
+    full.T = np.ascontiguousarray(np.asarray(full.T)[idx])
+    full.map_weights = np.ascontiguousarray(np.asarray(full.map_weights)[idx])
+    full._Tdev = full._wdev = None
+    return full
+
+
+def allreduce_sum(group=None):
+    """scalar reductions across ranks (log posterior, L2, prior): what the samplers call
+    through `forward._pxm_allreduce` when the operator is sharded"""
+    import torch.distributed as dist
+
+    def f(t):
+        t = t.clone()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t
+
+    return f

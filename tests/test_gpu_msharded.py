@@ -157,3 +157,82 @@ def test_two_processes_over_nvlink():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "MSHARDED OK" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_weaklensing_myula_iteration_sharded(ms, world):
+    """config 4 of BASELINE.json in miniature: one MYULA iteration of the spin-2 weak-lensing
+    operator with an S2_Wavelets_L1 prior, sharded over `world` ranks, against the unsharded
+    sampler with the same injected noise (which test_gpu_parity.py pins to the reference fixture)."""
+    import torch
+
+    from pxmcmc_b200 import device as D
+    from pxmcmc_b200.forward import ForwardOperator
+    from pxmcmc_b200.mcmc import MYULA, PxMCMCParams
+    from pxmcmc_b200.measurements import WeakLensing
+    from pxmcmc_b200.prior import S2_Wavelets_L1
+    from pxmcmc_b200.transforms import SphericalWaveletTransform
+
+    L, B, J = 72, 2.0, 2
+    rng = np.random.default_rng(21)
+    mask = rng.random((L, 2 * L - 1)) < 0.6
+    ngal = np.full((L, 2 * L - 1), 30.0)
+    wl = WeakLensing(L, mask=mask, ngal=ngal)
+    tr = SphericalWaveletTransform(L, B, J)
+    data = _rand_c(rng, wl.ndata)
+    sig = 1.0 / wl.inv_cov
+    op = ForwardOperator(data, sig, "synthesis", transform=tr, measurement=wl, nparams=tr.ncoefs)
+    prm = PxMCMCParams(delta=1e-3, lmda=2e-3, mu=1.0, nsamples=1, verbosity=0, track=[])
+    reg = S2_Wavelets_L1("synthesis", tr.inverse, tr.inverse_adjoint, prm.lmda * prm.mu * 50, L=L, B=B, J_min=J)
+    m = MYULA(op, reg, prm)
+    X = rng.laplace(size=tr.ncoefs) + 0j
+    P = op.forward(X)
+    w = rng.standard_normal(tr.ncoefs)
+    Tfull = np.asarray(reg.T)
+    gradg = op.calc_gradg(P)
+    Xn = D.to_host(D.myula_update_dev(D.to_dev_c(X), None, D.to_dev_c(gradg), D.to_dev_f(Tfull), 0.0, prm.delta, prm.lmda,
+                                      w_re=D.to_dev_f(w), noise_mode=1))
+    Pn = op.forward(Xn)
+    lp, l2, pr = m._logpi_dev(m._state(Xn), m._state(Pn))
+
+    sim = ms.SimulatedRanks(world, lambda r, ws: ms.ShardedWaveletPlan(L, B, J, r, ws),
+                            lambda r, ws: ms.ShardedShtPlan(L, 0, r, ws), lambda r, ws: ms.ShardedShtPlan(L, 2, r, ws))
+    ops, regs, Xl, Pl, wl_r = [], [], [], [], []
+    for r in range(world):
+        t_r = ms.ShardedSphericalWaveletTransform(L, B, J, r, world, plan=sim.plan_sets[0][r])
+        w_r = ms.ShardedWeakLensing(L, r, world, mask=mask, ngal=ngal, plans=(sim.plan_sets[1][r], sim.plan_sets[2][r]))
+        o_r = ForwardOperator(data[w_r.data_index], sig[w_r.data_index], "synthesis", transform=t_r, measurement=w_r,
+                              nparams=t_r.ncoefs)
+        o_r._upload()
+        g_r = ms.sharded_s2_wavelets_l1(t_r, prm.lmda * prm.mu * 50, L, B, J)
+        assert np.array_equal(np.asarray(g_r.T), Tfull[t_r.coef_layout.index])
+        ops.append(o_r)
+        regs.append(g_r)
+        wl_r.append(w_r)
+        Xl.append(D.to_dev_c(t_r.coef_layout.to_local(X)))
+        Pl.append(D.to_dev_c(P[w_r.data_index]))
+    assert sum(w_r.ndata for w_r in wl_r) == wl.ndata
+    Tl = [g._T_args()[0] for g in regs]
+    noise = [D.to_dev_f(ops[r].transform.coef_layout.to_local(w)) for r in range(world)]
+    torch.cuda.synchronize()
+
+    def iteration(r):
+        g = ops[r].calc_gradg(Pl[r])
+        xn = D.myula_update_dev(Xl[r], None, g, Tl[r], 0.0, prm.delta, prm.lmda, w_re=noise[r], noise_mode=1)
+        return xn, ops[r].forward(xn)
+
+    outs = sim.map(iteration)
+    Xs, Ps = np.zeros_like(Xn), np.zeros_like(Pn)
+    for r, (xn, pn) in enumerate(outs):
+        ops[r].transform.coef_layout.scatter_into(Xs, _host(xn))
+        Ps[wl_r[r].data_index] = _host(pn)
+    assert rel_l2(Xs, Xn) < 1e-12 and rel_l2(Ps, Pn) < 1e-12
+    # prox support / sign pattern identical (north_star)
+    assert np.array_equal(Xs == 0, Xn == 0) and np.array_equal(np.sign(Xs.real), np.sign(Xn.real))
+    # log posterior: partial sums per rank add up to the unsharded value
+    parts = []
+    for r in range(world):
+        mr = MYULA(ops[r], regs[r], prm)
+        parts.append(mr._logpi_dev(mr._state(outs[r][0]), mr._state(outs[r][1])))
+    assert abs(sum(p[1][0] for p in parts) - l2[0]) <= 1e-11 * abs(l2[0])
+    assert abs(sum(p[2][0] for p in parts) - pr[0]) <= 1e-11 * abs(pr[0])

@@ -220,3 +220,99 @@ def test_chain_sharding_gloo_world_size_2(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert "GATHER_OK" in outs[0][0]
+
+
+# ---------------------------------------------------------------- m-sharded partition (host logic)
+def test_msharded_partition_is_a_partition():
+    """every azimuthal order and every ring of every grid has exactly one owner; ring ranges are
+    whole blocks of 64; the snake keeps the triangular Legendre work balanced"""
+    from pxmcmc_b200 import msharded as ms
+
+    for world in (1, 2, 3, 4, 8):
+        for ell in (3, 64, 65, 130, 256, 512, 1024):
+            for rot in (0, 1, 5):
+                seen = np.zeros(ell, dtype=int)
+                for r in range(world):
+                    t0, t1 = ms.ring_range(ell, rot, r, world)
+                    assert t0 % 64 == 0 and 0 <= t0 <= t1 <= ell
+                    seen[t0:t1] += 1
+                assert np.all(seen == 1)
+        L = 512
+        work = np.zeros(world)
+        for am in range(L):
+            o = ms.owner_of_m(am, world)
+            assert 0 <= o < world
+            work[o] += L - am
+        assert work.max() / work.mean() < 1.02
+    masks = [ms.flm_owner_mask(12, r, 3) for r in range(3)]
+    assert np.array_equal(np.sum(masks, axis=0), np.ones(144))
+    with pytest.raises(Exception):
+        ms.ring_range(16, 0, 2, 2)
+
+
+def test_msharded_layout_roundtrip():
+    from pxmcmc_b200 import msharded as ms
+
+    ells, world = [4, 8, 100, 200, 200], 4
+    rng = np.random.default_rng(0)
+    n = sum(e * (2 * e - 1) for e in ells)
+    full = rng.standard_normal(n)
+    back = np.zeros(n)
+    total = 0
+    for r in range(world):
+        lay = ms.MapLayout(ells, range(1, len(ells) + 1), r, world)
+        loc = lay.to_local(full)
+        assert loc.shape == (lay.n_local,)
+        lay.scatter_into(back, loc)
+        total += lay.n_local
+    assert total == n and np.array_equal(back, full)
+    # small grids are rotated over the ranks instead of piling up on rank 0
+    owners = {next(r for r in range(world) if ms.ring_range(8, rot, r, world)[1] > 0) for rot in range(4)}
+    assert owners == {0, 1, 2, 3}
+
+
+_MS_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from pxmcmc_b200 import msharded as ms
+dist.init_process_group("gloo", rank=int(os.environ["RANK"]), world_size=int(os.environ["WORLD_SIZE"]))
+rank, world = dist.get_rank(), dist.get_world_size()
+# scalar reductions of a sharded sampler: partial sums per rank -> identical totals everywhere
+red = ms.allreduce_sum()
+ells = [4, 8, 70, 130]
+lay = ms.MapLayout(ells, range(1, 5), rank, world)
+full = np.arange(lay.n_full, dtype=float)
+part = torch.tensor([lay.to_local(full).sum()], dtype=torch.float64)
+tot = red(part)
+assert part.item() != tot.item() or world == 1
+assert tot.item() == full.sum()
+# local -> full reassembly through all_gather_object (what a driver does to save a sharded chain)
+pieces = [None] * world
+dist.all_gather_object(pieces, (lay.index, lay.to_local(full)))
+back = np.full(lay.n_full, -1.0)
+for idx, loc in pieces:
+    back[idx] = loc
+assert np.array_equal(back, full)
+if rank == 0:
+    print("MS_HOST_OK")
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_msharded_host_logic_gloo_world_size_2(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    script = tmp_path / "ms_worker.py"
+    script.write_text(_MS_WORKER.format(root=ROOT))
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e[-2000:]
+    assert "MS_HOST_OK" in outs[0][0]
