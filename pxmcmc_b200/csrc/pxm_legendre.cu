@@ -280,19 +280,21 @@ int launch_cfg(const double* tab, const PxmPeers& b, const PxmPeers& c, const Px
 template <int ORIENT>
 int launch_orient(const double* tab, const PxmPeers& b, const PxmPeers& c, const PxmLegItem* items,
                   const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream) {
-  constexpr int ST = 4;
+  // pipeline depth: few right-hand sides (single chain) make the kernel a pure table stream, so the
+  // narrow variants keep 8 stages (~10 KB each) in flight per CTA; the wide ones are DMMA-bound
+  constexpr int ST = 4, STN = 8;
   if (ORIENT == 0) {
     if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
     if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream);
   } else {
     if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
     if (nld == 64) return launch_cfg<ORIENT, 64, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 32) return launch_cfg<ORIENT, 32, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, ST>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 2, 4, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream);
   }
   pxm_set_error("legendre: unsupported column count " + std::to_string(nld));
   return PXM_ERR_ARG;

@@ -207,6 +207,7 @@ class ShardedShtPlan(_ShardedBase):
         assert self.pix_layout.rows == [(t0.value, t1.value)]
         self.npix_local = self.pix_layout.n_local
         self.nlm = self.L * self.L
+        self.table_bytes = int(lib.pxm_sht_plan_table_bytes(h))  # Lambda + W families, this rank's orders
         self._attach(exchange)
 
     def inverse(self, flm, gl=None):
