@@ -27,6 +27,7 @@ extern "C" {
 
 typedef struct pxm_sht_plan pxm_sht_plan;
 typedef struct pxm_wav_plan pxm_wav_plan;
+typedef struct pxm_hpx_plan pxm_hpx_plan;
 
 const char* pxm_last_error(void);
 int pxm_init(int device);
@@ -66,6 +67,21 @@ int pxm_wav_analysis_adjoint(pxm_wav_plan* plan, const void* d_coef, void* d_pix
 /* host-only: kappa0[L], kappa[(J-J_min+1)][L] of pys2let.wavelet_tiling
  * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);
+
+/* ---- HEALPix RING maps <-> harmonic coefficients (data preparation, once per run) ---
+ * healpy.alm2map / healpy.map2alm as wrapped by utils.alm2map / utils.map2alm
+ * (pxmcmc/utils.py:106-113; experiments/earthtopography/main.py:80-82,
+ * experiments/weaklensing/main.py:31-37).  L = lmax + 1; flm: [L*L] complex with the
+ * ssht index l*l+l+m (pys2let.lm_hp2lm converts from healpy's m >= 0 storage);
+ * map: [12 nside^2] complex (a real map has zero imaginary part).
+ * pxm_hpx_alm2map:          map[p] = sum_lm flm Y_lm(p)
+ * pxm_hpx_map2alm_adjoint:  flm    = sum_p  conj(Y_lm(p)) map[p]     (no weights)
+ * healpy.map2alm(iter=k) = (4 pi / npix) x adjoint, then k Jacobi refinements
+ * alm += (4 pi / npix) adjoint(map - alm2map(alm)), assembled by the host layer. */
+int pxm_hpx_plan_create(int nside, int L, pxm_hpx_plan** out);
+int pxm_hpx_plan_destroy(pxm_hpx_plan* plan);
+int pxm_hpx_alm2map(pxm_hpx_plan* plan, const void* d_flm, void* d_map, void* stream);
+int pxm_hpx_map2alm_adjoint(pxm_hpx_plan* plan, const void* d_map, void* d_flm, void* stream);
 
 /* ---- m-sharded plans: one chain, bandlimit too large or too slow for one GPU ---
  * (no counterpart in the reference, which is single-process)

@@ -37,6 +37,10 @@ SIGNATURES = {
     "pxm_wav_analysis": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_analysis_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wavelet_tiling": (_i, [_i, _d, _i, _vp, _vp, C.POINTER(_i)]),
+    "pxm_hpx_plan_create": (_i, [_i, _i, C.POINTER(_vp)]),
+    "pxm_hpx_plan_destroy": (_i, [_vp]),
+    "pxm_hpx_alm2map": (_i, [_vp, _vp, _vp, _vp]),
+    "pxm_hpx_map2alm_adjoint": (_i, [_vp, _vp, _vp, _vp]),
     "pxm_sht_plan_create_sharded": (_i, [_i, _i, _i, _i, _i, C.POINTER(_vp)]),
     "pxm_wav_plan_create_sharded": (_i, [_i, _d, _i, _i, _i, _i, C.POINTER(_vp)]),
     "pxm_sht_plan_prepare": (_i, [_vp]),

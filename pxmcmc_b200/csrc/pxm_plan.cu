@@ -67,6 +67,7 @@ struct RingBuf {
   int ell = 0;
   bool paired = true;
   int nslots = 0;
+  int rows = 0;         // rings of the grid (= ell on MW sampling; 4 nside - 1 on HEALPix)
   int rot = 0;          // rotation of the ring-block ownership (scale index)
   int t0 = 0, t1 = 0;   // rings owned by this rank
   ull off = 0;          // doubles into the workspace
@@ -86,6 +87,7 @@ struct HarmBuf {
 
 void make_ring(RingBuf& R, int ell, bool paired, int nld, ull& cursor, const Shard& sh = Shard(), int rot = 0) {
   R.ell = ell;
+  R.rows = ell;
   R.paired = paired;
   R.rot = rot;
   pxm_ring_range(ell, rot, sh.rank, sh.world, &R.t0, &R.t1);
@@ -233,7 +235,7 @@ void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf
       it.seg_count = 1;
       it.nmt_out = sg.nmt;
       it.cost = sg.nk * sg.nmt;
-      it.dst = pxm_owner_of_ring_block(R.ell, i, R.rot, sh.world);  // pushed to the owner of these 64 rings
+      it.dst = pxm_owner_of_ring_block(R.rows, i, R.rot, sh.world);  // pushed to the owner of these 64 rings
       S.segs.push_back(sg);
       S.items.push_back(it);
     }
@@ -269,7 +271,7 @@ void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H,
         // one segment per rank that owns part of the source rings (pulled from that rank's workspace)
         for (int q = 0; q < sh.world; ++q) {
           int qt0, qt1;
-          pxm_ring_range(src.R->ell, src.R->rot, q, sh.world, &qt0, &qt1);
+          pxm_ring_range(src.R->rows, src.R->rot, q, sh.world, &qt0, &qt1);
           if (qt1 <= qt0) continue;
           const int tb0 = qt0 / PXM_TILE_T, tb1 = pxm_ceil_div(qt1, PXM_TILE_T);
           PxmLegSeg sg = {};
@@ -906,6 +908,102 @@ int pxm_wav_analysis(pxm_wav_plan* p, const void* d_pix, void* d_coef, int nbatc
 }
 int pxm_wav_analysis_adjoint(pxm_wav_plan* p, const void* d_coef, void* d_pix, int nbatch, void* stream) {
   return wav_run(p, 3, const_cast<void*>(d_coef), d_pix, nbatch, stream);
+}
+
+// =========================================================================
+//        HEALPix plan (healpy.alm2map / map2alm: data preparation, once per run)
+// =========================================================================
+}  // extern "C"
+
+void pxm_hpx_half_angles(int nside, double* out);
+
+struct pxm_hpx_plan {
+  int nside = 0, L = 0, nrings = 0, nld = 0;
+  TableRef lam;
+  PxmDevVec<double> d_half;
+  double* d_tab = nullptr;
+  double* d_ws = nullptr;
+  RingBuf R;
+  HarmBuf H;
+  Stage s_lam, a_lam;
+};
+
+extern "C" {
+
+int pxm_hpx_plan_create(int nside, int L, pxm_hpx_plan** out) {
+  PXM_REQUIRE(nside >= 1 && nside <= 8192 && (nside & (nside - 1)) == 0, "nside must be a power of two in [1, 8192]");
+  PXM_REQUIRE(L >= 1 && L <= 1024, "L (= lmax + 1) must be in [1, 1024]");
+  std::unique_ptr<pxm_hpx_plan> p(new pxm_hpx_plan);
+  p->nside = nside;
+  p->L = L;
+  p->nrings = 4 * nside - 1;
+  p->nld = pxm_legendre_pad_columns(4);
+  std::vector<double> half(2 * (size_t)p->nrings);
+  pxm_hpx_half_angles(nside, half.data());
+  PXM_TRY(p->d_half.upload(half));
+  pxm_make_table_layout(p->lam.T, L, p->nrings, L, 0, 0, L, 0);
+  p->lam.T.d_half_angles = p->d_half.d;
+  p->lam.family = 0;
+  const ull tdoubles = std::max<ull>(p->lam.T.doubles, 1);
+  PXM_CUDA(cudaMalloc(&p->d_tab, tdoubles * 8));
+  PXM_CUDA(cudaMemset(p->d_tab, 0, tdoubles * 8));
+  PXM_TRY(pxm_generate_lambda(p->lam.T, p->d_tab, nullptr, 0));
+  ull wcur = PXM_WS_RESERVED;
+  p->R.ell = L;
+  p->R.rows = p->nrings;
+  p->R.paired = true;
+  p->R.nslots = L;
+  p->R.t0 = 0;
+  p->R.t1 = p->nrings;
+  p->R.slot_stride = (ull)pxm_round_up(p->nrings, 64) * p->nld;
+  p->R.off = wcur;
+  wcur += p->R.doubles();
+  make_harm(p->H, L, true, p->nld, wcur);
+  PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
+  PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
+  PXM_TRY(p->H.d_slot_off.upload(p->H.slot_off));
+  build_s_items(p->s_lam, p->lam, p->H, p->R, p->nld);
+  build_a_items(p->a_lam, {{&p->lam, &p->R}}, p->H, p->nld);
+  PXM_TRY(p->s_lam.upload());
+  PXM_TRY(p->a_lam.upload());
+  *out = p.release();
+  return PXM_OK;
+}
+
+int pxm_hpx_plan_destroy(pxm_hpx_plan* p) {
+  if (!p) return PXM_OK;
+  p->s_lam.release();
+  p->a_lam.release();
+  p->H.d_slot_off.release();
+  p->d_half.release();
+  if (p->d_tab) cudaFree(p->d_tab);
+  if (p->d_ws) cudaFree(p->d_ws);
+  delete p;
+  return PXM_OK;
+}
+
+// map[p] = sum_lm flm Y_lm(theta_p, phi_p)   (complex field; flm index l*l+l+m)
+int pxm_hpx_alm2map(pxm_hpx_plan* p, const void* d_flm, void* d_map, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  PXM_TRY(pxm_launch_lm_convert(1, const_cast<void*>(d_flm), p->d_ws, p->H.d_slot_off.d, nullptr, nullptr, p->L, 1,
+                                p->nld, 1, st));
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(0, p->d_tab, p->d_ws, p->d_ws, p->s_lam.d_items.d, p->s_lam.d_segs.d,
+                              (int)p->s_lam.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(1, st); PXM_TRY(pxm_hpx_ring_dft_launch(1, p->nside, p->L, d_map, p->d_ws, p->R.off, p->R.slot_stride, p->nld, st)); }
+  return PXM_OK;
+}
+
+// flm = sum_p conj(Y_lm(theta_p, phi_p)) map[p]   (no quadrature weight: the Euclidean adjoint of alm2map;
+// healpy.map2alm = (4 pi / npix) x this, plus Jacobi iterations built from the two calls)
+int pxm_hpx_map2alm_adjoint(pxm_hpx_plan* p, const void* d_map, void* d_flm, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  { ProfScope _ps(1, st); PXM_TRY(pxm_hpx_ring_dft_launch(0, p->nside, p->L, d_map, p->d_ws, p->R.off, p->R.slot_stride, p->nld, st)); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch(1, p->d_tab, p->d_ws, p->d_ws, p->a_lam.d_items.d, p->a_lam.d_segs.d,
+                              (int)p->a_lam.items.size(), p->nld, st, pxm_debug_naive())); }
+  PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, nullptr, nullptr, p->L, 1, p->nld, 1, st));
+  return PXM_OK;
 }
 
 // =========================================================================

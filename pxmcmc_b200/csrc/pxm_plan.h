@@ -40,6 +40,9 @@ struct PxmTableLayout {
   std::vector<int> slot_m, lb0, nlb;
   std::vector<unsigned long long> tile_off;  // doubles, relative to the arena the layout was made for
   size_t doubles = 0;
+  // device array [rings][2] of (sin, cos) of theta/2 for ring grids that are not MW (HEALPix);
+  // nullptr: MW ring t of bandlimit grid_L
+  const double* d_half_angles = nullptr;
 };
 
 // m-sharding: azimuthal orders are dealt to the ranks in a snake so that the
@@ -89,6 +92,8 @@ int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, 
                               cudaStream_t stream, int naive);
 int pxm_legendre_preload(int nld);
 int pxm_elem_preload();
+int pxm_hpx_ring_dft_launch(int dir, int nside, int L, const void* map, double* F, unsigned long long f_off,
+                            unsigned long long slot_stride, int nld, cudaStream_t stream);
 int pxm_fft_choose_M(int n, int* logM);
 int pxm_fft_rings_per_cta_log(int M);
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,

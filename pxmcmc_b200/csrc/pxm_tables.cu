@@ -23,7 +23,8 @@
 namespace {
 
 __global__ void k_wigner_tiles(double* __restrict__ tab, const PxmWigSlot* __restrict__ slots, int nslots, int rings,
-                               int grid_L, int lmax, int spin, const double* __restrict__ g) {
+                               int grid_L, int lmax, int spin, const double* __restrict__ g,
+                               const double* __restrict__ half_angles) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nslots * rings) return;
   const int si = (int)(idx / rings), t = (int)(idx % rings);
@@ -34,7 +35,12 @@ __global__ void k_wigner_tiles(double* __restrict__ tab, const PxmWigSlot* __res
   int lend = am + 16 * (sl.lb0 + sl.nlb);
   if (lend > lmax) lend = lmax;
   double sh, ch;
-  pxm_mw_half_angle(t, grid_L, &sh, &ch);
+  if (half_angles) {
+    sh = half_angles[2 * t];
+    ch = half_angles[2 * t + 1];
+  } else {
+    pxm_mw_half_angle(t, grid_L, &sh, &ch);
+  }
   PxmWigner w;
   pxm_wigner_init(w, sl.m, -spin, sh, ch);
   const double ssign = (as & 1) ? -1.0 : 1.0;
@@ -178,7 +184,7 @@ int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_
   PXM_TRY(ds.upload(hs));
   const long long total = (long long)T.nslots * T.rings;
   k_wigner_tiles<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_tab, ds.d, T.nslots, T.rings, T.grid_L, T.lmax,
-                                                                   T.spin, d_g);
+                                                                   T.spin, d_g, T.d_half_angles);
   PXM_LAUNCHED();
   PXM_CUDA(cudaStreamSynchronize(st));
   ds.release();

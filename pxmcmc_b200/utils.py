@@ -205,9 +205,153 @@ def mw_size(L):
     return L * (2 * L - 1)
 
 
-def map2alm(image, lmax, **kwargs):
-    raise NotImplementedError("HEALPix map2alm is setup-time only and not part of this build yet (SURVEY.md 8 a13)")
+# ----------------------------------------------------------------------------
+# HEALPix <-> harmonic space (data preparation of the reference's drivers)
+# ----------------------------------------------------------------------------
+class _LazyDevice:
+    """pxmcmc_b200.device on first use (keeps `import pxmcmc_b200.utils` free of torch)"""
+
+    def __getattr__(self, name):
+        from . import device
+
+        return getattr(device, name)
+
+
+D = _LazyDevice()
+
+
+def alm_hp_size(lmax):
+    return (lmax + 1) * (lmax + 2) // 2
+
+
+def alm_hp_index(el, m, lmax):
+    """healpy.Alm.getidx: m-major storage of the m >= 0 coefficients"""
+    return m * (2 * lmax + 1 - m) // 2 + el
+
+
+def lm_hp2lm(flm_hp, L):
+    """pys2let.lm_hp2lm (experiments/earthtopography/main.py:82): healpy's m >= 0 alm of a REAL map ->
+    ssht ordering l*l+l+m with f_{l,-m} = (-1)^m conj(f_{l,m})"""
+    flm_hp = np.asarray(flm_hp, dtype=complex)
+    lmax = L - 1
+    if flm_hp.size != alm_hp_size(lmax):
+        raise ValueError("alm has the wrong size for this bandlimit")
+    flm = np.zeros(L * L, dtype=complex)
+    for m in range(L):
+        els = np.arange(m, L)
+        a = flm_hp[alm_hp_index(els, m, lmax)]
+        flm[els * els + els + m] = a
+        if m > 0:
+            flm[els * els + els - m] = (-1.0) ** m * np.conj(a)
+    return flm
+
+
+def lm2lm_hp(flm, L):
+    """pys2let.lm2lm_hp: the m >= 0 half in healpy's storage"""
+    flm = np.asarray(flm, dtype=complex)
+    lmax = L - 1
+    out = np.zeros(alm_hp_size(lmax), dtype=complex)
+    for m in range(L):
+        els = np.arange(m, L)
+        out[alm_hp_index(els, m, lmax)] = flm[els * els + els + m]
+    return out
+
+
+def alm2map_mw(flm, L, spin=0):
+    """pys2let.alm2map_mw = ssht inverse transform on MW sampling; returns the flat complex map
+    (experiments/earthtopography/main.py:82, tests/conftest.py:49 of the reference)"""
+    from . import sht
+
+    return np.asarray(sht.inverse(flm, L, Spin=spin)).ravel()
+
+
+class _HealpixPlan:
+    _cache = {}
+
+    @classmethod
+    def get(cls, nside, L):
+        import torch
+
+        key = (int(nside), int(L), torch.cuda.current_device() if torch.cuda.is_available() else -1)
+        if key not in cls._cache:
+            cls._cache[key] = cls(nside, L)
+        return cls._cache[key]
+
+    def __init__(self, nside, L):
+        import ctypes as C
+
+        from ._lib import check, lib
+
+        D.dev()
+        self.nside, self.L, self.npix = int(nside), int(L), 12 * int(nside) ** 2
+        h = C.c_void_p()
+        check(lib.pxm_hpx_plan_create(self.nside, self.L, C.byref(h)))
+        self.h = h
+
+    def synth(self, flm_d):
+        """complex device flm [L*L] -> complex device map [npix]"""
+        import torch
+
+        from ._lib import check, lib, ptr, stream_ptr
+
+        out = torch.empty(self.npix, dtype=D.CDT, device=flm_d.device)
+        check(lib.pxm_hpx_alm2map(self.h, ptr(flm_d), ptr(out), stream_ptr()))
+        return out
+
+    def adjoint(self, map_d):
+        import torch
+
+        from ._lib import check, lib, ptr, stream_ptr
+
+        out = torch.empty(self.L * self.L, dtype=D.CDT, device=map_d.device)
+        check(lib.pxm_hpx_map2alm_adjoint(self.h, ptr(map_d), ptr(out), stream_ptr()))
+        return out
+
+
+def _nside_of(npix):
+    nside = int(round(np.sqrt(npix / 12.0)))
+    if 12 * nside * nside != npix or nside & (nside - 1):
+        raise ValueError("not a HEALPix map: size must be 12 nside^2 with nside a power of two")
+    return nside
+
+
+def map2alm(image, lmax, iter=3, **kwargs):
+    """healpy.map2alm as the reference wraps it (pxmcmc/utils.py:106-108): RING-ordered real map ->
+    a_lm, m >= 0, healpy storage; uniform weights 4 pi / npix and `iter` Jacobi refinements
+    (healpy's default iter=3).  Every transform runs on the device (pxm_hpx_*)."""
+    unsupported = {k: v for k, v in kwargs.items() if k not in ("mmax", "pol", "use_weights", "use_pixel_weights", "verbose", "datapath", "gal_cut")}
+    if unsupported or kwargs.get("use_weights") or kwargs.get("use_pixel_weights") or kwargs.get("gal_cut"):
+        raise NotImplementedError(f"map2alm options not supported: {sorted(kwargs)}")
+    if kwargs.get("mmax") not in (None, lmax):
+        raise NotImplementedError("mmax != lmax is not supported")
+    image = np.asarray(image, dtype=float)
+    if image.ndim != 1:
+        raise NotImplementedError("polarised (T, Q, U) maps are not supported")
+    L = int(lmax) + 1
+    plan = _HealpixPlan.get(_nside_of(image.size), L)
+    w = 4.0 * np.pi / plan.npix
+    f = D.to_dev_c(image)
+    flm = D.lincomb_dev([(w, plan.adjoint(f))])
+    for _ in range(int(iter)):
+        resid = D.lincomb_dev([(1.0, f), (-1.0, plan.synth(flm))])
+        flm = D.lincomb_dev([(1.0, flm), (w, plan.adjoint(resid))])
+    return lm2lm_hp(D.to_host(flm), L)
 
 
 def alm2map(alm, nside, **kwargs):
-    raise NotImplementedError("HEALPix alm2map is setup-time only and not part of this build yet (SURVEY.md 8 a13)")
+    """healpy.alm2map as the reference wraps it (pxmcmc/utils.py:111-113): a_lm (m >= 0, healpy
+    storage, lmax inferred from the size) -> RING-ordered real map"""
+    unsupported = {k for k in kwargs if k not in ("lmax", "mmax", "pol", "verbose", "inplace")}
+    if unsupported:
+        raise NotImplementedError(f"alm2map options not supported: {sorted(unsupported)}")
+    alm = np.asarray(alm, dtype=complex)
+    if alm.ndim != 1:
+        raise NotImplementedError("polarised alm are not supported")
+    lmax = kwargs.get("lmax")
+    if lmax is None:
+        lmax = int(round((-3 + np.sqrt(1 + 8 * alm.size)) / 2))
+    if alm_hp_size(lmax) != alm.size:
+        raise ValueError("alm size does not correspond to an lmax (mmax = lmax)")
+    L = lmax + 1
+    plan = _HealpixPlan.get(int(nside), L)
+    return D.to_host(plan.synth(D.to_dev_c(lm_hp2lm(alm, L)))).real.copy()

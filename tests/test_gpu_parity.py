@@ -384,3 +384,64 @@ def test_multichain_device_noise(px):
     # first increment is sqrt(2 delta) * N(0,1) to leading order
     z = m.chain[:, 0, :].ravel() / np.sqrt(2e-6)
     assert abs(z.std() - np.sqrt(1.0)) < 0.2
+
+
+# ------------------------------------------------------------------ HEALPix
+@pytest.mark.parametrize("nside,L", [(8, 12), (16, 40), (4, 3)])
+def test_healpix_against_oracle(px, nside, L):
+    """utils.alm2map / utils.map2alm (healpy's, as the reference wraps them) against the dense-Y_lm oracle"""
+    from oracle import healpix_ref as H
+
+    rng = np.random.default_rng(2)
+    Y = H.ylm_matrix(nside, L)
+    alm = np.zeros(H.alm_size(L - 1), complex)
+    for el in range(L):
+        for m in range(el + 1):
+            alm[H.alm_index(el, m, L - 1)] = rng.standard_normal() + (1j * rng.standard_normal() if m else 0)
+    mp = px.utils.alm2map(alm, nside)
+    assert mp.dtype == np.float64 and mp.shape == (12 * nside * nside,)
+    assert rel_l2(mp, H.alm2map(alm, nside, Y)) < TOL
+    noisy = mp + rng.standard_normal(mp.size)  # not band-limited: the iterations matter
+    for it in (0, 3):
+        assert rel_l2(px.utils.map2alm(noisy, L - 1, iter=it), H.map2alm(noisy, L - 1, iter=it, Y=Y)) < TOL
+    assert rel_l2(px.utils.map2alm(noisy, L - 1), H.map2alm(noisy, L - 1, iter=3, Y=Y)) < TOL  # healpy default
+    # the reference's HEALPix -> MW data path (experiments/earthtopography/main.py:80-82)
+    from oracle import ssht_ref
+
+    flm = px.utils.lm_hp2lm(px.utils.map2alm(noisy, L - 1), L)
+    mw = px.utils.alm2map_mw(flm, L, 0)
+    assert rel_l2(mw, ssht_ref.inverse(H.lm_hp2lm(H.map2alm(noisy, L - 1, Y=Y), L), L, 0).ravel()) < TOL
+
+
+def test_healpix_full_size_properties(px):
+    """nside 256, lmax 255 (the reference's ETOPO1 preparation): spot values against scipy's Y_lm,
+    Euclidean adjointness of the two device transforms, monopole, round trip"""
+    import torch
+    from scipy.special import sph_harm_y
+
+    from oracle import healpix_ref as H
+    from pxmcmc_b200 import device as D
+
+    nside, L = 256, 256
+    npix = 12 * nside * nside
+    rng = np.random.default_rng(4)
+    plan = px.utils._HealpixPlan.get(nside, L)
+    x = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    g = rng.standard_normal(npix) + 1j * rng.standard_normal(npix)
+    fx = D.to_host(plan.synth(D.to_dev_c(x)))
+    ag = D.to_host(plan.adjoint(D.to_dev_c(g)))
+    lhs, rhs = np.vdot(g, fx), np.vdot(ag, x)
+    assert abs(lhs - rhs) < 1e-11 * abs(lhs)
+    theta, phi = H.pix2ang(nside)
+    els = np.concatenate([np.full(2 * el + 1, el) for el in range(L)])
+    ms = np.concatenate([np.arange(-el, el + 1) for el in range(L)])
+    for p in (0, 3, 7, 1234, npix // 2 + 17, npix - 1, 2 * nside * (nside - 1) + 5):
+        exact = np.sum(x * sph_harm_y(els, ms, theta[p], phi[p]))
+        assert abs(fx[p] - exact) < 1e-10 * np.abs(fx).max()
+    a00 = px.utils.map2alm(np.full(npix, -3.0), L - 1, iter=0)[0]
+    assert np.isclose(a00, -3.0 * np.sqrt(4 * np.pi), rtol=1e-12)
+    alm = px.utils.lm2lm_hp(px.utils.lm_hp2lm(H.lm2lm_hp(x, L) * (np.arange(H.alm_size(L - 1)) >= 0), L), L)
+    alm[:L] = alm[:L].real  # m = 0 coefficients of a real map are real
+    back = px.utils.map2alm(px.utils.alm2map(alm, nside), L - 1)
+    assert rel_l2(back, alm) < 1e-5  # HEALPix quadrature + 3 refinements (not exact, as in healpy)
+    torch.cuda.synchronize()

@@ -292,3 +292,67 @@ def test_pathintegral_properties(rng):
     ring = np.zeros((L, 2 * L - 1))
     ring[ssht_ref.theta_to_index(np.pi / 2, L), :] = 2 * np.pi / (2 * L - 1)
     assert np.isclose(R.PathIntegral(sparse.csr_matrix(ring.reshape(1, -1))).forward(np.ones(L * (2 * L - 1))), 2 * np.pi)
+
+
+# ---------------------------------------------------------------- HEALPix oracle
+def test_healpix_oracle_pixel_centres_known_answers():
+    """closed-form RING pixel centres of the HEALPix primer (nside 1 and 2) and equal-area rings"""
+    from oracle import healpix_ref as H
+
+    th, ph = H.pix2ang(1)
+    assert np.allclose(np.cos(th), [2 / 3] * 4 + [0] * 4 + [-2 / 3] * 4, atol=1e-15)
+    assert np.allclose(ph / np.pi, [0.25, 0.75, 1.25, 1.75, 0, 0.5, 1, 1.5, 0.25, 0.75, 1.25, 1.75])
+    th, ph = H.pix2ang(2)
+    assert np.allclose(np.cos(th[:4]), 1 - 1 / 12) and np.allclose(ph[:4] / np.pi, [0.25, 0.75, 1.25, 1.75])
+    assert np.allclose(np.cos(th[4:12]), 2 / 3) and np.allclose(ph[4:12] / np.pi, (np.arange(8) + 0.5) / 4)
+    assert np.allclose(np.cos(th[12:20]), 1 / 3) and np.allclose(ph[12:20] / np.pi, np.arange(8) / 4)   # belt, unshifted
+    assert np.allclose(np.cos(th[20:28]), 0) and np.allclose(ph[20:28] / np.pi, (np.arange(8) + 0.5) / 4)
+    for nside in (1, 2, 4, 8):
+        rt = H.ring_table(nside)
+        assert len(rt) == 4 * nside - 1 and sum(r[0] for r in rt) == 12 * nside * nside
+        assert [r[1] for r in rt] == list(np.cumsum([0] + [r[0] for r in rt[:-1]]))
+        z = np.array([r[3] for r in rt])
+        assert np.allclose(z, -z[::-1])  # north/south mirror symmetry
+
+
+def test_healpix_oracle_transform_properties():
+    from oracle import healpix_ref as H
+
+    nside, L = 8, 12
+    rng = np.random.default_rng(0)
+    Y = H.ylm_matrix(nside, L)
+    alm = np.zeros(H.alm_size(L - 1), complex)
+    for el in range(L):
+        for m in range(el + 1):
+            alm[H.alm_index(el, m, L - 1)] = rng.standard_normal() + (1j * rng.standard_normal() if m else 0)
+    # healpy index convention and the real-map symmetry of lm_hp2lm
+    assert H.alm_index(0, 0, 11) == 0 and H.alm_index(11, 0, 11) == 11 and H.alm_index(1, 1, 11) == 12
+    flm = H.lm_hp2lm(alm, L)
+    assert np.array_equal(H.lm2lm_hp(flm, L), alm)
+    f = H.synthesis_complex(flm, nside, L, Y)
+    assert np.abs(f.imag).max() < 1e-13  # real field
+    # monopole: equal-area pixels integrate a constant exactly
+    assert np.isclose(H.map2alm(np.full(768, 2.5), L - 1, iter=0, Y=Y)[0], 2.5 * np.sqrt(4 * np.pi), rtol=1e-13)
+    # Jacobi refinement converges towards the band-limited input (healpy's iter=3 default)
+    mp = H.alm2map(alm, nside, Y)
+    errs = [np.abs(H.map2alm(mp, L - 1, iter=it, Y=Y) - alm).max() for it in (0, 1, 3)]
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-4
+    # Euclidean adjoint pair
+    g = rng.standard_normal(768) + 1j * rng.standard_normal(768)
+    x = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    assert np.isclose(np.vdot(g, H.synthesis_complex(x, nside, L, Y)), np.vdot(H.adjoint_complex(g, nside, L, Y), x))
+
+
+def test_host_lm_hp2lm_matches_oracle():
+    from oracle import healpix_ref as H
+    from pxmcmc_b200 import utils
+
+    L = 9
+    rng = np.random.default_rng(1)
+    alm = rng.standard_normal(H.alm_size(L - 1)) + 1j * rng.standard_normal(H.alm_size(L - 1))
+    assert np.array_equal(utils.lm_hp2lm(alm, L), H.lm_hp2lm(alm, L))
+    assert np.array_equal(utils.lm2lm_hp(utils.lm_hp2lm(alm, L), L), alm)
+    with pytest.raises(ValueError):
+        utils.lm_hp2lm(alm[:-1], L)
+    with pytest.raises(ValueError):
+        utils.map2alm(np.zeros(13), 3)
