@@ -438,12 +438,27 @@ def run_msharded(args):
     launches = _lib.lib.pxm_launch_count() - l0
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # ---- the same iteration replayed as ONE CUDA graph per rank (the product path for single chains:
+    # ~36 launches + 12 peer barriers per iteration are launch-latency bound when issued one by one)
+    eager_ms = ms_total
+    chain = m.capture(X, P, iterations=1)
+    for _ in range(20):
+        chain.step()
+    barrier()
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        chain.step()
+    g1.record()
+    barrier()
+    ms_total = g0.elapsed_time(g1)
+    X, P = chain.state()
     ok = tr.plan.barrier_ok() and wl.s0.barrier_ok() and wl.s2.barrier_ok()
     lp, l2, pr = m._logpi_dev(X, P)
-    stats = torch.tensor([ms_total, ms_kind[0], ms_kind[1], ms_kind[2], 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    stats = torch.tensor([ms_total, ms_kind[0], ms_kind[1], ms_kind[2], 0.0 if ok else 1.0, eager_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, leg_ms, fft_ms, el_ms, bad = [float(v) for v in stats.tolist()]
+    ms_total, leg_ms, fft_ms, el_ms, bad, eager_ms = [float(v) for v in stats.tolist()]
     # Legendre tables streamed per iteration: the synthesis pair of the wavelet plan (half of its four
     # families) for Psi and again for Psi^dagger; the spin-0 quadrature table and the spin-2 Lambda table
     # (half of each SHT plan) for Phi and again for Phi^dagger
@@ -482,6 +497,8 @@ def run_msharded(args):
                        "l2_note": f"Legendre tables streamed per iteration: {tab.item() / 2**20:.0f} MiB over all GPUs >> L2"},
             "gpu_launches": int(launches), "finite": bool(np.isfinite(lp).all() and abs(lp[0]) < 1e100), "peer_barrier_ok": bad == 0.0,
             "logposterior": float(np.real(lp[0])),
+            "launch_mode": "one CUDA graph per iteration and rank (value); eager_ms_per_step = the same kernels launched one by one",
+            "eager_ms_per_step": eager_ms / steps,
             "stage_ms_per_step_max_over_ranks": {"legendre": leg_ms / steps, "ring_fft": fft_ms / steps, "elementwise": el_ms / steps},
             "roofline": {"bound": "hbm", "kernel": "pxm_legendre_kernel (one right-hand side: table streaming bound)",
                          "achieved": tab.item() * steps / (leg_ms / 1e3) / 1e9 if leg_ms > 0 else None,

@@ -130,6 +130,13 @@ int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, c
                      const double* d_w_re, const double* d_w_im, void* d_Xout, void* d_prox_out, long long n,
                      long long nchains, double delta, double lmda, int noise_mode, unsigned long long seed,
                      unsigned long long step, unsigned int stream0, void* stream);
+/* CUDA-graph friendly variant: the Philox step is read from *d_step (device), so one captured
+ * iteration can be replayed; pxm_counter_add advances it from inside the graph. */
+int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                           void* d_Xout, void* d_prox_out, long long n, long long nchains, double delta, double lmda,
+                           int noise_mode, unsigned long long seed, const unsigned long long* d_step,
+                           unsigned int stream0, void* stream);
+int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream);
 /* pxm_resid_invcov: invcov @ (preds - data) of ForwardOperator._gradg_analysis
  * (pxmcmc/forward.py:66-69) for a diagonal, possibly complex, inverse covariance. */
 int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,

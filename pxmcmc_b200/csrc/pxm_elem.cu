@@ -109,10 +109,14 @@ struct MyulaArgs {
   double a, b, delta, sq2d;
   int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex)
   unsigned long long seed, step;
+  const unsigned long long* step_ptr;  // may be null; otherwise the step is read from the device (CUDA-graph replays)
   unsigned int stream0;
 };
 
+__global__ void k_counter_add(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+
 __global__ void k_myula_update(MyulaArgs p) {
+  if (p.step_ptr) p.step = *p.step_ptr;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.total; i += (size_t)gridDim.x * blockDim.x) {
     const cplx x = p.X[i];
     cplx px;
@@ -154,6 +158,7 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
   const size_t npairs = (p.n + 1) >> 1;
   const size_t nchains = p.total / p.n;
   const size_t tot = npairs * nchains;
+  if (p.step_ptr) p.step = *p.step_ptr;
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
     const size_t chain = q / npairs, pr = q - chain * npairs;
     double z[2];
@@ -450,8 +455,9 @@ int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, 
 int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
                      const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
                      double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
-                     unsigned int stream0, cudaStream_t st) {
+                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st) {
   MyulaArgs p;
+  p.step_ptr = d_step;
   p.X = (const cplx*)X;
   p.prox = (const cplx*)prox;
   p.gradg = (const cplx*)gradg;
@@ -476,6 +482,12 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
     k_myula_update_pair<<<grid_for((p.total + 1) / 2), 256, 0, st>>>(p);
   else
     k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
+int pxm_launch_counter_add(unsigned long long* ctr, unsigned long long inc, cudaStream_t st) {
+  k_counter_add<<<1, 1, 0, st>>>(ctr, inc);
   PXM_LAUNCHED();
   return PXM_OK;
 }
@@ -564,6 +576,7 @@ int pxm_elem_preload() {
   PXM_CUDA(cudaFuncGetAttributes(&a, k_scatter_w));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_r2c));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_csr_spmv));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_counter_add));
   return PXM_OK;
 }
 

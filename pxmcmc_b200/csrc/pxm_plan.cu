@@ -58,6 +58,7 @@ typedef unsigned long long ull;
 // peer) and, at word PXM_WS_ERR, the barrier's time-out flag
 constexpr ull PXM_WS_RESERVED = 512;
 constexpr int PXM_WS_ERR = 64;
+constexpr int PXM_WS_EPOCH = 65;  // this rank's barrier count (device-resident: barriers replay inside CUDA graphs)
 
 struct Shard {
   int rank = 0, world = 1;
@@ -361,30 +362,35 @@ Tiling make_tiling(int L, double B, int J_min) {
 // One 64-bit epoch per (rank, peer) in the reserved head of every workspace; release/acquire at
 // system scope over NVLink.  A time-out (a peer that never arrives) sets the error word instead
 // of hanging the GPU.
-__global__ void k_peer_barrier(PxmPeers peers, int rank, int world, ull epoch) {
-  const int q = threadIdx.x;
-  if (q >= world) return;
-  ull* remote = reinterpret_cast<ull*>(peers.p[q]) + rank;
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
-  const ull* mine = reinterpret_cast<const ull*>(peers.p[rank]) + q;
-  const long long t_start = clock64();
-  for (;;) {
-    ull v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-    if (v >= epoch) break;
-    if (clock64() - t_start > 20000000000LL) {  // ~10 s
-      reinterpret_cast<ull*>(peers.p[rank])[PXM_WS_ERR] = epoch;
-      break;
+__global__ void k_peer_barrier(PxmPeers peers, int rank, int world) {
+  const int q = threadIdx.x;  // one warp; lane q < world talks to peer q
+  ull* local = reinterpret_cast<ull*>(peers.p[rank]);
+  const ull epoch = local[PXM_WS_EPOCH] + 1;
+  __syncwarp();
+  if (q < world) {
+    ull* remote = reinterpret_cast<ull*>(peers.p[q]) + rank;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+    const ull* mine = local + q;
+    const long long t_start = clock64();
+    for (;;) {
+      ull v;
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v >= epoch) break;
+      if (clock64() - t_start > 20000000000LL) {  // ~10 s
+        local[PXM_WS_ERR] = epoch;
+        break;
+      }
+      __nanosleep(100);
     }
-    __nanosleep(100);
   }
+  __syncwarp();
+  if (q == 0) local[PXM_WS_EPOCH] = epoch;
 }
 
 struct PeerSet {
   Shard sh;
   PxmPeers peers = {};
-  ull epoch = 0;
   bool attached = false;
   int barrier(cudaStream_t st) {
     if (sh.world <= 1) return PXM_OK;
@@ -392,8 +398,7 @@ struct PeerSet {
       pxm_set_error("m-sharded plan used before pxm_*_plan_attach");
       return PXM_ERR_ARG;
     }
-    ++epoch;
-    k_peer_barrier<<<1, 32, 0, st>>>(peers, sh.rank, sh.world, epoch);
+    k_peer_barrier<<<1, 32, 0, st>>>(peers, sh.rank, sh.world);
     PXM_LAUNCHED();
     return PXM_OK;
   }
@@ -1116,7 +1121,24 @@ int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, c
                      unsigned long long step, unsigned int stream0, void* stream) {
   ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, d_w_re, d_w_im, d_Xout, d_prox_out, (size_t)n,
-                          (size_t)nchains, delta, lmda, noise_mode, seed, step, stream0, (cudaStream_t)stream);
+                          (size_t)nchains, delta, lmda, noise_mode, seed, step, nullptr, stream0, (cudaStream_t)stream);
+}
+
+// same, with the Philox step read from device memory: a captured CUDA graph of the iteration can be
+// replayed without re-recording (pxm_counter_add advances the counter inside the graph)
+int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                           void* d_Xout, void* d_prox_out, long long n, long long nchains, double delta, double lmda,
+                           int noise_mode, unsigned long long seed, const unsigned long long* d_step,
+                           unsigned int stream0, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(d_step != nullptr && (noise_mode == 2 || noise_mode == 3), "dstep update needs a device counter and Philox noise");
+  return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, nullptr, nullptr, d_Xout, d_prox_out, (size_t)n,
+                          (size_t)nchains, delta, lmda, noise_mode, seed, 0, d_step, stream0, (cudaStream_t)stream);
+}
+
+int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream) {
+  PXM_REQUIRE(d_counter != nullptr, "null counter");
+  return pxm_launch_counter_add(d_counter, inc, (cudaStream_t)stream);
 }
 
 int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,

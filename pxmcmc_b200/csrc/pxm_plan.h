@@ -106,7 +106,8 @@ int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, 
 int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
                      const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
                      double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
-                     unsigned int stream0, cudaStream_t st);
+                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st);
+int pxm_launch_counter_add(unsigned long long* ctr, unsigned long long inc, cudaStream_t st);
 int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* out, size_t n, size_t nchains,
                      cudaStream_t st);
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,

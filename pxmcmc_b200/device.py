@@ -191,14 +191,22 @@ def soft_dev(x, Tvec, Tscalar):
 
 
 def myula_update_dev(X, prox, gradg, Tvec, Tscalar, delta, lmda, w_re=None, w_im=None, noise_mode=0, seed=0, step=0,
-                     stream0=0, want_prox=False):
+                     stream0=0, want_prox=False, dstep=None):
+    """dstep: int64 device tensor holding the Philox step (read by the kernel, then advanced by one):
+    the form a captured CUDA graph can replay"""
     X2, was1 = batch2d(X)
     nb, n = X2.shape
     out = torch.empty_like(X2)
     pout = torch.empty_like(X2) if want_prox else None
-    check(lib.pxm_myula_update(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(w_re), ptr(w_im), ptr(out),
-                               ptr(pout), n, nb, float(delta), float(lmda), int(noise_mode), int(seed), int(step),
-                               int(stream0), stream_ptr()))
+    if dstep is not None:
+        check(lib.pxm_myula_update_dstep(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(out), ptr(pout), n, nb,
+                                         float(delta), float(lmda), int(noise_mode), int(seed), ptr(dstep), int(stream0),
+                                         stream_ptr()))
+        check(lib.pxm_counter_add(ptr(dstep), 1, stream_ptr()))
+    else:
+        check(lib.pxm_myula_update(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(w_re), ptr(w_im), ptr(out),
+                                   ptr(pout), n, nb, float(delta), float(lmda), int(noise_mode), int(seed), int(step),
+                                   int(stream0), stream_ptr()))
     if was1:
         out = out[0]
         pout = pout[0] if pout is not None else None

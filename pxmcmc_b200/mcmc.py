@@ -250,6 +250,11 @@ class MYULA(PxMCMC):
         if self.noise == "host":
             w_re, w_im = self._host_noise(n)
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im, noise_mode=1)
+        elif getattr(self, "_dstep", None) is not None:
+            # graph mode: the step lives on the device and is advanced by the captured graph itself
+            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
+                                     noise_mode=3 if self.complex else 2, seed=self.seed, stream0=self.stream0,
+                                     dstep=self._dstep)
         else:
             self._step_counter += 1
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
@@ -287,6 +292,16 @@ class MYULA(PxMCMC):
         X_new = self._propose_dev(X_curr, proxf, gradg)
         return X_new, D.to_dev_c(self._forward_dev(X_new))
 
+    def capture(self, X_curr, curr_preds, iterations=1):
+        """Record `iterations` passes of the loop body as ONE CUDA graph on private copies of the
+        state and return a `GraphedChain`: `.step()` replays it (a single launch instead of ~10-40
+        kernel launches: single-chain runs are launch-latency bound), `.state()` returns
+        the current (X, preds).  Needs `noise="device"` (the Philox step then lives in device memory
+        and is advanced inside the graph; the noise stream is the same as without the graph)."""
+        if self.noise != "device":
+            raise ValueError("capture() needs noise='device' (host RNG draws cannot be recorded)")
+        return GraphedChain(self, X_curr, curr_preds, iterations)
+
     def iterate_host(self, X_host, preds_host, X_out=None, preds_out=None):
         """The same iteration through HOST buffers (pinned torch CPU tensors or numpy
         arrays [nchains, .]): copies the state in, runs the kernels, copies the new
@@ -310,6 +325,44 @@ class MYULA(PxMCMC):
         """One proposal from (X, prox(X), gradg) (pxmcmc/mcmc.py:185-201)."""
         out = self._propose_dev(self._state(X), self._state(proxf), self._state(gradg))
         return out if D.is_dev(X) else D.to_host(out[0] if np.ndim(X) == 1 else out)
+
+
+class GraphedChain:
+    """A CUDA graph of MYULA iterations (see `MYULA.capture`)."""
+
+    def __init__(self, sampler, X, P, iterations=1):
+        self.sampler, self.iterations = sampler, int(iterations)
+        self.X = sampler._state(X).clone()
+        self.P = sampler._state(P).clone()
+        sampler._dstep = torch.full((1,), sampler._step_counter + 1, dtype=torch.int64, device=self.X.device)
+        # warm-up on a side stream (tables, kernel attributes, allocator pools), as CUDA graphs require
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            x, p = self.X, self.P
+            for _ in range(2):
+                x, p = sampler.iterate(x, p)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        sampler._dstep.fill_(sampler._step_counter + 1)  # the warm-up did not happen as far as the chain is concerned
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            x, p = self.X, self.P
+            for _ in range(self.iterations):
+                x, p = sampler.iterate(x, p)
+            self.X.copy_(x)
+            self.P.copy_(p)
+
+    def step(self):
+        """advance the chain by `iterations` iterations (asynchronous, like any kernel launch)"""
+        self.graph.replay()
+        self.sampler._step_counter += self.iterations
+
+    def state(self):
+        return self.X, self.P
+
+    def release(self):
+        self.sampler._dstep = None
 
 
 class PxMALA(MYULA):

@@ -51,6 +51,9 @@ if "1" in which or "1c" in which:
             st[0], st[1] = m.iterate(st[0], st[1])
         dt, nl = timeit(f, 200)
         out[tag] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "launches": nl}
+        chain = m.capture(st[0], st[1], iterations=1)
+        dtg, _ = timeit(chain.step, 500)
+        out[tag].update({"graph_ms_per_iteration": dtg * 1e3, "graph_iterations_per_s": 1 / dtg})
         print(tag, out[tag], flush=True)
 
 if "2" in which:
@@ -113,7 +116,9 @@ if "4" in which:
     def f():
         st[0], st[1] = m.iterate(st[0], st[1])
     dt, nl = timeit(f, 20)
-    out["config4 MYULA WeakLensing spin-2 L=512 B=2 single chain, 1 GPU"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "launches": nl, "ndata": int(mask.sum())}
+    chain = m.capture(st[0], st[1], iterations=1)
+    dtg, _ = timeit(chain.step, 50)
+    out["config4 MYULA WeakLensing spin-2 L=512 B=2 single chain, 1 GPU"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "launches": nl, "ndata": int(mask.sum()), "graph_ms_per_iteration": dtg * 1e3, "graph_iterations_per_s": 1 / dtg}
     print(out, flush=True)
 
 json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "config_timings.json"), "w"), indent=1)

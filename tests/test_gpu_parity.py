@@ -445,3 +445,40 @@ def test_healpix_full_size_properties(px):
     back = px.utils.map2alm(px.utils.alm2map(alm, nside), L - 1)
     assert rel_l2(back, alm) < 1e-5  # HEALPix quadrature + 3 refinements (not exact, as in healpy)
     torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ CUDA-graph replay of the iteration
+@pytest.mark.parametrize("iters_per_graph", [1, 3])
+def test_myula_graph_replay_matches_eager(px, iters_per_graph):
+    """a captured MYULA iteration (one launch) follows exactly the eager chain: same kernels, same
+    Philox stream (the step counter lives on the device and advances inside the graph)"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J = 24, 2.0, 1
+    rng = np.random.default_rng(8)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    prm = px.mcmc.PxMCMCParams(delta=1e-4, lmda=2e-4, mu=1.0, nsamples=1, verbosity=0, track=[])
+
+    def make():
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.7, "synthesis", L, B, J)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 3e-3, L=L, B=B, J_min=J)
+        return op, px.mcmc.MYULA(op, reg, prm, noise="device", seed=77, stream0=5)
+
+    op, eager = make()
+    X0 = D.to_dev_c(rng.laplace(size=(1, op.nparams)))
+    P0 = D.to_dev_c(op.forward(X0))
+    X, P = X0, P0
+    for _ in range(6):
+        X, P = eager.iterate(X, P)
+    _, graphed = make()
+    chain = graphed.capture(X0, P0, iterations=iters_per_graph)
+    for _ in range(6 // iters_per_graph):
+        chain.step()
+    torch.cuda.synchronize()
+    Xg, Pg = chain.state()
+    assert torch.equal(Xg, X) and torch.equal(Pg, P)  # bit-identical
+    assert graphed._step_counter == eager._step_counter == 6
+    with pytest.raises(ValueError):
+        px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, P0)
