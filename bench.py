@@ -180,8 +180,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's chatter off stdout: rank 0 prints ONE JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout at VERSION/WARN level: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from pxmcmc_b200 import _lib, device as D, sht
@@ -376,8 +375,7 @@ def run_msharded(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    os.environ["NCCL_DEBUG"] = "WARN"
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # rank 0 prints ONE JSON line on stdout
+    os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout at VERSION/WARN level: rank 0 prints ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pxmcmc_b200 import _lib, device as D

@@ -75,6 +75,7 @@ SIGNATURES = {
     "pxm_profile_end": (_i, [C.POINTER(_d), C.POINTER(_ll)]),
     "pxm_launch_count": (_ll, []),
     "pxm_debug_set_naive": (_i, [_i]),
+    "pxm_debug_set_fft_multipass": (_i, [_i]),
     "pxm_debug_wigner_row_host": (_i, [_i, _i, _i, _i, _i, _vp]),
 }
 for _name, (_res, _args) in SIGNATURES.items():

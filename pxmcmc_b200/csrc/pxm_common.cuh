@@ -134,4 +134,5 @@ struct PxmFftGroup {
   unsigned long long chirp_off;     // complex elements into the twiddle arena: c_j = exp(-i pi j^2/n), n entries
   unsigned long long bhat_off;      // complex: FFT_M of the chirp filter, M entries, in the kernel's own permuted order
   unsigned long long tw_off;        // complex: exp(-2 pi i k/M), k < M
+  unsigned long long bhat2_off;     // complex: FFT_M of the chirp filter in natural order (two-pass kernel)
 };

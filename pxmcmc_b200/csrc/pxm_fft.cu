@@ -266,6 +266,26 @@ __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cpl
   for (int i = threadIdx.x; i < M; i += blockDim.x) bhat[(i & 15) * (M >> 4) + (i >> 4)] = s[padi(i)];
 }
 
+// filter spectrum in NATURAL order for the two-pass kernel: Bhat[k] = sum_j b_j e^{-2 pi i j k / M},
+// b_j = conj(c_|j|) for |j| < n (wrapped), by direct summation (plan creation only)
+__global__ void fft_fill_bhat2_kernel(const PxmFftGroup* groups, int ngroups, cplx* arena) {
+  const PxmFftGroup gr = groups[blockIdx.y];
+  const int M = gr.M, n = gr.n;
+  const cplx* chirp = arena + gr.chirp_off;
+  cplx* out = arena + gr.bhat2_off;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < M; k += gridDim.x * blockDim.x) {
+    double re = chirp[0].x, im = -chirp[0].y;
+    for (int j = 1; j < n; ++j) {
+      // b_j (e^{-i a} + e^{+i a}) with a = 2 pi j k / M : the +j and the wrapped -j entry
+      const long long r = ((long long)j * k) % M;
+      const double c = cospi(2.0 * (double)r / (double)M);
+      re += 2.0 * c * chirp[j].x;
+      im += 2.0 * c * (-chirp[j].y);
+    }
+    out[k] = make_double2(re, im);
+  }
+}
+
 // ---- the ring transform ---------------------------------------------------------
 // DIR 0: pixels -> ring coefficients  F_m[t] = scale * sum_p f[t,p] e^{-i m phi_p}
 // DIR 1: ring coefficients -> pixels  f[t,p] = scale * sum_m F_m[t] e^{+i m phi_p}
@@ -277,12 +297,14 @@ __global__ void fft_fill_bhat_kernel(const PxmFftGroup* groups, int ngroups, cpl
 template <int DIR>
 __global__ void __launch_bounds__(256, PXM_FFT_MINB)
 pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* __restrict__ pix,
-                    size_t pix_chain_stride, double* __restrict__ F, int nld, const cplx* __restrict__ arena) {
+                    size_t pix_chain_stride, double* __restrict__ F, int nld, const cplx* __restrict__ arena,
+                    int min_logM) {
   extern __shared__ __align__(16) unsigned char fsm[];
   cplx* s = reinterpret_cast<cplx*>(fsm);
   int gi = 0;
   while (gi + 1 < ngroups && (int)blockIdx.x >= groups[gi + 1].cta_begin) ++gi;
   const PxmFftGroup gr = groups[gi];
+  if (min_logM > 0 && gr.logM < min_logM) return;  // this group belongs to the two-pass kernels
   const int chain = blockIdx.y;
   const int lgr = gr.pad;  // log2(rings per CTA)
   const int t0 = gr.ring0 + (((int)blockIdx.x - gr.cta_begin) << lgr);  // global ring index
@@ -379,6 +401,278 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
   }
 }
 
+
+// =============================================================================================
+// Two-pass variant for M = R1 x R2 <= 1024 (every ring grid up to L = 256): the whole Bluestein
+// convolution crosses shared memory twice instead of six times.
+//   pass 1  (thread = one j2, R1 points in registers, inputs straight from global memory):
+//           A[k1][j2] = W_M^{j2 k1} sum_{j1} y[j1 R2 + j2] W_R1^{j1 k1}
+//   middle  (thread = one k1, R2 points): Y[k2 R1 + k1] = sum_{j2} A[k1][j2] W_R2^{j2 k2};
+//           Z = Y * Bhat (natural order);  B[k1][j2] = W_M^{-j2 k1} sum_{k2} Z[k2 R1 + k1] W_R2^{-j2 k2}
+//   pass 3  (thread = one j2): z[j1 R2 + j2] = sum_{k1} B[k1][j2] W_R1^{-j1 k1}, straight to global memory
+// Rows k1 are padded by one element (conflict-free strided access of the middle pass); the ring
+// stride is = 2 (mod 8) elements so that the 4 rings x 2 columns a quarter-warp touches in the
+// ring-coefficient gather/scatter phases fall into distinct banks.
+// =============================================================================================
+template <bool INV>
+__device__ __forceinline__ void dft32(cplx* x) {
+  cplx e[16], o[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    e[k] = x[2 * k];
+    o[k] = x[2 * k + 1];
+  }
+  dft16<INV>(e);
+  dft16<INV>(o);
+  constexpr double C32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                              0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                              0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                              -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                              -0.92387953251128675613, -0.98078528040323044913};
+  constexpr double S32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                              0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
+                              0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
+                              0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                              0.38268343236508977173, 0.19509032201612826785};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const cplx t = (k == 0) ? o[0] : twc<INV>(o[k], C32[k], S32[k]);
+    x[k] = cadd(e[k], t);
+    x[k + 16] = csub(e[k], t);
+  }
+}
+template <int R, bool INV>
+__device__ __forceinline__ void dftN(cplx* x) {
+  if (R == 32)
+    dft32<INV>(x);
+  else
+    dftR<R, INV>(x);
+}
+// x[k] *= w^k, k < R (two interleaved product chains: <= R/2 roundings deep)
+template <int R>
+__device__ __forceinline__ void twiddle_powers(cplx* x, cplx w1) {
+  const cplx w2 = cmul(w1, w1);
+  cplx wo = w1, we = w2;
+#pragma unroll
+  for (int k = 1; k < R; k += 2) {
+    x[k] = cmul(x[k], wo);
+    if (k + 1 < R) x[k + 1] = cmul(x[k + 1], we);
+    if (k + 2 < R) {
+      wo = cmul(wo, w2);
+      we = cmul(we, w2);
+    }
+  }
+}
+
+// table loads (chirp, filter spectrum: L1/L2 hits) run PF elements ahead of their use, so their
+// latencies overlap instead of adding up along the in-order instruction stream
+template <int N, int PF, class Load, class Use>
+__device__ __forceinline__ void prefetched(Load ld, Use use) {
+  cplx buf[PF];
+#pragma unroll
+  for (int i = 0; i < PF && i < N; ++i) buf[i] = ld(i);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const cplx c = buf[i % PF];
+    if (i + PF < N) buf[i % PF] = ld(i + PF);
+    use(i, c);
+  }
+}
+
+__device__ __forceinline__ int ring_stride2(int R1, int R2) {
+  int rs = R1 * (R2 + 1);
+  return rs + ((2 - (rs & 7)) + 8) % 8;
+}
+
+// address of ring coefficient (m(j), ring) in the k4-interleaved array and its sign on the ring side
+__device__ __forceinline__ size_t f_address(const PxmFftGroup& gr, size_t frow, int j, double* sg) {
+  const int m = (j < gr.ell) ? j : j - gr.n;
+  *sg = 1.0;
+  if (gr.paired) {
+    const int am = m < 0 ? -m : m;
+    if (m < 0 && (am & 1)) *sg = -1.0;
+    return frow + (size_t)am * gr.slot_stride + (m < 0 ? 8 : 0);
+  }
+  return frow + (size_t)(m + gr.ell - 1) * gr.slot_stride;
+}
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft2_body(const PxmFftGroup& gr, cplx* __restrict__ s, cplx* __restrict__ mypix,
+                                               double* __restrict__ F, int nld, int chain,
+                                               const cplx* __restrict__ arena, int t0) {
+  constexpr int M = R1 * R2;
+  const int n = gr.n, rings = gr.rings;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ chirp = arena + gr.chirp_off;
+  const cplx* __restrict__ bhat = arena + gr.bhat2_off;
+  const cplx* __restrict__ tw = arena + gr.tw_off;
+  const size_t col0 = (size_t)(gr.paired ? chain * 4 : chain * 2);
+
+  // ---------------- pass 1: load (x chirp), DFT over j1, twiddle, to shared ----------------
+  for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
+    int r, j2;
+    if (DIR == 0) {
+      r = idx / R2;
+      j2 = idx - r * R2;
+    } else {  // 4 rings of one row-group on adjacent lanes: one 32-byte sector per (m, re/im)
+      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+      r = rhi * 4 + (rem & 3);
+      j2 = rem >> 2;
+    }
+    const int t = t0 + r;
+    const bool tvalid = t < rings;
+    // all loads of the thread are issued back to back (raw values straight into x[]), the
+    // arithmetic on them comes afterwards: one exposed memory latency per thread instead of R1
+    cplx x[R1];
+    if (DIR == 0) {
+      const cplx* row = mypix + (size_t)(t - gr.ring0) * n;
+#pragma unroll
+      for (int j1 = 0; j1 < R1; ++j1) {
+        const int j = j1 * R2 + j2;
+        x[j1] = (tvalid && j < n) ? row[j] : make_double2(0.0, 0.0);
+      }
+      prefetched<R1, 4>([&](int j1) { const int j = j1 * R2 + j2; return chirp[j < n ? j : 0]; },
+                        [&](int j1, cplx c) { x[j1] = cmul(x[j1], c); });  // padded entries are 0 anyway
+    } else {
+      const size_t frow = gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
+#pragma unroll
+      for (int j1 = 0; j1 < R1; ++j1) {
+        const int j = j1 * R2 + j2;
+        cplx v = make_double2(0.0, 0.0);
+        if (tvalid && j < n) {
+          double sg;
+          const size_t base = f_address(gr, frow, j, &sg);
+          v = make_double2(F[base], F[base + 4]);
+        }
+        x[j1] = v;
+      }
+      prefetched<R1, 4>([&](int j1) { const int j = j1 * R2 + j2; return chirp[j < n ? j : 0]; },
+                        [&](int j1, cplx c) {
+                          const int j = j1 * R2 + j2;
+                          const int m = (j < gr.ell) ? j : j - n;
+                          const double sg = (gr.paired && m < 0 && (m & 1)) ? -1.0 : 1.0;
+                          x[j1] = cmul(make_double2(sg * x[j1].x, -sg * x[j1].y), c);  // conj on load
+                        });
+    }
+    dftN<R1, false>(x);
+    twiddle_powers<R1>(x, tw[j2 * (gr.M / M)]);  // gr.M == M
+    cplx* dst = s + r * RS + j2;
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
+  }
+  __syncthreads();
+  // ---------------- middle: DFT over j2, filter, inverse DFT over k2, inverse twiddle ----------------
+  for (int idx = threadIdx.x; idx < nr * R1; idx += blockDim.x) {
+    const int r = idx / R1, k1 = idx - r * R1;
+    cplx* row = s + r * RS + k1 * (R2 + 1);
+    cplx x[R2];
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) x[j2] = row[j2];
+    dftN<R2, false>(x);
+    prefetched<R2, 4>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+    dftN<R2, true>(x);
+    cplx w1 = tw[k1];
+    w1.y = -w1.y;
+    twiddle_powers<R2>(x, w1);
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
+  }
+  __syncthreads();
+  // ---------------- pass 3: inverse DFT over k1, x chirp, scale, store ----------------
+  const double sc = gr.scale / (double)M;
+  for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
+    int r, j2;
+    if (DIR == 1) {
+      r = idx / R2;
+      j2 = idx - r * R2;
+    } else {
+      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+      r = rhi * 4 + (rem & 3);
+      j2 = rem >> 2;
+    }
+    const int t = t0 + r;
+    if (t >= rings) continue;
+    const cplx* src = s + r * RS + j2;
+    cplx x[R1];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) x[k1] = src[k1 * (R2 + 1)];
+    dftN<R1, true>(x);
+    if (DIR == 0) {
+      const size_t frow = gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
+      prefetched<R1, 4>([&](int j1) { const int j = j1 * R2 + j2; return chirp[j < n ? j : 0]; },
+                        [&](int j1, cplx c) {
+                          const int j = j1 * R2 + j2;
+                          if (j < n) {
+                            const cplx v = cmul(x[j1], c);
+                            double sg;
+                            const size_t base = f_address(gr, frow, j, &sg);
+                            F[base] = sg * sc * v.x;
+                            F[base + 4] = sg * sc * v.y;
+                          }
+                        });
+    } else {
+      cplx* row = mypix + (size_t)(t - gr.ring0) * n;
+      prefetched<R1, 4>([&](int j1) { const int j = j1 * R2 + j2; return chirp[j < n ? j : 0]; },
+                        [&](int j1, cplx c) {
+                          const int j = j1 * R2 + j2;
+                          if (j < n) {
+                            const cplx v = cmul(x[j1], c);
+                            row[j] = make_double2(v.x * sc, -v.y * sc);
+                          }
+                        });
+    }
+  }
+}
+
+// CLS 0: M <= 256 (radices <= 16), CLS 1: M = 512, 1024 (radix 32).  CTAs of groups that belong to
+// another class (or to the multi-pass kernel, M > 1024) exit at once.
+// The group descriptors travel as a kernel parameter (constant bank): finding a CTA's group and
+// reading its descriptor costs no dependent global loads at the head of every CTA.
+constexpr int PXM_FFT_MAX_GROUPS = 24;
+struct PxmFftGroupTable {
+  int ngroups;
+  int pad;
+  PxmFftGroup g[PXM_FFT_MAX_GROUPS];
+};
+
+// radix-32 class: 2 CTAs of 128 threads per SM (255 registers, no spills) measured faster than 3 (168, spills)
+#ifndef PXM_FFT2_MINB1
+#define PXM_FFT2_MINB1 2
+#endif
+template <int DIR, int CLS>
+__global__ void __launch_bounds__(CLS == 0 ? 256 : 128, CLS == 0 ? 2 : PXM_FFT2_MINB1)
+pxm_ring_fft2_kernel(const __grid_constant__ PxmFftGroupTable tab, cplx* __restrict__ pix,
+                     size_t pix_chain_stride, double* __restrict__ F, int nld, const cplx* __restrict__ arena) {
+  extern __shared__ __align__(16) unsigned char fsm[];
+  cplx* s = reinterpret_cast<cplx*>(fsm);
+  int gi = 0;
+  while (gi + 1 < tab.ngroups && (int)blockIdx.x >= tab.g[gi + 1].cta_begin) ++gi;
+  const PxmFftGroup& gr = tab.g[gi];
+  const int lgM = gr.logM;
+  if (CLS == 0 ? (lgM > 8) : (lgM < 9 || lgM > 10)) return;
+  const int chain = blockIdx.y;
+  const int t0 = gr.ring0 + (((int)blockIdx.x - gr.cta_begin) << gr.pad);
+  cplx* mypix = pix + (size_t)chain * pix_chain_stride + gr.pix_off;
+  if (CLS == 0) {
+    switch (lgM) {
+      case 4: ring_fft2_body<DIR, 4, 4>(gr, s, mypix, F, nld, chain, arena, t0); break;
+      case 5: ring_fft2_body<DIR, 4, 8>(gr, s, mypix, F, nld, chain, arena, t0); break;
+      case 6: ring_fft2_body<DIR, 8, 8>(gr, s, mypix, F, nld, chain, arena, t0); break;
+      case 7: ring_fft2_body<DIR, 8, 16>(gr, s, mypix, F, nld, chain, arena, t0); break;
+      default: ring_fft2_body<DIR, 16, 16>(gr, s, mypix, F, nld, chain, arena, t0); break;
+    }
+  } else {
+    if (lgM == 9)
+      ring_fft2_body<DIR, 16, 32>(gr, s, mypix, F, nld, chain, arena, t0);
+    else
+      ring_fft2_body<DIR, 32, 32>(gr, s, mypix, F, nld, chain, arena, t0);
+  }
+}
+
+constexpr int PXM_FFT2_SMEM = (16 * (16 * 17 + 2)) * 16 > (4 * (32 * 33 + 2)) * 16 ? (16 * (16 * 17 + 2)) * 16
+                                                                                  : (4 * (32 * 33 + 2)) * 16;
+
 }  // namespace
 
 int pxm_fft_choose_M(int n, int* logM) {
@@ -398,6 +692,7 @@ int pxm_fft_rings_per_cta_log(int M) {
   return lg;
 }
 
+static int g_fft_legacy = 0;
 constexpr int PXM_FFT_SMEM = (4096 + 256 + 32) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
 
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
@@ -407,6 +702,10 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     PXM_CUDA(cudaFuncSetAttribute(fft_fill_bhat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
     configured = true;
   }
   if (ngroups <= 0) return PXM_OK;  // a rank of an m-sharded plan that owns no ring
@@ -420,21 +719,57 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
   PXM_LAUNCHED();
   fft_fill_bhat_kernel<<<ngroups, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, (cplx*)d_arena);
   PXM_LAUNCHED();
-  return PXM_OK;
-}
-
-// dir 0: pix -> F ; dir 1: F -> pix
-int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, int ngroups, int ctas_per_chain, void* pix,
-                   size_t pix_chain_stride, double* F, int nld, const void* d_arena, int nchains,
-                   cudaStream_t stream) {
-  if (nchains <= 0 || ctas_per_chain <= 0) return PXM_OK;
-  dim3 grid(ctas_per_chain, nchains);
-  if (dir == 0)
-    pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, (cplx*)pix, pix_chain_stride, F,
-                                                                 nld, (const cplx*)d_arena);
-  else
-    pxm_ring_fft_kernel<1><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, (cplx*)pix, pix_chain_stride, F,
-                                                                 nld, (const cplx*)d_arena);
+  fft_fill_bhat2_kernel<<<dim3(8, ngroups), 128, 0, stream>>>(d_groups, ngroups, (cplx*)d_arena);
   PXM_LAUNCHED();
   return PXM_OK;
 }
+
+// class of a Bluestein length: bit 0: M <= 256, bit 1: M = 512 / 1024 (two-pass kernels), bit 2: M > 1024
+int pxm_fft_class_bit(int logM) { return logM <= 8 ? 1 : (logM <= 10 ? 2 : 4); }
+
+// dir 0: pix -> F ; dir 1: F -> pix.  class_mask: which kernel classes the stage's groups need
+int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, int ctas_per_chain,
+                   void* pix, size_t pix_chain_stride, double* F, int nld, const void* d_arena, int nchains,
+                   int class_mask, cudaStream_t stream) {
+  if (nchains <= 0 || ctas_per_chain <= 0) return PXM_OK;
+  dim3 grid(ctas_per_chain, nchains);
+  cplx* px = (cplx*)pix;
+  const cplx* ar = (const cplx*)d_arena;
+  PxmFftGroupTable tab;
+  tab.ngroups = ngroups;
+  tab.pad = 0;
+  if (ngroups <= PXM_FFT_MAX_GROUPS)
+    for (int i = 0; i < ngroups; ++i) tab.g[i] = h_groups[i];
+  if (g_fft_legacy || ngroups > PXM_FFT_MAX_GROUPS) {  // debugging aid: everything through the multi-pass kernel
+    if (dir == 0)
+      pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 0);
+    else
+      pxm_ring_fft_kernel<1><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 0);
+    PXM_LAUNCHED();
+    return PXM_OK;
+  }
+  if (class_mask & 2) {
+    if (dir == 0)
+      pxm_ring_fft2_kernel<0, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+    else
+      pxm_ring_fft2_kernel<1, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+    PXM_LAUNCHED();
+  }
+  if (class_mask & 1) {
+    if (dir == 0)
+      pxm_ring_fft2_kernel<0, 0><<<grid, 256, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+    else
+      pxm_ring_fft2_kernel<1, 0><<<grid, 256, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+    PXM_LAUNCHED();
+  }
+  if (class_mask & 4) {
+    if (dir == 0)
+      pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 11);
+    else
+      pxm_ring_fft_kernel<1><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 11);
+    PXM_LAUNCHED();
+  }
+  return PXM_OK;
+}
+
+void pxm_fft_set_legacy(int on) { g_fft_legacy = on; }

@@ -149,6 +149,7 @@ struct FftStage {
   std::vector<PxmFftGroup> groups;
   PxmDevVec<PxmFftGroup> d_groups;
   int ctas = 0;
+  int class_mask = 0;  // kernel classes the groups need (pxm_fft_class_bit)
   void release() { d_groups.release(); }
 };
 
@@ -170,6 +171,8 @@ struct FftTables {
     g.bhat_off = cursor;
     cursor += g.M;
     g.tw_off = cursor;
+    cursor += g.M;
+    g.bhat2_off = cursor;
     cursor += g.M;
     by_n[n] = g;
     return g;
@@ -206,6 +209,7 @@ void add_fft_group(FftStage& S, FftTables& tabs, const RingBuf& R, ull pix_off, 
   g.f_off = R.off;
   g.slot_stride = R.slot_stride;
   S.ctas += pxm_ceil_div(R.t1 - R.t0, g.rings_per_cta);
+  S.class_mask |= pxm_fft_class_bit(g.logM);
   S.groups.push_back(g);
 }
 
@@ -500,6 +504,11 @@ int pxm_debug_set_naive(int on) {
   return PXM_OK;
 }
 
+int pxm_debug_set_fft_multipass(int on) {
+  pxm_fft_set_legacy(on);
+  return PXM_OK;
+}
+
 int pxm_init(int device) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
@@ -612,12 +621,12 @@ static int sht_run(pxm_sht_plan* p, int which, void* d_flm, void* d_f, int nb, c
                                 st, naive)); }
     PXM_TRY(p->ps.barrier(st));  // every rank's tiles have landed
     FftStage& F = which == 0 ? p->fft_out_unit : p->fft_out_norm;
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
-                           p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, F.d_groups.d, F.groups.data(), (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, F.class_mask, st)); }
   } else {  // pixel -> harmonic
     FftStage& F = which == 2 ? p->fft_in_unit : p->fft_in_norm;
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, F.d_groups.d, (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
-                           p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, F.d_groups.d, F.groups.data(), (int)F.groups.size(), F.ctas, d_f, npix, p->d_ws, p->nld,
+                           p->ffttab.d_arena, nb, F.class_mask, st)); }
     Stage& S = which == 2 ? p->a_lam : p->a_w;
     PXM_TRY(p->ps.barrier(st));  // every rank's ring coefficients are in place
     { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, S.d_items.d, S.d_segs.d, (int)S.items.size(), p->nld,
@@ -877,27 +886,27 @@ static int wav_run(pxm_wav_plan* p, int which, void* d_coef, void* d_pix, int nb
   const bool coef_to_pix = (which == 0 || which == 3);
   // m-sharded: [local ring FFTs] | barrier | [pull rings -> own m's ; push own m's -> ring owners] | barrier | [local ring FFTs]
   if (coef_to_pix) {
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
-                           d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, D.fft_scales_in.groups.data(), (int)D.fft_scales_in.groups.size(), D.fft_scales_in.ctas,
+                           d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_scales_in.class_mask, st)); }
     PXM_TRY(p->ps.barrier(st));
     { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_multi.d_items.d, D.a_multi.d_segs.d,
                                 (int)D.a_multi.items.size(), p->nld, st, naive)); }
     { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_full.d_items.d, D.s_full.d_segs.d,
                                 (int)D.s_full.items.size(), p->nld, st, naive)); }
     PXM_TRY(p->ps.barrier(st));
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
-                           d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, D.fft_full_out.groups.data(), (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
+                           d_pix, npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_full_out.class_mask, st)); }
   } else {
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
-                           npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, D.fft_full_in.groups.data(), (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas, d_pix,
+                           npix, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_full_in.class_mask, st)); }
     PXM_TRY(p->ps.barrier(st));
     { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_full.d_items.d, D.a_full.d_segs.d,
                                 (int)D.a_full.items.size(), p->nld, st, naive)); }
     { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
                                 (int)D.s_multi.items.size(), p->nld, st, naive)); }
     PXM_TRY(p->ps.barrier(st));
-    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, (int)D.fft_scales_out.groups.size(),
-                           D.fft_scales_out.ctas, d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, st)); }
+    { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, D.fft_scales_out.groups.data(), (int)D.fft_scales_out.groups.size(),
+                           D.fft_scales_out.ctas, d_coef, ncoef, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_scales_out.class_mask, st)); }
   }
   return PXM_OK;
 }

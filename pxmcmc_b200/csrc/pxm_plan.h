@@ -98,8 +98,11 @@ int pxm_fft_choose_M(int n, int* logM);
 int pxm_fft_rings_per_cta_log(int M);
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
                          cudaStream_t stream);
-int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, int ngroups, int ctas_per_chain, void* pix,
-                   size_t pix_chain_stride, double* F, int nld, const void* d_arena, int nchains, cudaStream_t stream);
+int pxm_fft_class_bit(int logM);
+void pxm_fft_set_legacy(int on);
+int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, int ctas_per_chain,
+                   void* pix, size_t pix_chain_stride, double* F, int nld, const void* d_arena, int nchains,
+                   int class_mask, cudaStream_t stream);
 
 int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, void* out, size_t n, size_t nchains,
                     cudaStream_t st);

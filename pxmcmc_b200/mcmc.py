@@ -256,10 +256,14 @@ class MYULA(PxMCMC):
                                      noise_mode=3 if self.complex else 2, seed=self.seed, stream0=self.stream0,
                                      dstep=self._dstep)
         else:
-            self._step_counter += 1
+            # chain-group calls of one iteration (iterate_host) share a step; their Philox streams are
+            # offset so that chain c always uses stream stream0 + c, whatever the grouping
+            off = getattr(self, "_group_offset", None)
+            if off is None:
+                self._step_counter += 1
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
                                      noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter,
-                                     stream0=self.stream0)
+                                     stream0=self.stream0 + (off or 0))
         return out
 
     def run(self, start_point=None):
@@ -302,24 +306,72 @@ class MYULA(PxMCMC):
             raise ValueError("capture() needs noise='device' (host RNG draws cannot be recorded)")
         return GraphedChain(self, X_curr, curr_preds, iterations)
 
-    def iterate_host(self, X_host, preds_host, X_out=None, preds_out=None):
+    def iterate_host(self, X_host, preds_host, X_out=None, preds_out=None, groups=None):
         """The same iteration through HOST buffers (pinned torch CPU tensors or numpy
         arrays [nchains, .]): copies the state in, runs the kernels, copies the new
-        state and predictions back.  This is the end-to-end path bench.py times."""
+        state and predictions back.  This is the end-to-end path bench.py times.
+
+        With several chains the batch is cut into `groups` chain groups that flow through a
+        three-stage pipeline on three CUDA streams -- host->device copy of group g+1, kernels of
+        group g, device->host copy of group g-1 -- so that both PCIe directions and the SMs work at
+        the same time (the transfers, not the kernels, bound this path).  Results do not depend on
+        the grouping: chains are independent and chain c always draws Philox stream stream0 + c."""
         dv = D.dev()
         xh = X_host if D.is_dev(X_host) else torch.from_numpy(np.ascontiguousarray(X_host, dtype=np.complex128))
         ph = preds_host if D.is_dev(preds_host) else torch.from_numpy(np.ascontiguousarray(preds_host, dtype=np.complex128))
-        Xd = xh.to(dv, non_blocking=True)
-        Pd = ph.to(dv, non_blocking=True)
-        if Xd.dim() == 1:
-            Xd, Pd = Xd.unsqueeze(0), Pd.unsqueeze(0)
-        Xn, Pn = self.iterate(Xd, Pd)
-        if X_out is not None:
-            X_out.copy_(Xn.reshape(X_out.shape), non_blocking=True)
-            preds_out.copy_(Pn.reshape(preds_out.shape), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return X_out, preds_out
-        return D.to_host(Xn), D.to_host(Pn)
+        if xh.dim() == 1:
+            xh, ph = xh.unsqueeze(0), ph.unsqueeze(0)
+        nch = xh.shape[0]
+        if groups is None:
+            groups = 8 if (nch >= 64 and nch % 8 == 0) else (4 if (nch >= 16 and nch % 4 == 0) else 1)
+        if nch % groups or self.noise != "device" and groups > 1:
+            groups = 1
+        if groups == 1:
+            Xn, Pn = self.iterate(xh.to(dv, non_blocking=True), ph.to(dv, non_blocking=True))
+            if X_out is not None:
+                X_out.copy_(Xn.reshape(X_out.shape), non_blocking=True)
+                preds_out.copy_(Pn.reshape(preds_out.shape), non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return X_out, preds_out
+            return D.to_host(Xn), D.to_host(Pn)
+        if X_out is None:
+            X_out, preds_out = torch.empty_like(xh).pin_memory(), torch.empty_like(ph).pin_memory()
+        xo, po = X_out.reshape(xh.shape), preds_out.reshape(ph.shape)
+        st = getattr(self, "_pipe_streams", None)
+        if st is None:
+            st = self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        s_in, s_out = st
+        s_cmp = torch.cuda.current_stream()
+        s_in.wait_stream(s_cmp)
+        size = nch // groups
+        self._step_counter += 1
+        staged = []
+        for g in range(groups):  # all uploads are queued first: the copy engine never waits for the host
+            with torch.cuda.stream(s_in):
+                sl = slice(g * size, (g + 1) * size)
+                Xd, Pd = xh[sl].to(dv, non_blocking=True), ph[sl].to(dv, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            staged.append((sl, Xd, Pd, ev))
+        try:
+            for g, (sl, Xd, Pd, ev) in enumerate(staged):
+                s_cmp.wait_event(ev)
+                Xd.record_stream(s_cmp)
+                Pd.record_stream(s_cmp)
+                self._group_offset = g * size
+                Xn, Pn = self.iterate(Xd, Pd)
+                done = torch.cuda.Event()
+                done.record(s_cmp)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    Xn.record_stream(s_out)
+                    Pn.record_stream(s_out)
+                    xo[sl].copy_(Xn, non_blocking=True)
+                    po[sl].copy_(Pn, non_blocking=True)
+        finally:
+            self._group_offset = None
+        s_out.synchronize()
+        return X_out, preds_out
 
     def chain_step(self, X, proxf, gradg):
         """One proposal from (X, prox(X), gradg) (pxmcmc/mcmc.py:185-201)."""

@@ -34,7 +34,7 @@ def main():
 
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")
+    os.environ.pop("NCCL_DEBUG", None)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pxmcmc_b200 import device as D
     from pxmcmc_b200 import msharded as ms

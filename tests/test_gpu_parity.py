@@ -482,3 +482,50 @@ def test_myula_graph_replay_matches_eager(px, iters_per_graph):
     assert graphed._step_counter == eager._step_counter == 6
     with pytest.raises(ValueError):
         px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, P0)
+
+
+def test_ring_fft_two_pass_against_multipass(px):
+    """the two-pass ring FFT (all Bluestein lengths <= 1024) against the independent multi-pass kernel
+    (the path lengths > 1024 take), through all four wavelet operators at the BASELINE bandlimit"""
+    from pxmcmc_b200 import _lib
+    from pxmcmc_b200 import device as D
+
+    L, B, J = 256, 1.5, 2
+    rng = np.random.default_rng(13)
+    plan = D.WaveletPlan.get(L, B, J, 2)
+    coef = D.to_dev_c(rng.standard_normal((2, plan.ncoefs)) + 1j * rng.standard_normal((2, plan.ncoefs)))
+    pix = D.to_dev_c(rng.standard_normal((2, plan.npix)) + 1j * rng.standard_normal((2, plan.npix)))
+    for name, x in (("synthesis", coef), ("synthesis_adjoint", pix), ("analysis", pix), ("analysis_adjoint", coef)):
+        fast = D.to_host(getattr(plan, name)(x))
+        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(1))
+        try:
+            slow = D.to_host(getattr(plan, name)(x))
+        finally:
+            _lib.check(_lib.lib.pxm_debug_set_fft_multipass(0))
+        assert rel_l2(fast, slow) < 1e-13, name
+
+
+def test_iterate_host_pipeline_matches_device_iteration(px):
+    """the pipelined host-buffer iteration (chain groups on three streams) gives exactly the batch
+    iteration: same chains, same Philox streams, whatever the grouping"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J, nch = 16, 2.0, 1, 16
+    rng = np.random.default_rng(5)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    prm = px.mcmc.PxMCMCParams(delta=1e-4, lmda=2e-4, mu=1.0, nsamples=1, verbosity=0, track=[])
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.7, "synthesis", L, B, J, nchains=nch)
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 3e-3, L=L, B=B, J_min=J)
+    X0 = rng.laplace(size=(nch, op.nparams)) + 0j
+    P0 = D.to_host(op.forward(D.to_dev_c(X0)))
+    ref = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=9, stream0=3)
+    Xr, Pr = ref.iterate(D.to_dev_c(X0), D.to_dev_c(P0))
+    for groups in (1, 4):
+        m = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=9, stream0=3)
+        Xh, Ph = torch.from_numpy(X0.copy()).pin_memory(), torch.from_numpy(P0.copy()).pin_memory()
+        Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
+        m.iterate_host(Xh, Ph, Xo, Po, groups=groups)
+        assert torch.equal(Xo, Xr.cpu()) and torch.equal(Po, Pr.cpu()), groups
+        assert m._step_counter == 1
