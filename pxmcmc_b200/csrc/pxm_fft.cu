@@ -740,7 +740,12 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
   tab.pad = 0;
   if (ngroups <= PXM_FFT_MAX_GROUPS)
     for (int i = 0; i < ngroups; ++i) tab.g[i] = h_groups[i];
-  if (g_fft_legacy || ngroups > PXM_FFT_MAX_GROUPS) {  // debugging aid: everything through the multi-pass kernel
+  // Few CTAs (single chain, m-sharded ranks): the launch is one wave whose duration is the latency of a
+  // single CTA, and the multi-pass kernel spreads a ring over twice as many threads -> measured faster
+  // there (L=256 single chain 0.21 vs 0.30 ms per iteration); the two-pass kernel wins on throughput.
+  // (grids whose rings are all short, M <= 256, stay on the two-pass kernel: radices <= 16, fewer barriers)
+  const bool small_grid = (long long)ctas_per_chain * nchains < 1024 && (class_mask & 6) != 0;
+  if (g_fft_legacy == 1 || (small_grid && g_fft_legacy != 2) || ngroups > PXM_FFT_MAX_GROUPS) {
     if (dir == 0)
       pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 0);
     else
@@ -772,4 +777,5 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
   return PXM_OK;
 }
 
+// 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies)
 void pxm_fft_set_legacy(int on) { g_fft_legacy = on; }

@@ -124,6 +124,17 @@ class PxMCMC:
         pr = D.to_host(red(prd) if red else prd)
         return -self.mu * pr - L2, L2, pr
 
+    def _logpi_terms_dev(self, Xd, Pd):
+        """(L2, prior) as DEVICE tensors [nchains] (complex, real), or None when the operator has a
+        general covariance (host path)"""
+        if getattr(self.forward, "_diag", None) is None or not isinstance(self.prior, L1):
+            return None
+        red = getattr(self.forward, "_pxm_allreduce", None)
+        data_d, ic_d = self.forward._upload()
+        L2d = D.reduce_dev(1, Pd, b=data_d, c=ic_d)
+        prd = self._prior_dev(Xd)
+        return (red(L2d) if red else L2d), (red(prd) if red else prd)
+
     def _host_L2(self, preds):
         diff = np.asarray(self.forward.data) - preds
         return np.vdot(diff, self.forward.invcov @ diff)
@@ -453,10 +464,21 @@ class PxMALA(MYULA):
             prop_preds = D.to_dev_c(self._forward_dev(X_prop))
             gradg_prop = D.to_dev_c(self._gradg_dev(prop_preds))
             proxf_prop = self._proxf_dev(X_prop)
-            logtransXcXp = self._logtrans_dev(X_curr, X_prop, proxf_curr, gradg_curr)
-            logtransXpXc = self._logtrans_dev(X_prop, X_curr, proxf_prop, gradg_prop)
-            lp, l2, pr = self._logpi_dev(X_prop, prop_preds)
-            logpiXp, L2Xp, priorXp = lp[0], l2[0], pr[0]
+            terms = self._logpi_terms_dev(X_prop, prop_preds)
+            if terms is not None:
+                # the four reductions of the accept test leave the device in ONE copy (one host sync per iteration)
+                s1 = D.reduce_dev(2, X_curr, b=X_prop, c=proxf_curr, d=gradg_curr, delta=self.delta, lmda=self.lmda)
+                s2 = D.reduce_dev(2, X_prop, b=X_curr, c=proxf_prop, d=gradg_prop, delta=self.delta, lmda=self.lmda)
+                v = torch.cat([s1, s2, terms[0], terms[1].to(D.CDT)]).cpu().numpy()
+                logtransXcXp = -(1 / 2 * self.delta) * complex(v[0]) ** 2
+                logtransXpXc = -(1 / 2 * self.delta) * complex(v[1]) ** 2
+                L2Xp, priorXp = v[2], v[3].real
+                logpiXp = -self.mu * priorXp - L2Xp
+            else:
+                logtransXcXp = self._logtrans_dev(X_curr, X_prop, proxf_curr, gradg_curr)
+                logtransXpXc = self._logtrans_dev(X_prop, X_curr, proxf_prop, gradg_prop)
+                lp, l2, pr = self._logpi_dev(X_prop, prop_preds)
+                logpiXp, L2Xp, priorXp = lp[0], l2[0], pr[0]
             logalpha = logtransXpXc + logpiXp - logtransXcXp - logpiXc
             accept = _cplx_lt(np.log(np.random.rand()), logalpha)
             if accept:

@@ -496,9 +496,10 @@ def test_ring_fft_two_pass_against_multipass(px):
     coef = D.to_dev_c(rng.standard_normal((2, plan.ncoefs)) + 1j * rng.standard_normal((2, plan.ncoefs)))
     pix = D.to_dev_c(rng.standard_normal((2, plan.npix)) + 1j * rng.standard_normal((2, plan.npix)))
     for name, x in (("synthesis", coef), ("synthesis_adjoint", pix), ("analysis", pix), ("analysis_adjoint", coef)):
-        fast = D.to_host(getattr(plan, name)(x))
-        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(1))
         try:
+            _lib.check(_lib.lib.pxm_debug_set_fft_multipass(2))
+            fast = D.to_host(getattr(plan, name)(x))
+            _lib.check(_lib.lib.pxm_debug_set_fft_multipass(1))
             slow = D.to_host(getattr(plan, name)(x))
         finally:
             _lib.check(_lib.lib.pxm_debug_set_fft_multipass(0))
@@ -529,3 +530,40 @@ def test_iterate_host_pipeline_matches_device_iteration(px):
         m.iterate_host(Xh, Ph, Xo, Po, groups=groups)
         assert torch.equal(Xo, Xr.cpu()) and torch.equal(Po, Pr.cpu()), groups
         assert m._step_counter == 1
+
+
+def test_ring_fft_two_pass_all_radices_against_oracle(px):
+    """two-pass ring FFT forced on (mode 2) at L=70, B=2: Bluestein lengths 16...512, i.e. every radix
+    pair below (32, 32), paired (spin 0) and unpaired (spin 2) ring layouts, against the CPU oracle"""
+    from oracle import pxmcmc_ref as R
+    from oracle import ssht_ref
+    from pxmcmc_b200 import _lib
+    from pxmcmc_b200 import device as D
+
+    L, B, J = 70, 2.0, 2
+    rng = np.random.default_rng(17)
+    t = R.WaveletTransform(L, B, J)
+    plan = D.WaveletPlan.get(L, B, J, 3)
+    assert sorted(set(plan.bandlimits)) == [4, 8, 16, 32, 64, 70]
+    coef = rng.standard_normal((3, plan.ncoefs)) + 1j * rng.standard_normal((3, plan.ncoefs))
+    pix = rng.standard_normal((3, plan.npix)) + 1j * rng.standard_normal((3, plan.npix))
+    flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    flm[:4] = 0
+    try:
+        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(2))
+        got = {"synthesis": D.to_host(plan.synthesis(D.to_dev_c(coef))), "synthesis_adjoint": D.to_host(plan.synthesis_adjoint(D.to_dev_c(pix))),
+               "analysis": D.to_host(plan.analysis(D.to_dev_c(pix))), "analysis_adjoint": D.to_host(plan.analysis_adjoint(D.to_dev_c(coef)))}
+        s2 = D.ShtPlan.get(L, 2, 1)
+        got_s2 = {"inverse": D.to_host(s2.inverse(D.to_dev_c(flm))), "forward": D.to_host(s2.forward(D.to_dev_c(pix[0]))),
+                  "inverse_adjoint": D.to_host(s2.inverse_adjoint(D.to_dev_c(pix[0]))), "forward_adjoint": D.to_host(s2.forward_adjoint(D.to_dev_c(flm)))}
+    finally:
+        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(0))
+    for c in range(3):
+        assert rel_l2(got["synthesis"][c], t.inverse(coef[c])) < TOL
+        assert rel_l2(got["synthesis_adjoint"][c], t.inverse_adjoint(pix[c])) < TOL
+        assert rel_l2(got["analysis"][c], t.forward(pix[c])) < TOL
+        assert rel_l2(got["analysis_adjoint"][c], t.forward_adjoint(coef[c])) < TOL
+    assert rel_l2(got_s2["inverse"], ssht_ref.inverse(flm, L, 2).ravel()) < TOL
+    assert rel_l2(got_s2["forward"], ssht_ref.forward(pix[0].reshape(L, 2 * L - 1), L, 2)) < TOL
+    assert rel_l2(got_s2["inverse_adjoint"], ssht_ref.inverse_adjoint(pix[0].reshape(L, 2 * L - 1), L, 2)) < TOL
+    assert rel_l2(got_s2["forward_adjoint"], ssht_ref.forward_adjoint(flm, L, 2).ravel()) < TOL
