@@ -293,6 +293,7 @@ def run_ours(args):
         flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
         leg_ms, leg_n = ms_kind[0], cnt_kind[0]
         achieved = flops_step * args.steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else None
+        fft_gbs = 2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] > 0 else None
         line = {
             "metric": METRIC, "value": world * nch * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -307,27 +308,33 @@ def run_ours(args):
             "finite": finite,
             "stage_ms_per_step": {"legendre": leg_ms / args.steps, "ring_fft": ms_kind[1] / args.steps,
                                   "elementwise": ms_kind[2] / args.steps},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None,
-                         # dram__bytes_read+write per launch, mean of the 4 launches of one step, from the ncu --set full
-                         # capture profiles/kernels_r1b_metrics.txt (only valid for the default workload)
-                         "traffic": 0.649e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
-                         "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)",
-                         "launches_timed": int(leg_n),
-                         "algorithmic_flops_per_launch": flops_step / 4,
-                         "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
-            # second-largest (by time: largest) kernel, reported the same way: HBM class per SURVEY 8(d);
-            # algorithmic bytes = pixels/coefficients in + ring coefficients out = 32 B x (ncoef+npix) per Psi per chain
-            "roofline_fft": {"bound": "hbm", "kernel": "pxm_ring_fft_kernel (4 launches per step)",
-                             "achieved": 2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] > 0 else None,
-                             "peak": hbm_peak, "unit": "GB/s",
-                             "frac": (2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 / hbm_peak) if ms_kind[1] > 0 else None,
-                             "traffic": 0.470e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
-                             "note": "DRAM traffic equals the algorithmic bytes; the kernel is bound on chip (L1TEX data pipe 72-80 %, "
-                                     "FP64 pipe 35 %), see profiles/kernels_r1b_metrics.txt"},
+            # dominant kernel BY TIME: the ring FFT (HBM class per SURVEY 8(d): algorithmic bytes = pixels or
+            # coefficients in + ring coefficients out = 32 B x (ncoef + npix) per Psi per chain; 4 stages per step)
+            "roofline": {"bound": "hbm", "kernel": "pxm_ring_fft2_kernel (two-pass Bluestein ring FFT; 4 stages = 6 launches per step)",
+                         "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
+                         # dram__bytes_read+write per stage (mean of the 4 stages of one step), ncu --set full capture
+                         # profiles/fft2_r1e_metrics.txt (only valid for the default workload)
+                         "traffic": 0.50e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
+                         "launches_timed": int(cnt_kind[1]),
+                         "algorithmic_bytes_per_stage": 32.0 * (ncoef + npix) * nch / 2,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
+                         "note": "DRAM traffic ~ algorithmic bytes, HBM 13-15 % busy: the kernel is NOT memory bound. An odd ring length "
+                                 "2l-1 (511, 389, 259, ...) costs two power-of-two FFTs of length >= 2n (Bluestein): FP64 pipe 37-41 %, issue "
+                                 "slots 28-33 %, stalls long_scoreboard 27 % / wait 20 % / no_instruction 20 % (profiles/fft2_r1e_metrics.txt)"},
+            # the O(L^3) stage: FP64 tensor-core (DMMA) Legendre contraction, against cuBLAS DGEMM measured in this run
+            "roofline_legendre": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                                  "frac": (achieved / peak) if achieved else None,
+                                  # dram__bytes_read+write per launch, mean of the 4 launches of one step (profiles/kernels_r1b_metrics.txt)
+                                  "traffic": 0.649e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
+                                  "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)",
+                                  "launches_timed": int(leg_n),
+                                  "algorithmic_flops_per_launch": flops_step / 4,
+                                  "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
             "e2e": {"value": world * nch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host"},
+                    "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host, "
+                           "chain groups pipelined over three streams (H2D | kernels | D2H); PCIe-bound"},
             "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
