@@ -18,6 +18,14 @@
 //   * the last forward pass, the product with the filter spectrum and the first
 //     inverse pass act on the same 16 contiguous points and are fused in
 //     registers.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "pxm_common.cuh"
 
 namespace {
@@ -670,10 +678,451 @@ pxm_ring_fft2_kernel(const __grid_constant__ PxmFftGroupTable tab, cplx* __restr
   }
 }
 
+
+// =============================================================================================
+// Persistent, staged variant of the two-pass transform for the radix-32 class (M = 512, 1024):
+//   * grid = 2 CTAs per SM; a CTA walks over work items (ring block x chain, chain fastest) of
+//     the launch, so the group tables stay hot and no CTA start-up cost is paid per ring block;
+//   * the inputs of item i+1 (4 pixel rows = one contiguous 32 KB piece, or the 64/128-byte
+//     (m, row-group, chain) pieces of the k4-interleaved ring array) travel global -> shared
+//     with cp.async (LDGSTS, no registers) WHILE the middle pass and pass 3 of item i run: the
+//     FP64 pipe never waits on DRAM (the non-staged kernel: 27 % of its warp samples);
+//   * the zero-padded half of the Bluestein input and the unused half of its output are pruned
+//     from the first / last radix-R1 DFT (x_j = 0 for j >= n and only z_j, j < n, is needed;
+//     n <= M/2 always): a half-input DFT is two DFTs of half the size.
+// Staging of the ring array: piece (slot, row-group) is copied in 16-byte granules to granule
+// index G = slot * gpc + g with the XOR swizzle (G & 7) ^ ((G >> 3) & 7) inside every 128-byte
+// line, so the quarter-warp reads of pass 1 (4 rings x 2 slots) are bank-conflict free.
+// =============================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
+// 4-D tiled TMA copy global -> shared (tensor map in kernel-parameter space), completes on `bar`
+__device__ __forceinline__ void tma_g2s_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                           uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// The ring array of a paired group as a 4-D tensor of doubles:
+//   [16: (re, im) x (+m, -m) x 4 rings of a row-group][chain][row-group][order |m|]
+// One copy with box (16, 1, 1, ell) and the 128-byte swizzle brings the 128-byte pieces of all orders of one
+// (row-group, chain) to shared memory as rows of 128 bytes whose 16-byte chunks are XOR-ed with (row & 7):
+// the 8 consecutive orders a warp of pass 1 reads fall on every bank exactly twice (the minimum for
+// 64-bit loads).  One instruction per item instead of one 128-byte copy per order.
+constexpr int PXM_FFT3_MAX_MAPS = 8;
+struct Fft3Maps {
+  CUtensorMap m[PXM_FFT3_MAX_MAPS];
+};
+
+// (cos, sin)(2 pi k / 32), k < 16; k is a compile-time constant at every use (unrolled loops)
+__device__ __forceinline__ void w32(int k, double* c, double* sn) {
+  constexpr double CW32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
+                               0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
+                               0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
+                               -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
+                               -0.92387953251128675613, -0.98078528040323044913};
+  constexpr double SW32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
+                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
+                               0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
+                               0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
+                               0.38268343236508977173, 0.19509032201612826785};
+  *c = CW32[k];
+  *sn = SW32[k];
+}
+template <bool INV>
+__device__ __forceinline__ cplx tw32(cplx a, int k) {
+  double c, sn;
+  w32(k, &c, &sn);
+  return twc<INV>(a, c, sn);
+}
+// forward DFT of length R whose inputs x[R/2..R) are zero:  X[2q] = DFT_{R/2}(x)[q],
+// X[2q+1] = DFT_{R/2}(x_j W_R^j)[q]
+template <int R>
+__device__ __forceinline__ void dft_half_in(cplx* x) {
+  constexpr int H = R / 2, STEP = 32 / R;
+  cplx e[H], o[H];
+#pragma unroll
+  for (int j = 0; j < H; ++j) {
+    e[j] = x[j];
+    o[j] = (j == 0) ? x[0] : tw32<false>(x[j], j * STEP);
+  }
+  dftR<H, false>(e);
+  dftR<H, false>(o);
+#pragma unroll
+  for (int q = 0; q < H; ++q) {
+    x[2 * q] = e[q];
+    x[2 * q + 1] = o[q];
+  }
+}
+// inverse DFT of length R of which only the outputs z[0..R/2) are needed (left in x[0..R/2)):
+// z[j] = E[j] + W_R^{-j} O[j],  E / O = inverse DFT_{R/2} of the even / odd inputs
+template <int R>
+__device__ __forceinline__ void dft_half_out(cplx* x) {
+  constexpr int H = R / 2, STEP = 32 / R;
+  cplx e[H], o[H];
+#pragma unroll
+  for (int k = 0; k < H; ++k) {
+    e[k] = x[2 * k];
+    o[k] = x[2 * k + 1];
+  }
+  dftR<H, true>(e);
+  dftR<H, true>(o);
+#pragma unroll
+  for (int j = 0; j < H; ++j) x[j] = cadd(e[j], (j == 0) ? o[0] : tw32<true>(o[j], j * STEP));
+}
+
+struct Fft3Item {
+  int gi;     // group
+  int t0;     // first ring of the block
+  int chain;
+};
+
+// ring blocks of the radix-32 class in processing order (longest transforms first), built by the launcher
+constexpr int PXM_FFT3_MAX_BLOCKS = 1024;
+constexpr int PXM_FFT_MAX_GROUPS_C = 24;  // = PXM_FFT_MAX_GROUPS
+struct Fft3Blocks {
+  unsigned char gi[PXM_FFT3_MAX_BLOCKS];   // group
+  unsigned char blk[PXM_FFT3_MAX_BLOCKS];  // ring block inside the group
+  unsigned char map_of_group[PXM_FFT_MAX_GROUPS_C];  // tensor map of a group's ring array
+};
+// item -> (group, ring block, chain), chain fastest
+__device__ __forceinline__ void fft3_find(const PxmFftGroupTable& tab, const Fft3Blocks& blocks, int b, int chain,
+                                          Fft3Item* out) {
+  out->chain = chain;
+  out->gi = blocks.gi[b];
+  out->t0 = tab.g[out->gi].ring0 + ((int)blocks.blk[b] << tab.g[out->gi].pad);
+}
+
+// issue the TMA copies global -> shared of one item's inputs (one thread); they complete on `bar`
+template <int DIR>
+__device__ __forceinline__ void fft3_stage(const PxmFftGroup& gr, const Fft3Item& it, unsigned char* stage,
+                                           uint64_t* bar, const cplx* __restrict__ pix, size_t pix_chain_stride,
+                                           const CUtensorMap* map) {
+  if (threadIdx.x != 0) return;
+  const int nr = 1 << gr.pad;
+  if (DIR == 0) {  // the rows of a block are contiguous: one 1-D copy
+    const int rows = min(nr, gr.rings - it.t0);
+    const uint32_t bytes = (uint32_t)(rows * gr.n) * 16u;
+    const cplx* src = pix + (size_t)it.chain * pix_chain_stride + gr.pix_off + (size_t)(it.t0 - gr.ring0) * gr.n;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(stage, src, bytes, bar);
+  } else {
+    const int ngrp = min((nr + 3) >> 2, (gr.rings - it.t0 + 3) >> 2);
+    const int blk_bytes = (gr.ell * 128 + 1023) & ~1023;  // every row-group block keeps the swizzle phase
+    mbar_expect_tx(bar, (uint32_t)(ngrp * gr.ell * 128));
+    for (int g4 = 0; g4 < ngrp; ++g4) tma_g2s_4d(stage + g4 * blk_bytes, map, 0, it.chain, (it.t0 >> 2) + g4, 0, bar);
+  }
+}
+
+__device__ __forceinline__ double flip_sign(double x, int mask_hi) {
+  return __hiloint2double(__double2hiint(x) ^ mask_hi, __double2loint(x));
+}
+
+// chirp_s: this group's chirp times sqrt(scale / M) in shared memory (pass 1 and pass 3 each apply it once)
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft3Item& it, cplx* __restrict__ s,
+                                                const unsigned char* __restrict__ stage,
+                                                const cplx* __restrict__ chirp_s, const cplx* __restrict__ arena) {
+  constexpr int M = R1 * R2, H1 = R1 / 2;
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ tw = arena + gr.tw_off;
+  for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
+    int r, j2;
+    if (DIR == 0) {
+      r = idx / R2;
+      j2 = idx - r * R2;
+    } else {
+      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+      r = rhi * 4 + (rem & 3);
+      j2 = rem >> 2;
+    }
+    const cplx w1 = tw[j2 * (gr.M / M)];
+    const int nj = (it.t0 + r < rings) ? n : 0;  // rows past the end of the grid are zeros
+    cplx x[R1];
+    if (DIR == 0) {
+      const cplx* row = reinterpret_cast<const cplx*>(stage) + r * n;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        x[j1] = (j < nj) ? cmul(row[j], chirp_s[j]) : make_double2(0.0, 0.0);
+      }
+    } else {
+      const unsigned char* grp = stage + (size_t)(r >> 2) * ((ell * 128 + 1023) & ~1023);
+      const int rl = r & 3;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        cplx v = make_double2(0.0, 0.0);
+        if (j < nj) {
+          const bool minus = j >= ell;  // order m = j - n < 0: second half of the 128-byte row
+          const int am = minus ? n - j : j;
+          const int d = (minus ? 8 : 0) + rl;  // re at double d, im at d + 4 (two chunks further)
+          const unsigned char* row = grp + am * 128 + (d & 1) * 8;
+          const int sw = am & 7, ch = d >> 1;
+          const double re = *reinterpret_cast<const double*>(row + ((ch ^ sw) << 4));
+          const double im = *reinterpret_cast<const double*>(row + (((ch + 2) ^ sw) << 4));
+          const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+          // (-1)^m of the paired layout and the conjugation on load (x_p = conj(DFT(conj F))) are sign-bit flips
+          v = cmul(make_double2(flip_sign(re, neg), flip_sign(im, neg ^ (int)0x80000000)), chirp_s[j]);
+        }
+        x[j1] = v;
+      }
+    }
+    dft_half_in<R1>(x);
+    twiddle_powers<R1>(x, w1);
+    cplx* dst = s + r * RS + j2;
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
+  }
+}
+
+template <int R1, int R2>
+__device__ __forceinline__ void ring_fft3_middle(const PxmFftGroup& gr, cplx* __restrict__ s,
+                                                 const cplx* __restrict__ arena) {
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ bhat = arena + gr.bhat2_off;
+  const cplx* __restrict__ tw = arena + gr.tw_off;
+  for (int idx = threadIdx.x; idx < nr * R1; idx += blockDim.x) {
+    const int r = idx / R1, k1 = idx - r * R1;
+    cplx* row = s + r * RS + k1 * (R2 + 1);
+    cplx x[R2];
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) x[j2] = row[j2];
+    dftN<R2, false>(x);
+    prefetched<R2, 4>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+    dftN<R2, true>(x);
+    cplx w1 = tw[k1];
+    w1.y = -w1.y;
+    twiddle_powers<R2>(x, w1);
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
+  }
+}
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft3_pass3(const PxmFftGroup& gr, const Fft3Item& it, const cplx* __restrict__ s,
+                                                const cplx* __restrict__ chirp_s, cplx* __restrict__ pix,
+                                                size_t pix_chain_stride, double* __restrict__ F, int nld) {
+  constexpr int H1 = R1 / 2;
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const size_t col0 = (size_t)it.chain * 4;  // paired layout only (the launcher checks)
+  for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
+    int r, j2;
+    if (DIR == 1) {
+      r = idx / R2;
+      j2 = idx - r * R2;
+    } else {
+      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+      r = rhi * 4 + (rem & 3);
+      j2 = rem >> 2;
+    }
+    const int t = it.t0 + r;
+    if (t >= rings) continue;
+    const cplx* src = s + r * RS + j2;
+    cplx x[R1];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) x[k1] = src[k1 * (R2 + 1)];
+    dft_half_out<R1>(x);
+    if (DIR == 0) {
+      double* frow = F + gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
+      const size_t ss = gr.slot_stride;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        if (j < n) {
+          const cplx v = cmul(x[j1], chirp_s[j]);
+          const bool minus = j >= ell;
+          const int am = minus ? n - j : j;
+          double* dst = frow + (size_t)am * ss + (minus ? 8 : 0);
+          const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+          dst[0] = flip_sign(v.x, neg);
+          dst[4] = flip_sign(v.y, neg);  // next column of the k4-interleaved layout
+        }
+      }
+    } else {
+      cplx* row = pix + (size_t)it.chain * pix_chain_stride + gr.pix_off + (size_t)(t - gr.ring0) * n;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        if (j < n) {
+          const cplx v = cmul(x[j1], chirp_s[j]);
+          row[j] = make_double2(v.x, flip_sign(v.y, (int)0x80000000));
+        }
+      }
+    }
+  }
+}
+
+#ifdef PXM_FFT3_TIMING
+__device__ unsigned long long g_fft3_clk[16];
+#define FFT3_T(i)                                                        \
+  do {                                                                   \
+    const long long now_ = clock64();                                    \
+    if (threadIdx.x == 0) atomicAdd(&g_fft3_clk[DIR * 8 + (i)], (unsigned long long)(now_ - tprev_)); \
+    tprev_ = now_;                                                       \
+  } while (0)
+#else
+#define FFT3_T(i)
+#endif
+
+constexpr int PXM_FFT3_WORK = 8 * (16 * 33 + 2) * 16;  // >= 4 * (32 * 33 + 2) * 16
+constexpr int PXM_FFT3_STAGE = 32768;  // 4 rows x 511 x 16 bytes, or 256 orders x 128 bytes
+constexpr int PXM_FFT3_CHIRP = 512 * 16;
+constexpr int PXM_FFT3_SMEM = PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP + 16;
+
+template <int DIR>
+__global__ void __launch_bounds__(128, 2)
+pxm_ring_fft3_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_constant__ Fft3Blocks blocks,
+                     const __grid_constant__ Fft3Maps maps, cplx* __restrict__ pix, size_t pix_chain_stride,
+                     double* __restrict__ F, int nld, const cplx* __restrict__ arena, int nchains, long long nitems) {
+  extern __shared__ __align__(1024) unsigned char fsm[];
+  unsigned char* stage = fsm;  // 1024-byte aligned: the TMA swizzle phase is (row & 7)
+  cplx* s = reinterpret_cast<cplx*>(fsm + PXM_FFT3_STAGE);
+  cplx* chirp_s = reinterpret_cast<cplx*>(fsm + PXM_FFT3_STAGE + PXM_FFT3_WORK);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP);
+  long long item = blockIdx.x;
+  if (item >= nitems) return;
+  if (threadIdx.x == 0) {
+    if (smem_u32(fsm) & 1023) __trap();
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  Fft3Item cur, nxt;
+  // (block, chain) of the item, advanced without divisions
+  int ib = (int)(item / nchains), ic = (int)(item - (long long)ib * nchains);
+  const int db = (int)gridDim.x / nchains, dc = (int)gridDim.x - db * nchains;
+  fft3_find(tab, blocks, ib, ic, &cur);
+  nxt = cur;
+  fft3_stage<DIR>(tab.g[cur.gi], cur, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[cur.gi]]);
+#ifdef PXM_FFT3_TIMING
+  long long tprev_ = clock64();
+#endif
+  int chirp_group = -1;
+  for (; item < nitems; item += gridDim.x) {
+    const PxmFftGroup& gr = tab.g[cur.gi];
+    const bool big = gr.logM == 10;
+    if (cur.gi != chirp_group) {  // a few times per launch: the blocks of a group are consecutive items
+      __syncthreads();            // pass 3 of the previous item has finished with the old chirp
+      const cplx* __restrict__ chirp = arena + gr.chirp_off;
+      const double rs = sqrt(gr.scale / (double)gr.M);
+      for (int j = threadIdx.x; j < gr.n; j += blockDim.x) {
+        const cplx c = chirp[j];
+        chirp_s[j] = make_double2(c.x * rs, c.y * rs);
+      }
+      chirp_group = cur.gi;
+    }
+    __syncthreads();  // pass 3 of the previous item has left the work buffer
+    mbar_wait(bar, phase);  // the staged inputs have landed
+    phase ^= 1;
+    FFT3_T(0);
+    if (big)
+      ring_fft3_pass1<DIR, 32, 32>(gr, cur, s, stage, chirp_s, arena);
+    else
+      ring_fft3_pass1<DIR, 16, 32>(gr, cur, s, stage, chirp_s, arena);
+    FFT3_T(1);
+    __syncthreads();
+    FFT3_T(2);
+    if (item + gridDim.x < nitems) {
+      ib += db;
+      ic += dc;
+      if (ic >= nchains) {
+        ic -= nchains;
+        ++ib;
+      }
+      fft3_find(tab, blocks, ib, ic, &nxt);
+      fft3_stage<DIR>(tab.g[nxt.gi], nxt, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[nxt.gi]]);
+    }
+    FFT3_T(3);
+    if (big)
+      ring_fft3_middle<32, 32>(gr, s, arena);
+    else
+      ring_fft3_middle<16, 32>(gr, s, arena);
+    FFT3_T(4);
+    __syncthreads();
+    FFT3_T(5);
+    if (big)
+      ring_fft3_pass3<DIR, 32, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld);
+    else
+      ring_fft3_pass3<DIR, 16, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld);
+    FFT3_T(6);
+    cur = nxt;
+  }
+}
+
 constexpr int PXM_FFT2_SMEM = (16 * (16 * 17 + 2)) * 16 > (4 * (32 * 33 + 2)) * 16 ? (16 * (16 * 17 + 2)) * 16
                                                                                   : (4 * (32 * 33 + 2)) * 16;
 
 }  // namespace
+
+// tensor map of one paired ring array (see Fft3Maps), cached per (address, layout)
+static bool fft3_tensor_map(const double* base, int nld, unsigned long long slot_stride, int ell, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static std::mutex mu;
+  static EncodeFn encode = nullptr;
+  static bool tried = false;
+  static std::map<std::tuple<const double*, int, unsigned long long, int>, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = (EncodeFn)fn;
+  }
+  if (!encode || ell > 256) return false;
+  const auto key = std::make_tuple(base, nld, slot_stride, ell);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    CUtensorMap m;
+    const cuuint64_t dims[4] = {16, (cuuint64_t)(nld / 4), (cuuint64_t)(slot_stride / (4ULL * nld)), (cuuint64_t)ell};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)nld * 32, (cuuint64_t)slot_stride * 8};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {16, 1, 1, (cuuint32_t)ell};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+    if (cache.size() > 4096) cache.clear();
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return true;
+}
 
 int pxm_fft_choose_M(int n, int* logM) {
   int M = 16, lg = 4;
@@ -706,6 +1155,8 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
     configured = true;
   }
   if (ngroups <= 0) return PXM_OK;  // a rank of an m-sharded plan that owns no ring
@@ -745,7 +1196,7 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
   // there (L=256 single chain 0.21 vs 0.30 ms per iteration); the two-pass kernel wins on throughput.
   // (grids whose rings are all short, M <= 256, stay on the two-pass kernel: radices <= 16, fewer barriers)
   const bool small_grid = (long long)ctas_per_chain * nchains < 1024 && (class_mask & 6) != 0;
-  if (g_fft_legacy == 1 || (small_grid && g_fft_legacy != 2) || ngroups > PXM_FFT_MAX_GROUPS) {
+  if (g_fft_legacy == 1 || (small_grid && g_fft_legacy == 0) || ngroups > PXM_FFT_MAX_GROUPS) {
     if (dir == 0)
       pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 0);
     else
@@ -754,7 +1205,51 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
     return PXM_OK;
   }
   if (class_mask & 2) {
-    if (dir == 0)
+    // persistent staged kernel unless the two-pass one is forced or the ring array is not 16-byte granular
+    Fft3Blocks blocks;
+    Fft3Maps maps;
+    int nmaps = 0;
+    long long n1 = 0;
+    bool ok3 = g_fft_legacy != 2 && (((uintptr_t)F) & 15) == 0 && (nld & 3) == 0;
+    for (int lg = 10; lg >= 9 && ok3; --lg)
+      for (int i = 0; i < ngroups && ok3; ++i) {
+        const PxmFftGroup& g = h_groups[i];
+        if (g.logM != lg) continue;
+        const int end = (i + 1 < ngroups) ? h_groups[i + 1].cta_begin : ctas_per_chain;
+        const int nb = end - g.cta_begin;
+        // paired (+m, -m) layout only; TMA needs 16-byte granularity; the block and map tables have fixed sizes
+        if (!g.paired || g.nslots != g.ell || (g.f_off & 1) || (g.slot_stride % (4ULL * nld)) != 0 ||
+            n1 + nb > PXM_FFT3_MAX_BLOCKS || nb > 256 || nmaps >= PXM_FFT3_MAX_MAPS) {
+          ok3 = false;
+          break;
+        }
+        if (dir == 1 && !fft3_tensor_map(F + g.f_off, nld, g.slot_stride, g.ell, &maps.m[nmaps])) {
+          ok3 = false;
+          break;
+        }
+        blocks.map_of_group[i] = (unsigned char)nmaps++;
+        for (int b = 0; b < nb; ++b) {
+          blocks.gi[n1] = (unsigned char)i;
+          blocks.blk[n1] = (unsigned char)b;
+          ++n1;
+        }
+      }
+    if (ok3) {
+      static int nsm = 0;
+      if (nsm == 0) {
+        int devi = 0;
+        PXM_CUDA(cudaGetDevice(&devi));
+        PXM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devi));
+      }
+      const long long nitems = n1 * nchains;
+      const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);
+      if (dir == 0)
+        pxm_ring_fft3_kernel<0><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                  nitems);
+      else
+        pxm_ring_fft3_kernel<1><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                  nitems);
+    } else if (dir == 0)
       pxm_ring_fft2_kernel<0, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
     else
       pxm_ring_fft2_kernel<1, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
@@ -777,5 +1272,18 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
   return PXM_OK;
 }
 
-// 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies)
+// 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies),
+// 3: two-pass, with the persistent staged kernel for the radix-32 class (what 0 picks for large grids)
 void pxm_fft_set_legacy(int on) { g_fft_legacy = on; }
+
+// development aid (built with -DPXM_FFT3_TIMING only): cycles thread 0 of every CTA of the persistent
+// kernel spent in each phase since the last call
+#ifdef PXM_FFT3_TIMING
+extern "C" int pxm_debug_fft3_clocks(unsigned long long* out8) {
+  unsigned long long z[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, g_fft3_clk, sizeof(z));
+  cudaMemcpyToSymbol(g_fft3_clk, z, sizeof(z));
+  return 0;
+}
+#endif

@@ -484,9 +484,11 @@ def test_myula_graph_replay_matches_eager(px, iters_per_graph):
         px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, P0)
 
 
-def test_ring_fft_two_pass_against_multipass(px):
-    """the two-pass ring FFT (all Bluestein lengths <= 1024) against the independent multi-pass kernel
-    (the path lengths > 1024 take), through all four wavelet operators at the BASELINE bandlimit"""
+@pytest.mark.parametrize("mode", [2, 3])
+def test_ring_fft_two_pass_against_multipass(px, mode):
+    """the two-pass ring FFT (mode 2: all Bluestein lengths <= 1024; mode 3: its persistent, TMA-staged
+    variant for lengths 512 / 1024) against the independent multi-pass kernel (the path lengths > 1024
+    take), through all four wavelet operators at the BASELINE bandlimit"""
     from pxmcmc_b200 import _lib
     from pxmcmc_b200 import device as D
 
@@ -497,7 +499,7 @@ def test_ring_fft_two_pass_against_multipass(px):
     pix = D.to_dev_c(rng.standard_normal((2, plan.npix)) + 1j * rng.standard_normal((2, plan.npix)))
     for name, x in (("synthesis", coef), ("synthesis_adjoint", pix), ("analysis", pix), ("analysis_adjoint", coef)):
         try:
-            _lib.check(_lib.lib.pxm_debug_set_fft_multipass(2))
+            _lib.check(_lib.lib.pxm_debug_set_fft_multipass(mode))
             fast = D.to_host(getattr(plan, name)(x))
             _lib.check(_lib.lib.pxm_debug_set_fft_multipass(1))
             slow = D.to_host(getattr(plan, name)(x))
@@ -532,9 +534,11 @@ def test_iterate_host_pipeline_matches_device_iteration(px):
         assert m._step_counter == 1
 
 
-def test_ring_fft_two_pass_all_radices_against_oracle(px):
-    """two-pass ring FFT forced on (mode 2) at L=70, B=2: Bluestein lengths 16...512, i.e. every radix
-    pair below (32, 32), paired (spin 0) and unpaired (spin 2) ring layouts, against the CPU oracle"""
+@pytest.mark.parametrize("mode", [2, 3])
+def test_ring_fft_two_pass_all_radices_against_oracle(px, mode):
+    """two-pass ring FFT forced on (mode 2; mode 3: persistent staged kernel for length 512, ragged
+    item count) at L=70, B=2: Bluestein lengths 16...512, i.e. every radix pair below (32, 32), paired
+    (spin 0) and unpaired (spin 2) ring layouts, against the CPU oracle"""
     from oracle import pxmcmc_ref as R
     from oracle import ssht_ref
     from pxmcmc_b200 import _lib
@@ -550,7 +554,7 @@ def test_ring_fft_two_pass_all_radices_against_oracle(px):
     flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
     flm[:4] = 0
     try:
-        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(2))
+        _lib.check(_lib.lib.pxm_debug_set_fft_multipass(mode))
         got = {"synthesis": D.to_host(plan.synthesis(D.to_dev_c(coef))), "synthesis_adjoint": D.to_host(plan.synthesis_adjoint(D.to_dev_c(pix))),
                "analysis": D.to_host(plan.analysis(D.to_dev_c(pix))), "analysis_adjoint": D.to_host(plan.analysis_adjoint(D.to_dev_c(coef)))}
         s2 = D.ShtPlan.get(L, 2, 1)
