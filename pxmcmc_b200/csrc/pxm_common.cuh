@@ -135,4 +135,5 @@ struct PxmFftGroup {
   unsigned long long bhat_off;      // complex: FFT_M of the chirp filter, M entries, in the kernel's own permuted order
   unsigned long long tw_off;        // complex: exp(-2 pi i k/M), k < M
   unsigned long long bhat2_off;     // complex: FFT_M of the chirp filter in natural order (two-pass kernel)
+  unsigned long long tw2_off;       // complex, M = 512 / 1024 only: W_M^{j2 k1} as [k1][j2], then as [j2][k1] (2 M entries)
 };

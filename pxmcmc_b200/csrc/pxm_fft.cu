@@ -250,6 +250,17 @@ __global__ void fft_fill_tables_kernel(const PxmFftGroup* groups, int ngroups, c
     sincospi(-2.0 * (double)k / (double)gr.M, &sn, &cs);
     tw[k] = make_double2(cs, sn);
   }
+  if (gr.logM == 9 || gr.logM == 10) {  // twiddles of the persistent two-pass kernel, in both thread orders
+    const int R2 = 32, R1 = gr.M / R2;
+    cplx* tw2 = arena + gr.tw2_off;
+    for (int i = threadIdx.x; i < gr.M; i += blockDim.x) {
+      const int k1 = i / R2, j2 = i - k1 * R2;
+      double sn, cs;
+      sincospi(-2.0 * (double)((k1 * j2) % gr.M) / (double)gr.M, &sn, &cs);
+      tw2[k1 * R2 + j2] = make_double2(cs, sn);
+      tw2[gr.M + j2 * R1 + k1] = make_double2(cs, sn);
+    }
+  }
 }
 
 // filter spectrum in the digit-reversed order produced by the forward passes
@@ -853,18 +864,12 @@ __device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft
   const int n = gr.n, rings = gr.rings, ell = gr.ell;
   const int nr = 1 << gr.pad;
   const int RS = ring_stride2(R1, R2);
-  const cplx* __restrict__ tw = arena + gr.tw_off;
+  const cplx* __restrict__ tw2 = arena + gr.tw2_off;  // [k1][j2]
   for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
-    int r, j2;
-    if (DIR == 0) {
-      r = idx / R2;
-      j2 = idx - r * R2;
-    } else {
-      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
-      r = rhi * 4 + (rem & 3);
-      j2 = rem >> 2;
-    }
-    const cplx w1 = tw[j2 * (gr.M / M)];
+    // 4 rings of a row-group on adjacent lanes, 8 values of j2 per warp: the chirp / twiddle reads are
+    // broadcasts over the rings, the ring-array accesses are 32-byte sectors, the pixel rows 128-byte pieces
+    const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+    const int r = rhi * 4 + (rem & 3), j2 = rem >> 2;
     const int nj = (it.t0 + r < rings) ? n : 0;  // rows past the end of the grid are zeros
     cplx x[R1];
     if (DIR == 0) {
@@ -897,7 +902,7 @@ __device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft
       }
     }
     dft_half_in<R1>(x);
-    twiddle_powers<R1>(x, w1);
+    prefetched<R1 - 1, 4>([&](int i) { return tw2[(i + 1) * R2 + j2]; }, [&](int i, cplx w) { x[i + 1] = cmul(x[i + 1], w); });
     cplx* dst = s + r * RS + j2;
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
@@ -910,7 +915,7 @@ __device__ __forceinline__ void ring_fft3_middle(const PxmFftGroup& gr, cplx* __
   const int nr = 1 << gr.pad;
   const int RS = ring_stride2(R1, R2);
   const cplx* __restrict__ bhat = arena + gr.bhat2_off;
-  const cplx* __restrict__ tw = arena + gr.tw_off;
+  const cplx* __restrict__ tw2t = arena + gr.tw2_off + R1 * R2;  // [j2][k1]
   for (int idx = threadIdx.x; idx < nr * R1; idx += blockDim.x) {
     const int r = idx / R1, k1 = idx - r * R1;
     cplx* row = s + r * RS + k1 * (R2 + 1);
@@ -920,9 +925,8 @@ __device__ __forceinline__ void ring_fft3_middle(const PxmFftGroup& gr, cplx* __
     dftN<R2, false>(x);
     prefetched<R2, 4>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
     dftN<R2, true>(x);
-    cplx w1 = tw[k1];
-    w1.y = -w1.y;
-    twiddle_powers<R2>(x, w1);
+    prefetched<R2 - 1, 4>([&](int i) { return tw2t[(i + 1) * R1 + k1]; },
+                          [&](int i, cplx w) { x[i + 1] = cmulc(x[i + 1], w); });
 #pragma unroll
     for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
   }
@@ -938,15 +942,10 @@ __device__ __forceinline__ void ring_fft3_pass3(const PxmFftGroup& gr, const Fft
   const int RS = ring_stride2(R1, R2);
   const size_t col0 = (size_t)it.chain * 4;  // paired layout only (the launcher checks)
   for (int idx = threadIdx.x; idx < nr * R2; idx += blockDim.x) {
-    int r, j2;
-    if (DIR == 1) {
-      r = idx / R2;
-      j2 = idx - r * R2;
-    } else {
-      const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
-      r = rhi * 4 + (rem & 3);
-      j2 = rem >> 2;
-    }
+    // 4 rings of a row-group on adjacent lanes, 8 values of j2 per warp: the chirp / twiddle reads are
+    // broadcasts over the rings, the ring-array accesses are 32-byte sectors, the pixel rows 128-byte pieces
+    const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+    const int r = rhi * 4 + (rem & 3), j2 = rem >> 2;
     const int t = it.t0 + r;
     if (t >= rings) continue;
     const cplx* src = s + r * RS + j2;
@@ -1242,7 +1241,7 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
         PXM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devi));
       }
       const long long nitems = n1 * nchains;
-      const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);
+      const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);  // 2 CTAs per SM (shared memory, 252 registers)
       if (dir == 0)
         pxm_ring_fft3_kernel<0><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
                                                                   nitems);

@@ -174,6 +174,8 @@ struct FftTables {
     cursor += g.M;
     g.bhat2_off = cursor;
     cursor += g.M;
+    g.tw2_off = cursor;
+    if (g.logM == 9 || g.logM == 10) cursor += 2ULL * g.M;
     by_n[n] = g;
     return g;
   }
