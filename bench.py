@@ -310,18 +310,21 @@ def run_ours(args):
                                   "elementwise": ms_kind[2] / args.steps},
             # dominant kernel BY TIME: the ring FFT (HBM class per SURVEY 8(d): algorithmic bytes = pixels or
             # coefficients in + ring coefficients out = 32 B x (ncoef + npix) per Psi per chain; 4 stages per step)
-            "roofline": {"bound": "hbm", "kernel": "pxm_ring_fft2_kernel (two-pass Bluestein ring FFT; 4 stages = 6 launches per step)",
+            "roofline": {"bound": "hbm", "kernel": "pxm_ring_fft3_kernel (persistent TMA-staged two-pass Bluestein ring FFT; 4 stages = "
+                                                   "4 launches + 2 of pxm_ring_fft2_kernel<.,0> for lengths <= 256 per step)",
                          "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
                          # dram__bytes_read+write per stage (mean of the 4 stages of one step), ncu --set full capture
-                         # profiles/fft2_r1e_metrics.txt (only valid for the default workload)
-                         "traffic": 0.50e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
+                         # profiles/fft3_r1g_metrics.txt (only valid for the default workload)
+                         "traffic": 0.49e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
                          "launches_timed": int(cnt_kind[1]),
                          "algorithmic_bytes_per_stage": 32.0 * (ncoef + npix) * nch / 2,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
-                         "note": "DRAM traffic ~ algorithmic bytes, HBM 13-15 % busy: the kernel is NOT memory bound. An odd ring length "
-                                 "2l-1 (511, 389, 259, ...) costs two power-of-two FFTs of length >= 2n (Bluestein): FP64 pipe 37-41 %, issue "
-                                 "slots 28-33 %, stalls long_scoreboard 27 % / wait 20 % / no_instruction 20 % (profiles/fft2_r1e_metrics.txt)"},
+                         "note": "DRAM traffic = algorithmic bytes, HBM ~20 % busy: the kernel is NOT memory bound. An odd ring length "
+                                 "2l-1 (511, 389, 259, ...) costs two power-of-two FFTs of length >= 2n (Bluestein) on the FP64 pipe, which DFMA "
+                                 "shares with DMMA on this part (profiles/ubench_fp64_r1g.txt): FP64 pipe 49-52 % busy at 2 warps per scheduler "
+                                 "(shared memory caps the kernel at 8 warps per SM); at 100 % of the pipe the stage would take ~0.6 ms = 0.55 "
+                                 "of the HBM roofline (profiles/fft3_r1g_metrics.txt)"},
             # the O(L^3) stage: FP64 tensor-core (DMMA) Legendre contraction, against cuBLAS DGEMM measured in this run
             "roofline_legendre": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                   "frac": (achieved / peak) if achieved else None,
