@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <map>
 #include <mutex>
@@ -808,6 +809,14 @@ __device__ __forceinline__ void dft_half_out(cplx* x) {
   for (int j = 0; j < H; ++j) x[j] = cadd(e[j], (j == 0) ? o[0] : tw32<true>(o[j], j * STEP));
 }
 
+// table loads of the persistent kernel run this many elements ahead of their use (pass 1 / middle pass)
+#ifndef PXM_PF1
+#define PXM_PF1 4
+#endif
+#ifndef PXM_PF2
+#define PXM_PF2 4
+#endif
+
 struct Fft3Item {
   int gi;     // group
   int t0;     // first ring of the block
@@ -902,7 +911,7 @@ __device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft
       }
     }
     dft_half_in<R1>(x);
-    prefetched<R1 - 1, 4>([&](int i) { return tw2[(i + 1) * R2 + j2]; }, [&](int i, cplx w) { x[i + 1] = cmul(x[i + 1], w); });
+    prefetched<R1 - 1, PXM_PF1>([&](int i) { return tw2[(i + 1) * R2 + j2]; }, [&](int i, cplx w) { x[i + 1] = cmul(x[i + 1], w); });
     cplx* dst = s + r * RS + j2;
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
@@ -917,15 +926,18 @@ __device__ __forceinline__ void ring_fft3_middle(const PxmFftGroup& gr, cplx* __
   const cplx* __restrict__ bhat = arena + gr.bhat2_off;
   const cplx* __restrict__ tw2t = arena + gr.tw2_off + R1 * R2;  // [j2][k1]
   for (int idx = threadIdx.x; idx < nr * R1; idx += blockDim.x) {
-    const int r = idx / R1, k1 = idx - r * R1;
+    // 4 rings on adjacent lanes, 8 values of k1 per warp: the filter-spectrum and twiddle loads are
+    // broadcasts over the rings (a quarter of the L1 wavefronts), the row accesses stay conflict free
+    const int rhi = idx / (4 * R1), rem = idx - rhi * 4 * R1;
+    const int r = rhi * 4 + (rem & 3), k1 = rem >> 2;
     cplx* row = s + r * RS + k1 * (R2 + 1);
     cplx x[R2];
 #pragma unroll
     for (int j2 = 0; j2 < R2; ++j2) x[j2] = row[j2];
     dftN<R2, false>(x);
-    prefetched<R2, 4>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+    prefetched<R2, PXM_PF2>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
     dftN<R2, true>(x);
-    prefetched<R2 - 1, 4>([&](int i) { return tw2t[(i + 1) * R1 + k1]; },
+    prefetched<R2 - 1, PXM_PF2>([&](int i) { return tw2t[(i + 1) * R1 + k1]; },
                           [&](int i, cplx w) { x[i + 1] = cmulc(x[i + 1], w); });
 #pragma unroll
     for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
@@ -1241,7 +1253,12 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
         PXM_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, devi));
       }
       const long long nitems = n1 * nchains;
+#ifdef PXM_FFT3_TIMING
+      const int per_sm = getenv("PXM_FFT3_CTAS_PER_SM") ? atoi(getenv("PXM_FFT3_CTAS_PER_SM")) : 2;
+      const int g3 = (int)std::min<long long>(nitems, (long long)per_sm * nsm);
+#else
       const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);  // 2 CTAs per SM (shared memory, 252 registers)
+#endif
       if (dir == 0)
         pxm_ring_fft3_kernel<0><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
                                                                   nitems);
@@ -1274,6 +1291,44 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
 // 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies),
 // 3: two-pass, with the persistent staged kernel for the radix-32 class (what 0 picks for large grids)
 void pxm_fft_set_legacy(int on) { g_fft_legacy = on; }
+
+#ifdef PXM_FFT3_TIMING
+namespace {
+// register-only radix-32 DFT pairs (what the middle pass does between its shared-memory accesses)
+__global__ void __launch_bounds__(128, 2) dft32_ubench_kernel(cplx* out, int iters, double a) {
+  cplx x[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) x[k] = make_double2(a * (k + threadIdx.x), a * (k - 3.0));
+  for (int it = 0; it < iters; ++it) {
+    dft32<false>(x);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = cmul(x[k], make_double2(a, 0.5 * a));
+    dft32<true>(x);
+  }
+  cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc = cadd(acc, x[k]);
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+}  // namespace
+extern "C" int pxm_debug_dft_ubench(int ctas_per_sm, int iters, float* ms_out) {
+  int nsm = 0;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  cplx* out = nullptr;
+  cudaMalloc(&out, sizeof(cplx) * nsm * ctas_per_sm * 128);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  dft32_ubench_kernel<<<nsm * ctas_per_sm, 128>>>(out, 10, 0.001);
+  cudaEventRecord(e0);
+  dft32_ubench_kernel<<<nsm * ctas_per_sm, 128>>>(out, iters, 0.001);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(ms_out, e0, e1);
+  cudaFree(out);
+  return 0;
+}
+#endif
 
 // development aid (built with -DPXM_FFT3_TIMING only): cycles thread 0 of every CTA of the persistent
 // kernel spent in each phase since the last call

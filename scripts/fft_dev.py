@@ -53,4 +53,6 @@ for mode in modes:
         names = ["wait+bar0", "pass1", "bar1", "find+stage", "middle", "bar2", "pass3", "-"]
         for d in (0, 1):
             print(f"   fft3 DIR{d} phase cycles (thread 0 of each CTA, % of both): " + "  ".join(f"{n} {100 * c / tot:.1f}%" for n, c in zip(names, clk[8 * d:8 * d + 8]) if c), flush=True)
+        nitems = 2 * NB * sum((l + 3) // 4 if l > 128 else (l + 7) // 8 for l in plan.bandlimits + [L] if l > 64) * reps
+        print(f"   cycles per item (avg over {nitems} items): " + "  ".join(f"{n} {(clk[i] + clk[8 + i]) / nitems:.0f}" for i, n in enumerate(names) if clk[i]) + f"  total {tot / nitems:.0f}", flush=True)
 lib.pxm_debug_set_fft_multipass(0)

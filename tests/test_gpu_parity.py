@@ -571,3 +571,32 @@ def test_ring_fft_two_pass_all_radices_against_oracle(px, mode):
     assert rel_l2(got_s2["forward"], ssht_ref.forward(pix[0].reshape(L, 2 * L - 1), L, 2)) < TOL
     assert rel_l2(got_s2["inverse_adjoint"], ssht_ref.inverse_adjoint(pix[0].reshape(L, 2 * L - 1), L, 2)) < TOL
     assert rel_l2(got_s2["forward_adjoint"], ssht_ref.forward_adjoint(flm, L, 2).ravel()) < TOL
+
+
+@pytest.mark.parametrize("L", [512, 1024])
+def test_large_bandlimit_adjointness_and_exactness(px, L):
+    """the upper end of the north-star range (L <= 1024; Bluestein lengths 2048 / 4096 -> multi-pass ring FFT,
+    23 GiB of Legendre tables at L = 1024): Euclidean dot-tests of both operator pairs and the exactness of
+    synthesis(analysis(f)) on a band-limited f, the properties the reference's tests/test_transforms.py:16-46
+    assert at L = 10"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    plan = D.WaveletPlan(L, 2.0, 2, 1)  # not cached: the tables are released with the plan
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    def rnd(n):
+        return torch.randn(n, dtype=torch.float64, device="cuda", generator=g) + 1j * torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+
+    x, y = rnd(plan.ncoefs), rnd(plan.npix)
+    syn, syn_adj, ana, ana_adj = plan.synthesis(x), plan.synthesis_adjoint(y), plan.analysis(y), plan.analysis_adjoint(x)
+    d1, d2 = torch.vdot(y, syn), torch.vdot(x, ana)
+    assert abs(d1 - torch.vdot(syn_adj, x)) / abs(d1) < TOL
+    assert abs(d2 - torch.vdot(ana_adj, y)) / abs(d2) < TOL
+    back = plan.synthesis(plan.analysis(syn))
+    assert float((back - syn).abs().pow(2).sum().sqrt() / syn.abs().pow(2).sum().sqrt()) < TOL
+    from pxmcmc_b200._lib import check, lib
+
+    check(lib.pxm_wav_plan_destroy(plan.h))
+    plan.h = None
