@@ -322,7 +322,8 @@ class MYULA(PxMCMC):
         arrays [nchains, .]): copies the state in, runs the kernels, copies the new
         state and predictions back.  This is the end-to-end path bench.py times.
 
-        With several chains the batch is cut into `groups` chain groups that flow through a
+        With several chains the batch is cut into `groups` chain groups (a count, or a list of group
+        sizes) that flow through a
         three-stage pipeline on three CUDA streams -- host->device copy of group g+1, kernels of
         group g, device->host copy of group g-1 -- so that both PCIe directions and the SMs work at
         the same time (the transfers, not the kernels, bound this path).  Results do not depend on
@@ -335,8 +336,17 @@ class MYULA(PxMCMC):
         nch = xh.shape[0]
         if groups is None:
             groups = 8 if (nch >= 64 and nch % 8 == 0) else (4 if (nch >= 16 and nch % 4 == 0) else 1)
-        if nch % groups or self.noise != "device" and groups > 1:
-            groups = 1
+        if isinstance(groups, int):
+            if nch % groups or self.noise != "device" and groups > 1:
+                groups = 1
+            sizes = [nch // groups] * groups
+        else:
+            sizes = [int(g) for g in groups]
+            if sum(sizes) != nch or min(sizes) < 1:
+                raise ValueError("group sizes must be positive and add up to the number of chains")
+            if self.noise != "device":
+                sizes = [nch]
+        groups = len(sizes)
         if groups == 1:
             Xn, Pn = self.iterate(xh.to(dv, non_blocking=True), ph.to(dv, non_blocking=True))
             if X_out is not None:
@@ -354,12 +364,12 @@ class MYULA(PxMCMC):
         s_in, s_out = st
         s_cmp = torch.cuda.current_stream()
         s_in.wait_stream(s_cmp)
-        size = nch // groups
+        starts = [sum(sizes[:g]) for g in range(groups)]
         self._step_counter += 1
         staged = []
         for g in range(groups):  # all uploads are queued first: the copy engine never waits for the host
             with torch.cuda.stream(s_in):
-                sl = slice(g * size, (g + 1) * size)
+                sl = slice(starts[g], starts[g] + sizes[g])
                 Xd, Pd = xh[sl].to(dv, non_blocking=True), ph[sl].to(dv, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_in)
@@ -369,7 +379,7 @@ class MYULA(PxMCMC):
                 s_cmp.wait_event(ev)
                 Xd.record_stream(s_cmp)
                 Pd.record_stream(s_cmp)
-                self._group_offset = g * size
+                self._group_offset = starts[g]
                 Xn, Pn = self.iterate(Xd, Pd)
                 done = torch.cuda.Event()
                 done.record(s_cmp)

@@ -1,0 +1,16 @@
+"""PCIe copy bandwidth of the box (pinned host memory): H2D alone, D2H alone, both at once."""
+import torch, time
+n = 1 << 29  # 512 MiB
+h1 = torch.empty(n, dtype=torch.uint8).pin_memory(); h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
+d1 = torch.empty(n, dtype=torch.uint8, device="cuda"); d2 = torch.empty(n, dtype=torch.uint8, device="cuda")
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+def run(h2d, d2h, reps=5):
+    torch.cuda.synchronize(); t = time.perf_counter()
+    for _ in range(reps):
+        if h2d:
+            with torch.cuda.stream(s1): d1.copy_(h1, non_blocking=True)
+        if d2h:
+            with torch.cuda.stream(s2): h2.copy_(d2, non_blocking=True)
+    torch.cuda.synchronize(); return reps * n / (time.perf_counter() - t) / 1e9
+run(True, True, 1)
+print(f"H2D alone {run(True, False):.1f} GB/s, D2H alone {run(False, True):.1f} GB/s, both at once {run(True, True):.1f} GB/s each direction")

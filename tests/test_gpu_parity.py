@@ -525,7 +525,7 @@ def test_iterate_host_pipeline_matches_device_iteration(px):
     P0 = D.to_host(op.forward(D.to_dev_c(X0)))
     ref = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=9, stream0=3)
     Xr, Pr = ref.iterate(D.to_dev_c(X0), D.to_dev_c(P0))
-    for groups in (1, 4):
+    for groups in (1, 4, [1, 3, 4, 8]):
         m = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=9, stream0=3)
         Xh, Ph = torch.from_numpy(X0.copy()).pin_memory(), torch.from_numpy(P0.copy()).pin_memory()
         Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
