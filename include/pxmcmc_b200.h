@@ -171,6 +171,16 @@ int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* s
 int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
                  int nrows, long long ncols, long long nchains, void* stream);
 
+/* ---- uncertainty quantification ---------------------------------------------
+ * credible_interval_range (pxmcmc/uncertainty.py:7-16): two quantiles of every column of a stored
+ * chain [nsamples][ld] of doubles, numpy's default "linear" method.  The caller passes, for each
+ * quantile q, the lower order statistic lo = floor(v) and the weight gamma = v - lo of the virtual
+ * index v = (n - 1) q (numpy's own expression, evaluated on the host); out = lerp(x[lo],
+ * x[lo+1], gamma) evaluated as numpy's _lerp does.  nsamples <= pxm_quantile_columns_max_samples(). */
+int pxm_quantile_columns(const double* d_chain, long long nsamples, long long ncols, long long ld, long long lo_a,
+                         double gamma_a, long long lo_b, double gamma_b, double* d_out_a, double* d_out_b, void* stream);
+int pxm_quantile_columns_max_samples(void);
+
 /* ---- measurement aids (bench.py) ---------------------------------------------
  * pxm_profile_begin/end bracket a region in which every library call records a
  * CUDA-event pair on its launching stream; end() returns the summed device time

@@ -4,6 +4,8 @@
 //
 // All per-chain arrays are [nchains][n] row-major; thresholds, data, inverse
 // covariance and weights are shared by all chains and indexed by i.
+#include <math_constants.h>
+
 #include "pxm_common.cuh"
 
 namespace {
@@ -431,6 +433,55 @@ __global__ void k_csr_spmv(const int* __restrict__ indptr, const int* __restrict
   if (lane == 0) y[chain * (size_t)nrows + row] = make_double2(re, im);
 }
 
+// ---------------------------------------------------------------------------
+// Column quantiles of a stored chain [nsamples][ld] (np.quantile(chain, (q_a, q_b), axis=0), method
+// "linear": /root/reference/pxmcmc/uncertainty.py:7-16).  A CTA keeps C adjacent columns in shared
+// memory (rows arrive as C consecutive doubles: coalesced), sorts every column with a bitonic network
+// and interpolates exactly like numpy's _lerp: a + (b-a) t, or b - (b-a)(1-t) when t >= 0.5.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double lerp_np(double a, double b, double t) {
+  const double d = b - a;
+  return (t >= 0.5) ? b - d * (1.0 - t) : a + d * t;
+}
+__global__ void k_quantile_columns(const double* __restrict__ chain, long long nsamples, long long ncols, long long ld,
+                                   int npad, int C, long long lo_a, double g_a, long long lo_b, double g_b,
+                                   double* __restrict__ out_a, double* __restrict__ out_b) {
+  extern __shared__ double qs[];
+  const long long col0 = (long long)blockIdx.x * C;
+  const int cs = npad + 1;  // column stride: the transposing stores of a row land in distinct banks
+  const int nc = (int)min((long long)C, ncols - col0);
+  for (long long i = threadIdx.x; i < (long long)npad * C; i += blockDim.x) {
+    const long long row = i / C;
+    const int c = (int)(i - row * C);
+    double v = CUDART_INF;  // padding sorts to the end
+    if (row < nsamples && c < nc) v = chain[row * ld + col0 + c];
+    qs[c * cs + row] = v;
+  }
+  __syncthreads();
+  const int half = npad >> 1;
+  for (int size = 2; size <= npad; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < half * nc; i += blockDim.x) {
+        const int c = i / half, k = i - c * half;
+        const int pos = 2 * k - (k & (stride - 1));
+        double* col = qs + c * cs;
+        const double x = col[pos], y = col[pos + stride];
+        const bool up = (pos & size) == 0;
+        if ((x > y) == up) {
+          col[pos] = y;
+          col[pos + stride] = x;
+        }
+      }
+      __syncthreads();
+    }
+  for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+    const double* col = qs + c * cs;
+    const long long hi_a = min(lo_a + 1, nsamples - 1), hi_b = min(lo_b + 1, nsamples - 1);
+    out_a[col0 + c] = lerp_np(col[lo_a], col[hi_a], g_a);
+    out_b[col0 + c] = lerp_np(col[lo_b], col[hi_b], g_b);
+  }
+}
+
 inline int grid_for(size_t total, int block = 256) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -623,6 +674,34 @@ int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, doub
   if (!total) return PXM_OK;
   k_gradlogpi<<<grid_for(total), 256, 0, st>>>((const cplx*)X, (const cplx*)prox, Tv, Ts, (const cplx*)gradg, lmda,
                                                 (cplx*)out, n, total);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
+// largest chain length the in-shared-memory sort handles (one column of 2^14 doubles + padding)
+int pxm_quantile_max_samples() { return 16384; }
+
+int pxm_launch_quantile_columns(const double* chain, long long nsamples, long long ncols, long long ld, long long lo_a,
+                                double g_a, long long lo_b, double g_b, double* out_a, double* out_b, cudaStream_t st) {
+  if (nsamples <= 0 || ncols <= 0) return PXM_OK;
+  if (nsamples > pxm_quantile_max_samples()) {
+    pxm_set_error("quantile: more samples than the shared-memory sort holds (16384)");
+    return PXM_ERR_UNSUPPORTED;
+  }
+  int npad = 2;
+  while (npad < nsamples) npad <<= 1;
+  const size_t budget = 200 * 1024;
+  int C = (int)(budget / ((size_t)(npad + 1) * 8));
+  if (C > 32) C = 32;
+  if (C < 1) C = 1;
+  const size_t smem = (size_t)C * (npad + 1) * 8;
+  static bool configured = false;
+  if (!configured) {
+    PXM_CUDA(cudaFuncSetAttribute(k_quantile_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  const long long grid = (ncols + C - 1) / C;
+  k_quantile_columns<<<(unsigned)grid, 256, smem, st>>>(chain, nsamples, ncols, ld, npad, C, lo_a, g_a, lo_b, g_b, out_a, out_b);
   PXM_LAUNCHED();
   return PXM_OK;
 }

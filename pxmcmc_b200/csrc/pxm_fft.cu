@@ -869,7 +869,7 @@ template <int DIR, int R1, int R2>
 __device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft3Item& it, cplx* __restrict__ s,
                                                 const unsigned char* __restrict__ stage,
                                                 const cplx* __restrict__ chirp_s, const cplx* __restrict__ arena) {
-  constexpr int M = R1 * R2, H1 = R1 / 2;
+  constexpr int H1 = R1 / 2;
   const int n = gr.n, rings = gr.rings, ell = gr.ell;
   const int nr = 1 << gr.pad;
   const int RS = ring_stride2(R1, R2);
@@ -1017,15 +1017,15 @@ __global__ void __launch_bounds__(128, 2)
 pxm_ring_fft3_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_constant__ Fft3Blocks blocks,
                      const __grid_constant__ Fft3Maps maps, cplx* __restrict__ pix, size_t pix_chain_stride,
                      double* __restrict__ F, int nld, const cplx* __restrict__ arena, int nchains, long long nitems) {
-  extern __shared__ __align__(1024) unsigned char fsm[];
-  unsigned char* stage = fsm;  // 1024-byte aligned: the TMA swizzle phase is (row & 7)
-  cplx* s = reinterpret_cast<cplx*>(fsm + PXM_FFT3_STAGE);
-  cplx* chirp_s = reinterpret_cast<cplx*>(fsm + PXM_FFT3_STAGE + PXM_FFT3_WORK);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm + PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP);
+  extern __shared__ __align__(1024) unsigned char fsm3[];
+  unsigned char* stage = fsm3;  // 1024-byte aligned: the TMA swizzle phase is (row & 7)
+  cplx* s = reinterpret_cast<cplx*>(fsm3 + PXM_FFT3_STAGE);
+  cplx* chirp_s = reinterpret_cast<cplx*>(fsm3 + PXM_FFT3_STAGE + PXM_FFT3_WORK);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm3 + PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP);
   long long item = blockIdx.x;
   if (item >= nitems) return;
   if (threadIdx.x == 0) {
-    if (smem_u32(fsm) & 1023) __trap();
+    if (smem_u32(fsm3) & 1023) __trap();
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }

@@ -1200,6 +1200,15 @@ int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* s
   return pxm_launch_r2c(d_x, d_out, (size_t)total, (cudaStream_t)stream);
 }
 
+int pxm_quantile_columns(const double* d_chain, long long nsamples, long long ncols, long long ld, long long lo_a,
+                         double gamma_a, long long lo_b, double gamma_b, double* d_out_a, double* d_out_b, void* stream) {
+  PXM_REQUIRE(ld >= ncols && lo_a >= 0 && lo_b >= 0 && lo_a < nsamples && lo_b < nsamples, "quantile: bad index or stride");
+  ProfScope _ps(2, (cudaStream_t)stream);
+  return pxm_launch_quantile_columns(d_chain, nsamples, ncols, ld, lo_a, gamma_a, lo_b, gamma_b, d_out_a, d_out_b,
+                                     (cudaStream_t)stream);
+}
+int pxm_quantile_columns_max_samples(void) { return pxm_quantile_max_samples(); }
+
 int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
                  int nrows, long long ncols, long long nchains, void* stream) {
   ProfScope _ps(2, (cudaStream_t)stream);

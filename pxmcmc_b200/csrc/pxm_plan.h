@@ -128,4 +128,8 @@ int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st);
 int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* vals, const void* x, void* y, int nrows,
                         size_t ncols, size_t nchains, cudaStream_t st);
 
+int pxm_quantile_max_samples();
+int pxm_launch_quantile_columns(const double* chain, long long nsamples, long long ncols, long long ld, long long lo_a,
+                                double g_a, long long lo_b, double g_b, double* out_a, double* out_b, cudaStream_t st);
+
 int pxm_debug_naive();

@@ -600,3 +600,47 @@ def test_large_bandlimit_adjointness_and_exactness(px, L):
 
     check(lib.pxm_wav_plan_destroy(plan.h))
     plan.h = None
+
+
+def test_credible_interval_ranges_match_the_reference_bit_for_bit(px):
+    """pxmcmc/uncertainty.py through the GPU column-quantile kernel against the vectors the unmodified
+    reference produced (np.quantile, method "linear"): ragged column counts, 37 to 5000 samples
+    (padded to the next power of two in shared memory), ties; == not allclose"""
+    import torch
+
+    from oracle.gen_golden_uncertainty import CASES, make_chain
+    from pxmcmc_b200 import uncertainty as U
+
+    g = golden("ref_uncertainty.npz")
+    for i, (n, p, seed) in enumerate(CASES):
+        chain = make_chain(n, p, seed)
+        assert np.array_equal(U.credible_interval_range(chain), g[f"ci_{i}"])
+        assert np.array_equal(U.credible_interval_range(chain, alpha=0.1), g[f"ci10_{i}"])
+        dev = U.credible_interval_range(torch.from_numpy(chain).cuda())
+        assert isinstance(dev, torch.Tensor) and np.array_equal(dev.cpu().numpy(), g[f"ci_{i}"])
+        # column tiles smaller than the array (several uploads)
+        assert np.array_equal(U.credible_interval_range(chain, max_bytes=8 * n * 40), g[f"ci_{i}"])
+    maps = U.wavelet_credible_interval_range(make_chain(*CASES[0]), 10, 2, 2)
+    assert [list(m.shape) for m in maps] == g["wav_shapes"].tolist()
+    assert np.array_equal(np.concatenate([m.ravel() for m in maps]), g["wav_flat"])
+    logpis = -np.abs(make_chain(1, 400, 14)[0])
+    assert U.credible_region_threshold(logpis) == g["threshold"] and U.credible_region_threshold(logpis, alpha=0.2) == g["threshold20"]
+    assert U.in_credible_region(g["threshold"] - 1.0, g["threshold"]) and not U.in_credible_region(g["threshold"] + 1.0, g["threshold"])
+    with pytest.raises(TypeError):
+        U.credible_interval_range(make_chain(8, 4, 1) + 1j)
+
+
+def test_chain_to_pixels_is_the_batched_synthesis(px):
+    """the plot scripts' per-sample transform.inverse loop (experiments/earthtopography/plot.py:103-109)
+    as batched launches: real part of Psi(sample) against the oracle"""
+    from oracle import pxmcmc_ref as R
+    from pxmcmc_b200 import uncertainty as U
+
+    L, B, J = 10, 2.0, 2
+    t = px.transforms.SphericalWaveletTransform(L, B, J)
+    ref = R.WaveletTransform(L, B, J)
+    chain = np.random.default_rng(3).standard_normal((7, t.ncoefs))
+    pix = U.chain_to_pixels(chain, t, batch=3)
+    assert pix.shape == (7, L * (2 * L - 1)) and pix.dtype == np.float64
+    for i in range(7):
+        assert rel_l2(pix[i], ref.inverse(chain[i].astype(complex)).real) < TOL

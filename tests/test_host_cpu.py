@@ -316,3 +316,51 @@ def test_msharded_host_logic_gloo_world_size_2(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert "MS_HOST_OK" in outs[0][0]
+
+
+def test_quantile_virtual_index_reproduces_numpy_and_the_reference_fixture():
+    """host half of credible_interval_range: numpy's virtual index / _lerp arithmetic, checked bit for
+    bit against np.quantile and against the vectors the unmodified reference produced
+    (tests/golden/ref_uncertainty.npz, oracle/gen_golden_uncertainty.py)"""
+    from conftest import golden
+    from oracle.gen_golden_uncertainty import CASES, make_chain
+    from pxmcmc_b200.uncertainty import _virtual_index
+
+    def lerp(a, b, t):
+        d = b - a
+        return np.where(t >= 0.5, b - d * (1.0 - t), a + d * t)
+
+    g = golden("ref_uncertainty.npz")
+    for i, (n, p, seed) in enumerate(CASES):
+        s = np.sort(make_chain(n, p, seed), axis=0)
+        for alpha, key in ((0.05, f"ci_{i}"), (0.1, f"ci10_{i}")):
+            q = []
+            for qq in (alpha / 2, 1 - alpha / 2):
+                lo, gam = _virtual_index(n, qq)
+                q.append(lerp(s[lo], s[min(lo + 1, n - 1)], gam))
+                assert np.array_equal(q[-1], np.quantile(s, qq, axis=0))
+            assert np.array_equal(q[1] - q[0], g[key])
+    with pytest.raises(ValueError):
+        _virtual_index(10, 1.5)
+
+
+def test_saving_roundtrip_uses_the_reference_dataset_names(tmp_path):
+    """save_mcmc / load_mcmc (pxmcmc/saving.py:18-36): dataset and attribute names of the reference"""
+    from pxmcmc_b200 import saving
+    from pxmcmc_b200.mcmc import PxMCMCParams
+
+    class Run:
+        pass
+
+    run = Run()
+    run.logPi, run.L2s, run.priors = np.arange(4.0), np.arange(4.0) * 2, np.arange(4.0) * 3
+    run.chain, run.preds = np.arange(12.0).reshape(4, 3), np.ones((4, 5))
+    run.acceptance_trace, run.deltas_trace = [1, 0, 1, 1], [1e-6, 2e-6, 2e-6, 3e-6, 3e-6]
+    prm = PxMCMCParams(nsamples=4, nburn=1, ngap=2, track=["chain"])
+    path = saving.save_mcmc(run, prm, str(tmp_path), filename="out", L=10, setting="synthesis")
+    data, attrs = saving.load_mcmc(path)
+    assert sorted(data) == sorted(["logposterior", "predictions", "chain", "L2s", "priors", "acceptances", "deltas"])
+    assert np.array_equal(data["chain"], run.chain) and data["acceptances"].dtype == np.int8
+    assert int(attrs["nsamples"]) == 4 and int(attrs["L"]) == 10 and str(attrs["setting"]) == "synthesis"
+    for k in prm.__dict__:
+        assert k in attrs
