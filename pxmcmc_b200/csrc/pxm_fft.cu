@@ -1204,9 +1204,10 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
     for (int i = 0; i < ngroups; ++i) tab.g[i] = h_groups[i];
   // Few CTAs (single chain, m-sharded ranks): the launch is one wave whose duration is the latency of a
   // single CTA, and the multi-pass kernel spreads a ring over twice as many threads -> measured faster
-  // there (L=256 single chain 0.21 vs 0.30 ms per iteration); the two-pass kernel wins on throughput.
+  // there (L=256: 1 chain 0.099 vs 0.115 ms of ring FFT per iteration, 2 chains equal, 4 chains 0.187 vs 0.157:
+  // gpurun_out/fft_dev_small.log); the persistent two-pass kernel wins on throughput.
   // (grids whose rings are all short, M <= 256, stay on the two-pass kernel: radices <= 16, fewer barriers)
-  const bool small_grid = (long long)ctas_per_chain * nchains < 1024 && (class_mask & 6) != 0;
+  const bool small_grid = (long long)ctas_per_chain * nchains < 700 && (class_mask & 6) != 0;
   if (g_fft_legacy == 1 || (small_grid && g_fft_legacy == 0) || ngroups > PXM_FFT_MAX_GROUPS) {
     if (dir == 0)
       pxm_ring_fft_kernel<0><<<grid, 256, PXM_FFT_SMEM, stream>>>(d_groups, ngroups, px, pix_chain_stride, F, nld, ar, 0);
