@@ -64,6 +64,11 @@ int pxm_wav_synthesis(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int n
 int pxm_wav_synthesis_adjoint(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
 int pxm_wav_analysis(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
 int pxm_wav_analysis_adjoint(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int nbatch, void* stream);
+/* Harmonic-space ends of the synthesis pair: synthesis without its last A_inv(L,0) (output f_lm, [nbatch][L^2],
+ * index l^2+l+m) and synthesis_adjoint without its first A_inv^dagger (input f_lm).  A measurement that starts with
+ * A_fwd(L,0) (WeakLensing, pxmcmc/measurements.py:223,239) composes with them exactly (A_fwd o A_inv = I on f_lm). */
+int pxm_wav_synthesis_harmonic(pxm_wav_plan* plan, const void* d_coef, void* d_flm, int nbatch, void* stream);
+int pxm_wav_synthesis_adjoint_harmonic(pxm_wav_plan* plan, const void* d_flm, void* d_coef, int nbatch, void* stream);
 /* host-only: kappa0[L], kappa[(J-J_min+1)][L] of pys2let.wavelet_tiling
  * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);

@@ -36,6 +36,8 @@ SIGNATURES = {
     "pxm_wav_synthesis_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_analysis": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_analysis_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pxm_wav_synthesis_harmonic": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pxm_wav_synthesis_adjoint_harmonic": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wavelet_tiling": (_i, [_i, _d, _i, _vp, _vp, C.POINTER(_i)]),
     "pxm_hpx_plan_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "pxm_hpx_plan_destroy": (_i, [_vp]),

@@ -686,6 +686,7 @@ struct pxm_wav_plan {
   RingBuf Rfull;
   std::vector<RingBuf> Rsc;
   HarmBuf H;
+  PxmDevVec<unsigned char> d_own;  // per harmonic slot: 1 when this rank owns the azimuthal order
   FftTables ffttab;
   WavDirection syn, ana;  // syn: synthesis + synthesis_adjoint ; ana: analysis + analysis_adjoint
 
@@ -797,6 +798,12 @@ int pxm_wav_plan_create_sharded(int L, double B, int J_min, int max_batch, int r
   p->Rsc.resize(S);
   for (int i = 0; i < S; ++i) make_ring(p->Rsc[i], p->til.bandlimits[i], true, p->nld, wcur, sh, i + 1);
   make_harm(p->H, L, true, p->nld, wcur);
+  PXM_TRY(p->H.d_slot_off.upload(p->H.slot_off));  // for the harmonic-space entry points
+  {
+    std::vector<unsigned char> own(p->H.slot_off.size());
+    for (size_t sl = 0; sl < own.size(); ++sl) own[sl] = pxm_owner_of_m((int)sl, world) == rank;
+    PXM_TRY(p->d_own.upload(own));
+  }
   PXM_CUDA(cudaMalloc(&p->d_ws, wcur * 8));
   PXM_CUDA(cudaMemset(p->d_ws, 0, wcur * 8));
   p->ws_bytes = wcur * 8;
@@ -840,6 +847,8 @@ int pxm_wav_plan_destroy(pxm_wav_plan* p) {
     D->d_g.release();
   }
   p->ffttab.release();
+  p->H.d_slot_off.release();
+  p->d_own.release();
   if (p->d_tab) cudaFree(p->d_tab);
   if (p->d_ws) cudaFree(p->d_ws);
   delete p;
@@ -924,6 +933,48 @@ int pxm_wav_analysis(pxm_wav_plan* p, const void* d_pix, void* d_coef, int nbatc
 }
 int pxm_wav_analysis_adjoint(pxm_wav_plan* p, const void* d_coef, void* d_pix, int nbatch, void* stream) {
   return wav_run(p, 3, const_cast<void*>(d_coef), d_pix, nbatch, stream);
+}
+
+// Harmonic-space ends of the synthesis pair.  Psi = A_inv(L,0) o [sum_j kappa_j A_fwd(L_j,0)]: a measurement that
+// starts with A_fwd(L,0) (WeakLensing, /root/reference/pxmcmc/measurements.py:223) meets A_fwd o A_inv = I on f_lm
+// (MW sampling is exact), and its adjoint ends with A_fwd^dagger against Psi^dagger's leading A_inv^dagger: the two full-L
+// transforms of each direction are skipped.  d_flm: [nbatch][L^2] complex, index l^2 + l + m; on an
+// m-sharded plan only the orders this rank owns are written / read.
+int pxm_wav_synthesis_harmonic(pxm_wav_plan* p, const void* d_coef, void* d_flm, int nb, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  const unsigned char* own = p->ps.sh.world > 1 ? p->d_own.d : nullptr;
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, D.fft_scales_in.groups.data(), (int)D.fft_scales_in.groups.size(),
+                         D.fft_scales_in.ctas, const_cast<void*>(d_coef), (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_in.class_mask, st)); }
+  PXM_TRY(p->ps.barrier(st));  // every rank's ring coefficients are in place
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                              (int)D.a_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  PXM_TRY(p->ps.barrier(st));  // peers are done pulling from this rank's ring buffers
+  { ProfScope _ps(2, st); PXM_TRY(pxm_launch_lm_convert(0, d_flm, p->d_ws, p->H.d_slot_off.d, own, nullptr, p->L, 1, p->nld, nb, st)); }
+  return PXM_OK;
+}
+int pxm_wav_synthesis_adjoint_harmonic(pxm_wav_plan* p, const void* d_flm, void* d_coef, int nb, void* stream) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  const unsigned char* own = p->ps.sh.world > 1 ? p->d_own.d : nullptr;
+  { ProfScope _ps(2, st); PXM_TRY(pxm_launch_lm_convert(1, const_cast<void*>(d_flm), p->d_ws, p->H.d_slot_off.d, own, nullptr, p->L, 1, p->nld, nb, st)); }
+  PXM_TRY(p->ps.barrier(st));  // peers are done reading the ring buffers this stage overwrites
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+                              (int)D.s_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  PXM_TRY(p->ps.barrier(st));  // every rank's tiles have landed
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, D.fft_scales_out.groups.data(), (int)D.fft_scales_out.groups.size(),
+                         D.fft_scales_out.ctas, d_coef, (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_out.class_mask, st)); }
+  return PXM_OK;
 }
 
 // =========================================================================

@@ -123,6 +123,14 @@ class WaveletPlan:
     def analysis_adjoint(self, coef):
         return self._run(lib.pxm_wav_analysis_adjoint, coef, self.ncoefs, self.npix, True)
 
+    def synthesis_harmonic(self, coef):
+        """synthesis stopped in harmonic space: coefficients -> f_lm [L^2] of the image"""
+        return self._run(lib.pxm_wav_synthesis_harmonic, coef, self.ncoefs, self.L * self.L, True)
+
+    def synthesis_adjoint_harmonic(self, flm):
+        """adjoint of `synthesis_harmonic`"""
+        return self._run(lib.pxm_wav_synthesis_adjoint_harmonic, flm, self.L * self.L, self.ncoefs, True)
+
 
 class ShtPlan:
     """pxm_sht_plan: the four pyssht-level transforms for one (L, spin, nbatch)."""

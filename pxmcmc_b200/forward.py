@@ -60,7 +60,20 @@ class ForwardOperator:
     def _forward_analysis(self, X):
         return self.measurement.forward(X)
 
+    # Weak lensing behind a wavelet synthesis: Psi ends with A_inv(L,0) and the measurement starts with A_fwd(L,0);
+    # A_fwd o A_inv = I on f_lm (MW sampling is exact), so the two full-L transforms of each direction are skipped
+    # (same result to round-off, a third of the Legendre tables never streamed).  Set
+    # `fuse_harmonic = False` for the reference's literal composition.
+    fuse_harmonic = True
+
+    def _fused(self):
+        t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
+        return (self.fuse_harmonic and self.setting == "synthesis" and getattr(m, "_pxm_harmonic_input", False)
+                and hasattr(t, "_inverse_harmonic") and getattr(t, "spin", 0) == 0 and getattr(t, "L", None) == getattr(m, "L", -1))
+
     def _forward_synthesis(self, X):
+        if self._fused():
+            return self.measurement._forward_from_harmonic(self.transform._inverse_harmonic(X))
         return self.measurement.forward(self.transform.inverse(X))
 
     def _residual(self, preds):
@@ -76,6 +89,8 @@ class ForwardOperator:
         return self.measurement.adjoint(self._residual(preds))
 
     def _gradg_synthesis(self, preds):
+        if self._fused():
+            return self.transform._inverse_adjoint_harmonic(self.measurement._adjoint_to_harmonic(self._residual(preds)))
         return self.transform.inverse_adjoint(self._gradg_analysis(preds))
 
     def _build_inverse_covariance_matrix(self, sig_d):

@@ -233,3 +233,21 @@ class WeakLensing(WeakLensingHarmonic):
 
     def adjoint(self, gamma):
         return self._adjoint(gamma, masking=True, cov_weighting=True)
+
+    # the same operator with the convergence given / returned as harmonic coefficients: `forward` without its
+    # leading spin-0 forward SHT (measurements.py:223), `adjoint` without its trailing forward_adjoint (:239)
+    _pxm_harmonic_input = True
+
+    def _forward_from_harmonic(self, klm):
+        idx, w, gl = self._upload()
+        x = D.to_dev_c(klm)
+        nb = 1 if x.dim() == 1 else x.shape[0]
+        gamma = D.ShtPlan.get(self.L, 2, nb).inverse(x, gl=gl)
+        return D.like_input(D.gather_dev(gamma, idx, w, self.ndata), klm)
+
+    def _adjoint_to_harmonic(self, gamma):
+        idx, w, gl = self._upload()
+        y = D.to_dev_c(gamma)
+        nb = 1 if y.dim() == 1 else y.shape[0]
+        g = D.scatter_dev(y, idx, w, self.npix)
+        return D.like_input(D.ShtPlan.get(self.L, 2, nb).inverse_adjoint(g, gl=gl), gamma)

@@ -94,6 +94,16 @@ class SphericalWaveletTransform(Transform):
         nb = 1 if x.dim() == 1 else x.shape[0]
         return D.like_input(getattr(self._plan(nb), name)(x), X)
 
+    # harmonic-space ends of the synthesis pair (used by ForwardOperator when the measurement starts with a
+    # spin-0 forward SHT: A_fwd(L,0) o A_inv(L,0) = I on f_lm)
+    def _inverse_harmonic(self, X):
+        """wavelet coefficients -> f_lm of the image (``inverse`` without its final inverse SHT)"""
+        return self._apply("synthesis_harmonic", X)
+
+    def _inverse_adjoint_harmonic(self, flm):
+        """adjoint of ``_inverse_harmonic``"""
+        return self._apply("synthesis_adjoint_harmonic", flm)
+
     def forward(self, X):
         """image -> wavelet coefficients"""
         return self._apply("analysis", X)

@@ -239,6 +239,13 @@ def test_weaklensing_golden(px):
     t = px.transforms.SphericalWaveletTransform(L, 2, 2)
     fo = px.forward.ForwardOperator(g["gdata"], 1 / wl.inv_cov, "synthesis", transform=t, measurement=wl, nparams=t.ncoefs)
     assert rel_l2(fo.invcov.diagonal(), g["op_invcov"]) < 1e-15
+    # default: harmonic-space composition (the two cancelling full-L SHTs of each direction skipped) ...
+    assert fo._fused()
+    assert rel_l2(fo.forward(g["X"]), g["op_forward"]) < TOL
+    assert rel_l2(fo.calc_gradg(g["op_forward"]), g["op_gradg"]) < TOL
+    # ... and the reference's literal composition through pixel space
+    fo.fuse_harmonic = False
+    assert not fo._fused()
     assert rel_l2(fo.forward(g["X"]), g["op_forward"]) < TOL
     assert rel_l2(fo.calc_gradg(g["op_forward"]), g["op_gradg"]) < TOL
     with pytest.raises(ValueError):
@@ -644,3 +651,33 @@ def test_chain_to_pixels_is_the_batched_synthesis(px):
     assert pix.shape == (7, L * (2 * L - 1)) and pix.dtype == np.float64
     for i in range(7):
         assert rel_l2(pix[i], ref.inverse(chain[i].astype(complex)).real) < TOL
+
+
+def test_weaklensing_harmonic_fusion_equals_pixel_space_composition(px):
+    """Phi(Psi X) and Psi^dagger(Phi^dagger r) through harmonic space against the literal composition through pixel
+    space at L = 96 with a mask, batch of 3 chains; the harmonic ends of the synthesis pair are an adjoint pair"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J = 96, 2.0, 2
+    rng = np.random.default_rng(23)
+    mask = rng.random((L, 2 * L - 1)) > 0.3
+    ngal = rng.uniform(10, 40, size=(L, 2 * L - 1))
+    wl = px.measurements.WeakLensing(L, mask=mask, ngal=ngal)
+    t = px.transforms.SphericalWaveletTransform(L, B, J, nchains=3)
+    data = rng.standard_normal(wl.ndata) + 1j * rng.standard_normal(wl.ndata)
+    fo = px.forward.ForwardOperator(data, 1 / wl.inv_cov, "synthesis", transform=t, measurement=wl, nparams=t.ncoefs)
+    X = D.to_dev_c(rng.standard_normal((3, t.ncoefs)) + 1j * rng.standard_normal((3, t.ncoefs)))
+    fused_p = fo.forward(X)
+    fused_g = fo.calc_gradg(fused_p)
+    fo.fuse_harmonic = False
+    plain_p = fo.forward(X)
+    plain_g = fo.calc_gradg(plain_p)
+    assert rel_l2(D.to_host(fused_p), D.to_host(plain_p)) < 1e-12
+    assert rel_l2(D.to_host(fused_g), D.to_host(plain_g)) < 1e-12
+    x1 = rng.standard_normal(t.ncoefs) + 1j * rng.standard_normal(t.ncoefs)
+    y1 = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    a = np.vdot(y1, t._inverse_harmonic(x1))
+    b = np.vdot(t._inverse_adjoint_harmonic(y1), x1)
+    assert abs(a - b) / abs(a) < TOL
