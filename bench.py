@@ -359,6 +359,9 @@ def run_ours(args):
 # ---------------------------------------------------------------------------------------
 # config 4 of BASELINE.json: ONE weak-lensing chain at L=512, m-sharded over the GPUs (strong scaling)
 # ---------------------------------------------------------------------------------------
+WL_TRAFFIC = 4.52e9  # dram bytes of the 4 Legendre launches of one iteration (profiles/legendre_wl_r1h_metrics.txt)
+
+
 def wl_mask(L):
     """equatorial band |90deg - theta| < 10deg plus the same band in a frame tilted by the
     ICRS->galactic pole angle (stand-in for utils.build_mask(L, 10))"""
@@ -471,10 +474,14 @@ def run_msharded(args):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
     ms_total, leg_ms, fft_ms, el_ms, bad, eager_ms = [float(v) for v in stats.tolist()]
-    # Legendre tables streamed per iteration: the synthesis pair of the wavelet plan (half of its four
-    # families) for Psi and again for Psi^dagger; the spin-0 quadrature table and the spin-2 Lambda table
-    # (half of each SHT plan) for Phi and again for Phi^dagger
-    tab = torch.tensor([float(tr.plan.table_bytes + wl.s0.table_bytes + wl.s2.table_bytes)], dtype=torch.float64, device="cuda")
+    # Legendre tables streamed per iteration (harmonic-space composition of Phi o Psi): the kappa_j-weighted
+    # quadrature tables W_j of the wavelet plan for Psi and again for Psi^dagger, the spin-2 Lambda table (half of
+    # that SHT plan) for Phi and again for Phi^dagger; the wavelet plan's Lambda_L and the spin-0 plan are never read
+    fam = (C.c_longlong * 4)()
+    _lib.check(_lib.lib.pxm_wav_plan_table_bytes_by_family(tr.plan.h, fam))
+    fused = op._fused()
+    tab_bytes = 2 * fam[1] + wl.s2.table_bytes if fused else 2 * (fam[0] + fam[1]) + wl.s0.table_bytes + wl.s2.table_bytes
+    tab = torch.tensor([float(tab_bytes)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tab, op=dist.ReduceOp.SUM)
 
@@ -516,10 +523,10 @@ def run_msharded(args):
                          "achieved": tab.item() * steps / (leg_ms / 1e3) / 1e9 if leg_ms > 0 else None,
                          "peak": world * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
                          if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else world * 6650.0,
-                         "unit": "GB/s", # dram__bytes_read+write summed over the 8 Legendre launches of one iteration, ncu --set full at N=1
-                         # (profiles/legendre_wl_r1c_metrics.txt); only valid for the default workload
-                         "traffic": 6.85e9 if (L, B, J_min, world) == (512, 2.0, 2, 1) else None,
-                         "note": "per ITERATION (8 launches): algorithmic bytes = every Legendre table the iteration uses, read once "
+                         "unit": "GB/s", # dram__bytes_read+write summed over the 4 Legendre launches of one iteration, ncu --set full at N=1
+                         # (profiles/legendre_wl_r1h_metrics.txt); only valid for the default workload
+                         "traffic": WL_TRAFFIC if (L, B, J_min, world) == (512, 2.0, 2, 1) and fused else None,
+                         "note": "per ITERATION (4 launches): algorithmic bytes = every Legendre table the iteration uses, read once "
                                  "(sum over GPUs); with ONE right-hand side the contraction is a table stream, not DMMA-bound; "
                                  f"algorithmic flops {flops:.3e} per iteration -> {flops * steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else 0:.2f} TFLOP/s aggregate"},
             "e2e": {"value": e2e_steps / e2e.item(), "unit": "iterations/s", "h2d_bytes_per_step": int(nbytes.item()),

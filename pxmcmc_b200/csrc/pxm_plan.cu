@@ -872,6 +872,19 @@ int pxm_wav_plan_bandlimits(const pxm_wav_plan* p, int* out, int cap) {
   return PXM_OK;
 }
 
+// bytes of the four table families of this rank: {synthesis Lambda_L, synthesis W_j kappa_j, analysis W_L, analysis Lambda_j kappa_j}
+int pxm_wav_plan_table_bytes_by_family(const pxm_wav_plan* p, long long* out4) {
+  PXM_REQUIRE(p != nullptr && out4 != nullptr, "null argument");
+  const WavDirection* dirs[2] = {&p->syn, &p->ana};
+  for (int d = 0; d < 2; ++d) {
+    out4[2 * d] = (long long)dirs[d]->full.T.doubles * 8;
+    long long sc = 0;
+    for (const TableRef& tr : dirs[d]->scales) sc += (long long)tr.T.doubles * 8;
+    out4[2 * d + 1] = sc;
+  }
+  return PXM_OK;
+}
+
 // host-only: harmonic kernels kappa0 / kappa_j (what pys2let.wavelet_tiling exposes)
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out) {
   PXM_REQUIRE(L >= 1 && B > 1.0 && J_min >= 0, "tiling arguments");

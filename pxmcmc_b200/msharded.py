@@ -188,6 +188,13 @@ class ShardedWaveletPlan(_ShardedBase):
     def analysis_adjoint(self, coef_local):
         return self._call(lib.pxm_wav_analysis_adjoint, coef_local, self.ncoefs_local, self.npix_local)
 
+    def synthesis_harmonic(self, coef_local):
+        """local coefficients -> f_lm (full length, only this rank's orders populated)"""
+        return self._call(lib.pxm_wav_synthesis_harmonic, coef_local, self.ncoefs_local, self.L * self.L)
+
+    def synthesis_adjoint_harmonic(self, flm):
+        return self._call(lib.pxm_wav_synthesis_adjoint_harmonic, flm, self.L * self.L, self.ncoefs_local)
+
 
 class ShardedShtPlan(_ShardedBase):
     """pxm_sht_plan for rank `rank` of `world`: pixel vectors are the local rows, flm
@@ -302,6 +309,14 @@ class ShardedSphericalWaveletTransform:
     def forward_adjoint(self, X):
         return self._apply("analysis_adjoint", X)
 
+    spin = 0
+
+    def _inverse_harmonic(self, X):
+        return self._apply("synthesis_harmonic", X)
+
+    def _inverse_adjoint_harmonic(self, flm):
+        return self._apply("synthesis_adjoint_harmonic", flm)
+
 
 class ShardedWeakLensing:
     """`WeakLensing` (pxmcmc/measurements.py:185-304) of one rank: convergence rows in,
@@ -344,6 +359,18 @@ class ShardedWeakLensing:
         g = D.scatter_dev(y, self._idx, self._w, self.npix)
         glm = self.s2.inverse_adjoint(g, gl=self._gl)
         return D.like_input(self.s0.forward_adjoint(glm), gamma)
+
+    # harmonic-space input / output (see measurements.WeakLensing): the f_lm stay m-sharded between the
+    # wavelet plan and the spin-2 plan, which deal the orders to the ranks with the same owner_of_m
+    _pxm_harmonic_input = True
+
+    def _forward_from_harmonic(self, klm):
+        gamma = self.s2.inverse(D.to_dev_c(klm), gl=self._gl)
+        return D.like_input(D.gather_dev(gamma, self._idx, self._w, self.ndata), klm)
+
+    def _adjoint_to_harmonic(self, gamma):
+        g = D.scatter_dev(D.to_dev_c(gamma), self._idx, self._w, self.npix)
+        return D.like_input(self.s2.inverse_adjoint(g, gl=self._gl), gamma)
 
 
 def sharded_s2_wavelets_l1(transform, T, L, B, J_min, cls=None, **kw):
