@@ -173,6 +173,19 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """pin this rank's threads to the CPUs next to its GPU BEFORE any pinned host buffer is allocated (first touch):
+    the end-to-end path moves ~1 GB per step and GPU over PCIe, and host memory on the far socket halves that"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:  # noqa: BLE001  (restricted cpuset, no NVML: keep the inherited affinity)
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -180,6 +193,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpus = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout at VERSION/WARN level: rank 0 prints ONE JSON line
@@ -341,6 +355,7 @@ def run_ours(args):
                     "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host, "
                            "chain groups pipelined over three streams (H2D | kernels | D2H); PCIe-bound"},
             "clocks": sampler.summary(),
+            "host_cpus_rank0": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None,
         }
         if not args.no_cpu_baseline and world == 1:
             os.environ["PXM_ORACLE_REPS"] = "4"  # ~13 s of CPU work at L=256
