@@ -660,19 +660,29 @@ struct PxmFftGroupTable {
 #ifndef PXM_FFT2_MINB1
 #define PXM_FFT2_MINB1 2
 #endif
+// CTAs (within one chain) that a launch of one class actually has work for: a launch covers only those instead
+// of starting -- and immediately retiring -- the CTAs of every other class (n = 0: identity, all CTAs)
+constexpr int PXM_FFT2_MAX_REMAP = 254;
+struct Fft2Remap {
+  int n;
+  unsigned short cta[PXM_FFT2_MAX_REMAP];
+};
+
 template <int DIR, int CLS>
 __global__ void __launch_bounds__(CLS == 0 ? 256 : 128, CLS == 0 ? 2 : PXM_FFT2_MINB1)
-pxm_ring_fft2_kernel(const __grid_constant__ PxmFftGroupTable tab, cplx* __restrict__ pix,
-                     size_t pix_chain_stride, double* __restrict__ F, int nld, const cplx* __restrict__ arena) {
+pxm_ring_fft2_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_constant__ Fft2Remap remap,
+                     cplx* __restrict__ pix, size_t pix_chain_stride, double* __restrict__ F, int nld,
+                     const cplx* __restrict__ arena) {
   extern __shared__ __align__(16) unsigned char fsm[];
   cplx* s = reinterpret_cast<cplx*>(fsm);
+  const int cta = remap.n ? (int)remap.cta[blockIdx.x] : (int)blockIdx.x;
   int gi = 0;
-  while (gi + 1 < tab.ngroups && (int)blockIdx.x >= tab.g[gi + 1].cta_begin) ++gi;
+  while (gi + 1 < tab.ngroups && cta >= tab.g[gi + 1].cta_begin) ++gi;
   const PxmFftGroup& gr = tab.g[gi];
   const int lgM = gr.logM;
   if (CLS == 0 ? (lgM > 8) : (lgM < 9 || lgM > 10)) return;
   const int chain = blockIdx.y;
-  const int t0 = gr.ring0 + (((int)blockIdx.x - gr.cta_begin) << gr.pad);
+  const int t0 = gr.ring0 + ((cta - gr.cta_begin) << gr.pad);
   cplx* mypix = pix + (size_t)chain * pix_chain_stride + gr.pix_off;
   if (CLS == 0) {
     switch (lgM) {
@@ -1216,6 +1226,26 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
     PXM_LAUNCHED();
     return PXM_OK;
   }
+  // CTA lists of the two-pass classes (class 0: M <= 256, class 1: M = 512 / 1024)
+  Fft2Remap remap[2];
+  for (int c = 0; c < 2; ++c) {
+    remap[c].n = 0;
+    bool fits = true;
+    for (int i = 0; i < ngroups && fits; ++i) {
+      const bool mine = c == 0 ? h_groups[i].logM <= 8 : (h_groups[i].logM == 9 || h_groups[i].logM == 10);
+      if (!mine) continue;
+      const int end = (i + 1 < ngroups) ? h_groups[i + 1].cta_begin : ctas_per_chain;
+      for (int b = h_groups[i].cta_begin; b < end; ++b) {
+        if (remap[c].n >= PXM_FFT2_MAX_REMAP || b > 65535) {
+          fits = false;
+          break;
+        }
+        remap[c].cta[remap[c].n++] = (unsigned short)b;
+      }
+    }
+    if (!fits) remap[c].n = 0;  // identity: every CTA of the chain is started
+  }
+  const dim3 grid0(remap[0].n ? remap[0].n : ctas_per_chain, nchains), grid1(remap[1].n ? remap[1].n : ctas_per_chain, nchains);
   if (class_mask & 2) {
     // persistent staged kernel unless the two-pass one is forced or the ring array is not 16-byte granular
     Fft3Blocks blocks;
@@ -1267,16 +1297,16 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
         pxm_ring_fft3_kernel<1><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
                                                                   nitems);
     } else if (dir == 0)
-      pxm_ring_fft2_kernel<0, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+      pxm_ring_fft2_kernel<0, 1><<<grid1, 128, PXM_FFT2_SMEM, stream>>>(tab, remap[1], px, pix_chain_stride, F, nld, ar);
     else
-      pxm_ring_fft2_kernel<1, 1><<<grid, 128, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+      pxm_ring_fft2_kernel<1, 1><<<grid1, 128, PXM_FFT2_SMEM, stream>>>(tab, remap[1], px, pix_chain_stride, F, nld, ar);
     PXM_LAUNCHED();
   }
   if (class_mask & 1) {
     if (dir == 0)
-      pxm_ring_fft2_kernel<0, 0><<<grid, 256, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+      pxm_ring_fft2_kernel<0, 0><<<grid0, 256, PXM_FFT2_SMEM, stream>>>(tab, remap[0], px, pix_chain_stride, F, nld, ar);
     else
-      pxm_ring_fft2_kernel<1, 0><<<grid, 256, PXM_FFT2_SMEM, stream>>>(tab, px, pix_chain_stride, F, nld, ar);
+      pxm_ring_fft2_kernel<1, 0><<<grid0, 256, PXM_FFT2_SMEM, stream>>>(tab, remap[0], px, pix_chain_stride, F, nld, ar);
     PXM_LAUNCHED();
   }
   if (class_mask & 4) {
