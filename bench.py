@@ -331,7 +331,7 @@ def run_ours(args):
                          "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
                          # dram__bytes_read+write per stage (mean of the 4 stages of one step), ncu --set full capture
-                         # profiles/fft3_r1g_metrics.txt (only valid for the default workload)
+                         # profiles/fft3_r1j_metrics.txt (only valid for the default workload)
                          "traffic": 0.49e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
                          "launches_timed": int(cnt_kind[1]),
                          "algorithmic_bytes_per_stage": 32.0 * (ncoef + npix) * nch / 2,
@@ -340,7 +340,7 @@ def run_ours(args):
                                  "2l-1 (511, 389, 259, ...) costs two power-of-two FFTs of length >= 2n (Bluestein) on the FP64 pipe, which DFMA "
                                  "shares with DMMA on this part (profiles/ubench_fp64_r1g.txt): FP64 pipe 49-52 % busy at 2 warps per scheduler "
                                  "(shared memory caps the kernel at 8 warps per SM); at 100 % of the pipe the stage would take ~0.6 ms = 0.55 "
-                                 "of the HBM roofline (profiles/fft3_r1g_metrics.txt)"},
+                                 "of the HBM roofline (profiles/fft3_r1j_metrics.txt)"},
             # the O(L^3) stage: FP64 tensor-core (DMMA) Legendre contraction, against cuBLAS DGEMM measured in this run
             "roofline_legendre": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                                   "frac": (achieved / peak) if achieved else None,
