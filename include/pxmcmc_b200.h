@@ -144,6 +144,27 @@ int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gr
                            int noise_mode, unsigned long long seed, const unsigned long long* d_step,
                            unsigned int stream0, void* stream);
 int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream);
+/* PxMALA (pxmcmc/mcmc.py:218-289) without a host round trip per iteration.  d_state: 16 doubles
+ *   {delta, 1-delta/lmda, delta/lmda, sqrt(2 delta), log pi(Xc) re, im, L2(Xc) re, im, prior(Xc), accepted, log u,
+ *    log alpha re, im, -, -, -}
+ * pxm_myula_update_dpar / pxm_reduce_dpar: the proposal and the kind-2 reduction with the step size read from
+ * d_state; pxm_pxmala_accept: log alpha from the four reductions, uniform from the step's Philox stream, decision,
+ * traces (acceptances int8[i], deltas[i+1]) and -- tune != 0 -- the new step size, all written on the device;
+ * pxm_select_if: dst_k <- src_k (complex arrays) when *d_flag != 0 (the accepted proposal becomes the state).
+ * CUDA-graph form: step = 0 (update) and i < 0 (accept) make the kernels take the Philox step and the iteration index
+ * from d_state[14] and d_state[13]; pxm_pxmala_accept then advances both. */
+int pxm_myula_update_dpar(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                          void* d_Xout, void* d_prox_out, long long n, long long nchains, const double* d_par,
+                          int noise_mode, unsigned long long seed, unsigned long long step, unsigned int stream0,
+                          void* stream);
+int pxm_reduce_dpar(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
+                    const double* d_par, double lmda, long long n, long long nchains, void* d_partial, void* d_out,
+                    void* stream);
+int pxm_pxmala_accept(double* d_state, const void* d_s1, const void* d_s2, const void* d_L2p, const void* d_priorp,
+                      double mu, double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
+                      unsigned int stream_id, signed char* d_acc_trace, double* d_delta_trace, void* stream);
+int pxm_select_if(const double* d_flag, void* const* d_dst, const void* const* d_src, const long long* counts,
+                  int narrays, void* stream);
 /* pxm_resid_invcov: invcov @ (preds - data) of ForwardOperator._gradg_analysis
  * (pxmcmc/forward.py:66-69) for a diagonal, possibly complex, inverse covariance. */
 int pxm_resid_invcov(const void* d_preds, const void* d_data, const void* d_invcov, void* d_out, long long n,

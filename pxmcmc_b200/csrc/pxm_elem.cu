@@ -112,13 +112,24 @@ struct MyulaArgs {
   int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex)
   unsigned long long seed, step;
   const unsigned long long* step_ptr;  // may be null; otherwise the step is read from the device (CUDA-graph replays)
+  const double* dpar;  // may be null; otherwise {delta, 1 - delta/lmda, delta/lmda, sqrt(2 delta)} live on the device (PxMALA's tuned step)
   unsigned int stream0;
 };
+__device__ __forceinline__ void myula_device_params(MyulaArgs& p) {
+  if (p.step_ptr) p.step = *p.step_ptr;
+  if (p.dpar) {
+    p.delta = p.dpar[0];
+    p.a = p.dpar[1];
+    p.b = p.dpar[2];
+    p.sq2d = p.dpar[3];
+    if (p.step == 0) p.step = (unsigned long long)p.dpar[14];  // CUDA-graph replays: the step lives in the state block
+  }
+}
 
 __global__ void k_counter_add(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
 
 __global__ void k_myula_update(MyulaArgs p) {
-  if (p.step_ptr) p.step = *p.step_ptr;
+  myula_device_params(p);
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.total; i += (size_t)gridDim.x * blockDim.x) {
     const cplx x = p.X[i];
     cplx px;
@@ -160,7 +171,7 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
   const size_t npairs = (p.n + 1) >> 1;
   const size_t nchains = p.total / p.n;
   const size_t tot = npairs * nchains;
-  if (p.step_ptr) p.step = *p.step_ptr;
+  myula_device_params(p);
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
     const size_t chain = q / npairs, pr = q - chain * npairs;
     double z[2];
@@ -210,6 +221,7 @@ struct ReduceArgs {
   const cplx* d;   // kind2: gradg(X1)
   const double* w; // kind0 weights (may be null)
   double delta, lmda;
+  const double* dpar;  // may be null; otherwise delta = dpar[0] (device-resident PxMALA step)
   size_t n;
   cplx* partial;  // [nchains][gridDim.x]
   cplx* out;      // [nchains]
@@ -238,6 +250,7 @@ __device__ __forceinline__ cplx block_sum(cplx v) {
 }
 
 __global__ void k_reduce_stage1(ReduceArgs p) {
+  if (p.dpar) p.delta = p.dpar[0];
   const size_t chain = blockIdx.y;
   const size_t off = chain * p.n;
   cplx acc = make_double2(0.0, 0.0);
@@ -482,6 +495,97 @@ __global__ void k_quantile_columns(const double* __restrict__ chain, long long n
   }
 }
 
+// ---------------------------------------------------------------------------
+// PxMALA accept / reject on the device (/root/reference/pxmcmc/mcmc.py:240-259, :277-289): one thread evaluates
+// log alpha = log q(Xc|Xp) + log pi(Xp) - log q(Xp|Xc) - log pi(Xc) from the four reductions, draws the uniform
+// from the Philox stream of the step, writes the decision, the traces and -- when tuning -- the new step size,
+// so that an iteration needs no host round trip.  State block S (doubles):
+//   0 delta | 1 1-delta/lmda | 2 delta/lmda | 3 sqrt(2 delta) | 4,5 log pi(Xc) | 6,7 L2(Xc) | 8 prior(Xc) | 9 accepted
+//   10 log u | 11,12 log alpha | 13 iteration index | 14 Philox step  (13, 14: used -- and advanced -- when the
+//   launch passes i < 0, the form a captured CUDA graph replays)
+// ---------------------------------------------------------------------------
+struct AcceptArgs {
+  double* S;
+  const cplx* s1;      // sum (Xp - Xc - (delta/2) grad log pi(Xc))^2
+  const cplx* s2;      // sum (Xc - Xp - (delta/2) grad log pi(Xp))^2
+  const cplx* L2p;
+  const cplx* priorp;  // real part used
+  double mu, lmda;
+  int tune;
+  long long i;         // iteration index
+  unsigned long long seed, step;
+  unsigned int stream;
+  signed char* acc_trace;   // [>= i+1]
+  double* delta_trace;      // [>= i+2]; entry 0 = initial delta
+};
+__global__ void k_pxmala_accept(AcceptArgs p) {
+  if (threadIdx.x || blockIdx.x) return;
+  double* S = p.S;
+  const bool counters_on_device = p.i < 0;
+  if (counters_on_device) {
+    p.i = (long long)S[13];
+    p.step = (unsigned long long)S[14];
+  }
+  const double delta = S[0];
+  const double k = -(1.0 / 2 * delta);  // as coded in the reference: (1/2*delta) = delta/2
+  const cplx a1 = p.s1[0], a2 = p.s2[0];
+  const cplx q1 = make_double2(a1.x * a1.x - a1.y * a1.y, a1.x * a1.y + a1.y * a1.x);  // s1 ** 2
+  const cplx q2 = make_double2(a2.x * a2.x - a2.y * a2.y, a2.x * a2.y + a2.y * a2.x);
+  const cplx ltXcXp = make_double2(k * q1.x, k * q1.y), ltXpXc = make_double2(k * q2.x, k * q2.y);
+  const cplx L2p = p.L2p[0];
+  const double priorp = p.priorp[0].x;
+  const cplx lpp = make_double2(-p.mu * priorp - L2p.x, -L2p.y);
+  cplx la = make_double2(ltXpXc.x + lpp.x, ltXpXc.y + lpp.y);
+  la = make_double2(la.x - ltXcXp.x, la.y - ltXcXp.y);
+  la = make_double2(la.x - S[4], la.y - S[5]);
+  // uniform of this step: the Philox block no coefficient pair can reach
+  uint32_t c[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, (uint32_t)p.step, (uint32_t)(p.step >> 32) ^ (p.stream * 0x85EBCA6Bu)};
+  philox4x32_10(c, (uint32_t)p.seed, (uint32_t)(p.seed >> 32) ^ p.stream);
+  const unsigned long long bits = ((unsigned long long)c[0] << 32) | c[1];
+  const double lu = log(((double)(bits >> 11) + 0.5) * (1.0 / 9007199254740992.0));
+  // numpy's ordering of complex numbers: real parts first, then imaginary parts (log u is real)
+  const bool accept = (lu < la.x) || (lu == la.x && 0.0 < la.y);
+  S[9] = accept ? 1.0 : 0.0;
+  S[10] = lu;
+  S[11] = la.x;
+  S[12] = la.y;
+  if (accept) {
+    S[4] = lpp.x;
+    S[5] = lpp.y;
+    S[6] = L2p.x;
+    S[7] = L2p.y;
+    S[8] = priorp;
+  }
+  p.acc_trace[p.i] = accept ? 1 : 0;
+  if (p.tune) {
+    double d = delta * (1 + ((accept ? 1.0 : 0.0) - 0.5) / pow((double)(p.i + 1), 0.75));
+    d = fmin(fmax(d, p.lmda * 1e-8), p.lmda / 2);
+    S[0] = d;
+    S[1] = 1 - d / p.lmda;
+    S[2] = d / p.lmda;
+    S[3] = sqrt(2 * d);
+    p.delta_trace[p.i + 1] = d;
+  }
+  if (counters_on_device) {
+    S[13] = (double)(p.i + 1);
+    S[14] = (double)(p.step + 1);
+  }
+}
+// the accepted proposal becomes the current state: up to four arrays copied when S[9] != 0
+struct SelectArgs {
+  const double* flag;
+  cplx* dst[4];
+  const cplx* src[4];
+  size_t n[4];
+};
+__global__ void k_select(SelectArgs p) {
+  if (*p.flag == 0.0) return;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.n[a]; i += (size_t)gridDim.x * blockDim.x)
+      p.dst[a][i] = p.src[a][i];
+}
+
 inline int grid_for(size_t total, int block = 256) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -506,9 +610,10 @@ int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, 
 int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
                      const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
                      double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
-                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st) {
+                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st, const double* d_par) {
   MyulaArgs p;
   p.step_ptr = d_step;
+  p.dpar = d_par;
   p.X = (const cplx*)X;
   p.prox = (const cplx*)prox;
   p.gradg = (const cplx*)gradg;
@@ -556,9 +661,10 @@ constexpr int PXM_REDUCE_PARTS = 148;
 
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
                       double delta, double lmda, size_t n, size_t nchains, void* partial, void* out,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* d_par) {
   ReduceArgs p;
   p.kind = kind;
+  p.dpar = d_par;
   p.a = (const cplx*)a;
   p.b = (const cplx*)b;
   p.c = (const cplx*)c;
@@ -702,6 +808,46 @@ int pxm_launch_quantile_columns(const double* chain, long long nsamples, long lo
   }
   const long long grid = (ncols + C - 1) / C;
   k_quantile_columns<<<(unsigned)grid, 256, smem, st>>>(chain, nsamples, ncols, ld, npad, C, lo_a, g_a, lo_b, g_b, out_a, out_b);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
+int pxm_launch_pxmala_accept(double* S, const void* s1, const void* s2, const void* L2p, const void* priorp, double mu,
+                             double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
+                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, cudaStream_t st) {
+  AcceptArgs p;
+  p.S = S;
+  p.s1 = (const cplx*)s1;
+  p.s2 = (const cplx*)s2;
+  p.L2p = (const cplx*)L2p;
+  p.priorp = (const cplx*)priorp;
+  p.mu = mu;
+  p.lmda = lmda;
+  p.tune = tune;
+  p.i = i;
+  p.seed = seed;
+  p.step = step;
+  p.stream = stream_id;
+  p.acc_trace = acc_trace;
+  p.delta_trace = delta_trace;
+  k_pxmala_accept<<<1, 32, 0, st>>>(p);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
+int pxm_launch_select(const double* flag, void* const* dst, const void* const* src, const size_t* counts, int narrays,
+                      cudaStream_t st) {
+  SelectArgs p;
+  p.flag = flag;
+  size_t mx = 0;
+  for (int a = 0; a < 4; ++a) {
+    p.dst[a] = a < narrays ? (cplx*)dst[a] : nullptr;
+    p.src[a] = a < narrays ? (const cplx*)src[a] : nullptr;
+    p.n[a] = a < narrays ? counts[a] : 0;
+    mx = p.n[a] > mx ? p.n[a] : mx;
+  }
+  if (!mx) return PXM_OK;
+  k_select<<<grid_for(mx), 256, 0, st>>>(p);
   PXM_LAUNCHED();
   return PXM_OK;
 }

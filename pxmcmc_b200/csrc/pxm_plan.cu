@@ -1211,6 +1211,42 @@ int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gr
                           (size_t)nchains, delta, lmda, noise_mode, seed, 0, d_step, stream0, (cudaStream_t)stream);
 }
 
+// PxMALA without a host round trip per iteration: the tuned step size lives in a device state block
+// (layout: pxm_elem.cu, k_pxmala_accept), the accept test and the state hand-over run on the device
+int pxm_myula_update_dpar(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
+                          void* d_Xout, void* d_prox_out, long long n, long long nchains, const double* d_par,
+                          int noise_mode, unsigned long long seed, unsigned long long step, unsigned int stream0,
+                          void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(d_par != nullptr && (noise_mode == 2 || noise_mode == 3), "dpar update needs a device state block and Philox noise");
+  return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, nullptr, nullptr, d_Xout, d_prox_out, (size_t)n,
+                          (size_t)nchains, 0.0, 1.0, noise_mode, seed, step, nullptr, stream0, (cudaStream_t)stream, d_par);
+}
+int pxm_reduce_dpar(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
+                    const double* d_par, double lmda, long long n, long long nchains, void* d_partial, void* d_out,
+                    void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(kind == 2 && d_par != nullptr, "reduce_dpar: kind 2 with a device state block");
+  return pxm_launch_reduce(kind, a, b, c, d, w, 0.0, lmda, (size_t)n, (size_t)nchains, d_partial, d_out,
+                           (cudaStream_t)stream, d_par);
+}
+int pxm_pxmala_accept(double* d_state, const void* d_s1, const void* d_s2, const void* d_L2p, const void* d_priorp,
+                      double mu, double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
+                      unsigned int stream_id, signed char* d_acc_trace, double* d_delta_trace, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(d_state && d_s1 && d_s2 && d_L2p && d_priorp && d_acc_trace && d_delta_trace, "pxmala_accept: null argument");
+  return pxm_launch_pxmala_accept(d_state, d_s1, d_s2, d_L2p, d_priorp, mu, lmda, tune, i, seed, step, stream_id,
+                                  d_acc_trace, d_delta_trace, (cudaStream_t)stream);
+}
+int pxm_select_if(const double* d_flag, void* const* d_dst, const void* const* d_src, const long long* counts,
+                  int narrays, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(d_flag != nullptr && narrays >= 1 && narrays <= 4, "select_if: 1 to 4 arrays");
+  size_t n[4] = {0, 0, 0, 0};
+  for (int a = 0; a < narrays; ++a) n[a] = (size_t)counts[a];
+  return pxm_launch_select(d_flag, d_dst, d_src, n, narrays, (cudaStream_t)stream);
+}
+
 int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream) {
   PXM_REQUIRE(d_counter != nullptr, "null counter");
   return pxm_launch_counter_add(d_counter, inc, (cudaStream_t)stream);

@@ -109,12 +109,19 @@ int pxm_launch_soft(int is_complex, const void* x, const double* Tv, double Ts, 
 int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const double* Tv, double Ts,
                      const double* w_re, const double* w_im, void* Xout, void* prox_out, size_t n, size_t nchains,
                      double delta, double lmda, int noise_mode, unsigned long long seed, unsigned long long step,
-                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st);
+                     const unsigned long long* d_step, unsigned int stream0, cudaStream_t st,
+                     const double* d_par = nullptr);
 int pxm_launch_counter_add(unsigned long long* ctr, unsigned long long inc, cudaStream_t st);
 int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* out, size_t n, size_t nchains,
                      cudaStream_t st);
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
-                      double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st);
+                      double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st,
+                      const double* d_par = nullptr);
+int pxm_launch_pxmala_accept(double* S, const void* s1, const void* s2, const void* L2p, const void* priorp, double mu,
+                             double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
+                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, cudaStream_t st);
+int pxm_launch_select(const double* flag, void* const* dst, const void* const* src, const size_t* counts, int narrays,
+                      cudaStream_t st);
 int pxm_launch_lincomb(int nx, const void* const* xs, const double* as, const double* z, double cz, double c0,
                        void* out, size_t total, cudaStream_t st);
 int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, double Ts, const void* gradg, double lmda,

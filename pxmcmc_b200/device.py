@@ -221,6 +221,46 @@ def myula_update_dev(X, prox, gradg, Tvec, Tscalar, delta, lmda, w_re=None, w_im
     return (out, pout) if want_prox else out
 
 
+_scratch = {}
+
+
+def myula_update_dpar_dev(X, prox, gradg, Tvec, Tscalar, dpar, noise_mode, seed, step, stream0=0):
+    """the proposal with {delta, 1-delta/lmda, delta/lmda, sqrt(2 delta)} read from the device block `dpar`"""
+    X2, was1 = batch2d(X)
+    nb, n = X2.shape
+    out = torch.empty_like(X2)
+    check(lib.pxm_myula_update_dpar(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(out), None, n, nb, ptr(dpar),
+                                    int(noise_mode), int(seed), int(step), int(stream0), stream_ptr()))
+    return out[0] if was1 else out
+
+
+def reduce_dpar_dev(a, b, c, d, dpar, lmda):
+    """kind-2 reduction (PxMALA transition) with the step size read from the device block `dpar`"""
+    a2, _ = batch2d(a)
+    nb, n = a2.shape
+    key = (nb, a2.device)
+    if key not in _scratch:
+        _scratch[key] = torch.empty(nb * lib.pxm_reduce_scratch_elems(), dtype=CDT, device=a2.device)
+    out = torch.empty(nb, dtype=CDT, device=a2.device)
+    check(lib.pxm_reduce_dpar(2, ptr(a2), ptr(b), ptr(c), ptr(d), None, ptr(dpar), float(lmda), n, nb, ptr(_scratch[key]),
+                              ptr(out), stream_ptr()))
+    return out
+
+
+def pxmala_accept_dev(state, s1, s2, L2p, priorp, mu, lmda, tune, i, seed, step, stream_id, acc_trace, delta_trace):
+    check(lib.pxm_pxmala_accept(ptr(state), ptr(s1), ptr(s2), ptr(L2p), ptr(priorp), float(mu), float(lmda), int(bool(tune)),
+                                int(i), int(seed), int(step), int(stream_id), ptr(acc_trace), ptr(delta_trace), stream_ptr()))
+
+
+def select_if_dev(flag, dsts, srcs):
+    """dst_k <- src_k (complex tensors of equal sizes) when the device double *flag is non-zero"""
+    k = len(dsts)
+    d = (C.c_void_p * 4)(*([t.data_ptr() for t in dsts] + [0] * (4 - k)))
+    sr = (C.c_void_p * 4)(*([t.data_ptr() for t in srcs] + [0] * (4 - k)))
+    cnt = (C.c_longlong * 4)(*([t.numel() for t in dsts] + [0] * (4 - k)))
+    check(lib.pxm_select_if(ptr(flag), d, sr, cnt, k, stream_ptr()))
+
+
 def gradlogpi_dev(X, prox, Tvec, Tscalar, gradg, lmda):
     X2, was1 = batch2d(X)
     out = torch.empty_like(X2)
@@ -234,9 +274,6 @@ def resid_dev(preds, data, invcov):
     out = torch.empty_like(p2)
     check(lib.pxm_resid_invcov(ptr(p2), ptr(data), ptr(invcov), ptr(out), p2.shape[1], p2.shape[0], stream_ptr()))
     return out[0] if was1 else out
-
-
-_scratch = {}
 
 
 def reduce_dev(kind, a, b=None, c=None, d=None, w=None, delta=0.0, lmda=1.0):

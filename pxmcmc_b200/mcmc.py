@@ -443,6 +443,8 @@ class PxMALA(MYULA):
     (pxmcmc/mcmc.py:204-289).  The accept decision uses numpy's global RNG after the
     Gaussian draw, as in the reference."""
 
+    use_graph = True  # device-resident loop: replay the iteration as one CUDA graph
+
     def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), tune_delta=True, **kw):
         super().__init__(forward, prox, mcmcparams, **kw)
         if self.nchains != 1:
@@ -458,8 +460,96 @@ class PxMALA(MYULA):
         val = self._logtrans_dev(self._state(X1), self._state(X2), self._state(proxf), self._state(gradg))
         return val if np.iscomplexobj(X1) or np.iscomplexobj(X2) or np.iscomplexobj(proxf) or np.iscomplexobj(gradg) or D.is_dev(X1) else val.real
 
+    def _device_resident(self):
+        """True when an iteration can run without a host round trip: Philox noise, a native operator with a
+        diagonal covariance and a native L1 prior, one chain"""
+        return (self.noise == "device" and self.nchains == 1 and getattr(self.forward, "_pxm_native", False)
+                and getattr(self.forward, "_diag", None) is not None and isinstance(self.prior, L1)
+                and getattr(self.prior, "_pxm_native", False) and getattr(self.forward, "_pxm_allreduce", None) is None)
+
+    def _run_device(self, start_point=None):
+        """The same loop with the accept test on the device (`pxm_pxmala_accept`): the step size, log pi(Xc) and the
+        traces live in device memory, the accepted proposal is copied over the state by a predicated kernel, and the
+        host reads the decision only on the thinning grid (where the reference stores accepted samples)."""
+        dv = D.dev()
+        X_curr, curr_preds = self._initial_sample(start_point)
+        X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
+        gradg_curr = D.to_dev_c(self._gradg_dev(curr_preds)).clone()
+        proxf_curr = D.to_dev_c(self._proxf_dev(X_curr)).clone()
+        lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
+        S = torch.zeros(16, dtype=D.FDT)
+        S[0], S[1], S[2], S[3] = self.delta, 1 - self.delta / self.lmda, self.delta / self.lmda, np.sqrt(2 * self.delta)
+        S[4], S[5], S[6], S[7], S[8] = np.real(lp[0]), np.imag(lp[0]), np.real(l2[0]), np.imag(l2[0]), pr[0]
+        S = S.to(dv)
+        cap = 1 << 16
+        acc = torch.zeros(cap, dtype=torch.int8, device=dv)
+        dl = torch.zeros(cap + 1, dtype=D.FDT, device=dv)
+        dl[0] = self.delta
+        mode = 3 if self.complex else 2
+        cur = [X_curr, curr_preds, gradg_curr, proxf_curr]
+
+        def body(i_arg, step_arg):
+            """one iteration; (i_arg, step_arg) = (-1, 0): iteration index and Philox step come from S[13], S[14]"""
+            X_prop = D.myula_update_dpar_dev(cur[0], cur[3], cur[2], None, 0.0, S, mode, self.seed, step_arg, self.stream0)
+            prop_preds = D.to_dev_c(self._forward_dev(X_prop))
+            gradg_prop = D.to_dev_c(self._gradg_dev(prop_preds))
+            proxf_prop = D.to_dev_c(self._proxf_dev(X_prop))
+            L2p, priorp = self._logpi_terms_dev(X_prop, prop_preds)
+            s1 = D.reduce_dpar_dev(cur[0], X_prop, cur[3], cur[2], S, self.lmda)
+            s2 = D.reduce_dpar_dev(X_prop, cur[0], proxf_prop, gradg_prop, S, self.lmda)
+            # priorp is the real view of a complex reduction result: same address, the kernel reads its real part
+            D.pxmala_accept_dev(S, s1, s2, L2p, priorp, self.mu, self.lmda, self.tune_delta, i_arg, self.seed, step_arg,
+                                self.stream0, acc, dl)
+            D.select_if_dev(S[9:], cur, [X_prop, prop_preds, gradg_prop, proxf_prop])
+
+        # One CUDA graph per iteration (~30 launches otherwise issued one by one from Python): warm up eagerly on a
+        # side stream as CUDA graphs require (these ARE the first iterations of the chain), then capture with the
+        # counters in the state block
+        graph = None
+        i = j = 0
+
+        def after(i):
+            nonlocal j
+            on_grid = i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
+            verbose = self.verbosity > 0 and (i + 1) % self.verbosity == 0
+            if on_grid or verbose:
+                st = S.cpu().numpy()  # the only host synchronisation
+                if on_grid and st[9] != 0.0:
+                    self._tracking(j, cur[0], cur[1], [complex(st[4], st[5])], [complex(st[6], st[7])], [st[8]])
+                    j += 1
+                if verbose:
+                    self._print_progress(j - 1, st[4], L2=st[6], prior=st[8], acceptanceRate=float(acc[: i + 1].double().mean().item()))
+
+        while j < self.nsamples:
+            if i + 1 >= cap:
+                raise RuntimeError(f"PxMALA: more than {cap} iterations in one run(); split the run")
+            self._step_counter += 1
+            if graph is None and i >= 2 and self.use_graph:
+                S[13], S[14] = float(i), float(self._step_counter)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(graph, stream=side):
+                        body(-1, 0)
+                torch.cuda.current_stream().wait_stream(side)
+            if graph is not None:
+                graph.replay()
+            else:
+                body(i, self._step_counter)
+            after(i)
+            i += 1
+        X_curr, curr_preds = cur[0], cur[1]
+        self.acceptance_trace = [int(v) for v in acc[:i].cpu().numpy()]
+        self.deltas_trace = [float(v) for v in dl[: (i + 1 if self.tune_delta else 1)].cpu().numpy()]
+        self.delta = float(S[0].item())
+        self._final_state = (X_curr, curr_preds)
+        print("\nDONE")
+
     def run(self, start_point=None):
         """the loop of pxmcmc/mcmc.py:218-275"""
+        if self._device_resident():
+            return self._run_device(start_point)
         self.acceptance_trace = []
         self.deltas_trace = [self.delta]
         i = 0

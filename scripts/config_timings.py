@@ -73,15 +73,18 @@ if "2" in which:
     nit = len(m.acceptance_trace)
     dt = (time.perf_counter() - t0) / nit
     out["config2 PxMALA L=256 B=1.5 analysis (host accept, host noise)"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "iterations": nit, "launches": (_lib.lib.pxm_launch_count() - l0) / nit, "acceptance": float(np.mean(m.acceptance_trace))}
-    prm.nsamples = 400
-    m = PxMALA(op, reg, prm, tune_delta=True, noise="device", seed=3)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    m.run(np.zeros(op.nparams))
-    torch.cuda.synchronize()
-    nit = len(m.acceptance_trace)
-    dt = (time.perf_counter() - t0) / nit
-    out["config2 PxMALA L=256 B=1.5 analysis (host accept, Philox noise)"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "iterations": nit, "acceptance": float(np.mean(m.acceptance_trace))}
+    prm.nsamples, prm.ngap = 41, 100  # the reference's default thinning: accepted samples stored every 100 iterations
+    for tag, dev_loop in (("host accept, Philox noise", False), ("device accept and step-size tuning, Philox noise", True)):
+        m = PxMALA(op, reg, prm, tune_delta=True, noise="device", seed=3)
+        if not dev_loop:
+            m._device_resident = lambda: False
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        m.run(np.zeros(op.nparams))
+        torch.cuda.synchronize()
+        nit = len(m.acceptance_trace)
+        dt = (time.perf_counter() - t0) / nit
+        out[f"config2 PxMALA L=256 B=1.5 analysis ({tag}, ngap=100)"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "iterations": nit, "acceptance": float(np.mean(m.acceptance_trace))}
     print(out, flush=True)
 
 if "3" in which:

@@ -681,3 +681,52 @@ def test_weaklensing_harmonic_fusion_equals_pixel_space_composition(px):
     a = np.vdot(y1, t._inverse_harmonic(x1))
     b = np.vdot(t._inverse_adjoint_harmonic(y1), x1)
     assert abs(a - b) / abs(a) < TOL
+
+
+def _philox_uniform(seed, stream, step):
+    """host restatement of the uniform `pxm_pxmala_accept` draws: Philox4x32-10, counter
+    (0xFFFFFFFF, 0xFFFFFFFF, step_lo, step_hi ^ stream*0x85EBCA6B), key (seed_lo, seed_hi ^ stream)"""
+    M = 0xFFFFFFFF
+    c = [M, M, step & M, ((step >> 32) & M) ^ ((stream * 0x85EBCA6B) & M)]
+    k0, k1 = seed & M, ((seed >> 32) & M) ^ (stream & M)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & M, p1 & M, ((p0 >> 32) ^ c[3] ^ k1) & M, p0 & M]
+        k0, k1 = (k0 + 0x9E3779B9) & M, (k1 + 0xBB67AE85) & M
+    bits = (c[0] << 32) | c[1]
+    return ((bits >> 11) + 0.5) / 9007199254740992.0
+
+
+@pytest.mark.parametrize("setting", ["analysis", "synthesis"])
+def test_pxmala_device_resident_loop_equals_the_host_synchronised_loop(px, setting, monkeypatch):
+    """PxMALA with the accept test, the step-size tuning and the state hand-over on the device (no host round trip per
+    iteration) against the loop that decides on the host, fed the same Philox proposals and the same uniforms: identical
+    acceptance trace, same step sizes, same tracked samples"""
+    L, B, J = 16, 2.0, 2
+    rng = np.random.default_rng(41)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    runs = []
+    for device_loop in (True, False):
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.05, setting, L, B, J)
+        # a step of the order of the noise variance: both accepted and rejected proposals occur
+        p = px.mcmc.PxMCMCParams(nsamples=5, nburn=4, ngap=2, delta=2e-3, lmda=1e-2, mu=2.0, verbosity=0,
+                                 track=["logposterior", "L2", "prior", "chain", "predictions"])
+        if setting == "analysis":
+            reg = px.prior.L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu)
+        else:
+            reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu, L=L, B=B, J_min=J)
+        m = px.mcmc.PxMALA(op, reg, p, tune_delta=True, noise="device", seed=77, stream0=2)
+        assert m._device_resident()
+        start = np.random.default_rng(3).laplace(size=op.nparams) * 0.1
+        if not device_loop:
+            monkeypatch.setattr(m, "_device_resident", lambda: False)
+            steps = iter(range(1, 10 ** 6))
+            monkeypatch.setattr(np.random, "rand", lambda: _philox_uniform(77, 2, next(steps)))
+        m.run(start)
+        runs.append(m)
+    a, b = runs
+    assert 0 < sum(a.acceptance_trace) < len(a.acceptance_trace)  # both branches exercised
+    assert a.acceptance_trace == b.acceptance_trace
+    assert np.allclose(a.deltas_trace, b.deltas_trace, rtol=1e-12, atol=0)
+    assert rel_l2(a.chain, b.chain) < TOL and rel_l2(a.preds, b.preds) < TOL
+    assert rel_l2(a.logPi, b.logPi) < TOL and rel_l2(a.L2s, b.L2s) < TOL and rel_l2(a.priors, b.priors) < TOL
