@@ -144,6 +144,10 @@ int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gr
                            int noise_mode, unsigned long long seed, const unsigned long long* d_step,
                            unsigned int stream0, void* stream);
 int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream);
+/* d_out[chain][n] <- N(0,1) from the Philox stream (seed, stream0 + chain, step); d_step != NULL: the step is read from
+ * the device (CUDA-graph replays).  The numbers the update kernel draws in its real-noise mode (SKROCK's Z, mcmc.py:344). */
+int pxm_philox_normal(double* d_out, long long n, long long nchains, unsigned long long seed, unsigned long long step,
+                      const unsigned long long* d_step, unsigned int stream0, void* stream);
 /* PxMALA (pxmcmc/mcmc.py:218-289) without a host round trip per iteration.  d_state: 16 doubles
  *   {delta, 1-delta/lmda, delta/lmda, sqrt(2 delta), log pi(Xc) re, im, L2(Xc) re, im, prior(Xc), accepted, log u,
  *    log alpha re, im, -, -, -}

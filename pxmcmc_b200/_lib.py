@@ -65,6 +65,7 @@ SIGNATURES = {
     "pxm_myula_update": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _ll, _ll, _d, _d, _i, _u64, _u64, _u32, _vp]),
     "pxm_myula_update_dstep": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _ll, _ll, _d, _d, _i, _u64, _vp, _u32, _vp]),
     "pxm_counter_add": (_i, [_vp, _u64, _vp]),
+    "pxm_philox_normal": (_i, [_vp, _ll, _ll, _u64, _u64, _vp, _u32, _vp]),
     "pxm_myula_update_dpar": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _ll, _ll, _vp, _i, _u64, _u64, _u32, _vp]),
     "pxm_reduce_dpar": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _ll, _vp, _vp, _vp]),
     "pxm_pxmala_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _i, _ll, _u64, _u64, _u32, _vp, _vp, _vp]),

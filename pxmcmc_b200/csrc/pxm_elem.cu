@@ -586,6 +586,21 @@ __global__ void k_select(SelectArgs p) {
       p.dst[a][i] = p.src[a][i];
 }
 
+// standard normals from the Philox stream (seed, stream0 + chain, step): element e of a chain is normal (e & 1) of
+// pair e >> 1 -- the same numbers the MYULA update kernel draws (SKROCK's Z, /root/reference/pxmcmc/mcmc.py:344)
+__global__ void k_philox_normal(double* __restrict__ out, size_t n, size_t nchains, unsigned long long seed,
+                                unsigned long long step, const unsigned long long* step_ptr, unsigned int stream0) {
+  if (step_ptr) step = *step_ptr;
+  const size_t npairs = (n + 1) >> 1, tot = npairs * nchains;
+  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
+    const size_t chain = q / npairs, pr = q - chain * npairs;
+    double z0, z1;
+    philox_normal2(seed, stream0 + (unsigned int)chain, step, pr, &z0, &z1);
+    out[chain * n + 2 * pr] = z0;
+    if (2 * pr + 1 < n) out[chain * n + 2 * pr + 1] = z1;
+  }
+}
+
 inline int grid_for(size_t total, int block = 256) {
   size_t g = (total + block - 1) / block;
   const size_t cap = 148 * 16;
@@ -848,6 +863,14 @@ int pxm_launch_select(const double* flag, void* const* dst, const void* const* s
   }
   if (!mx) return PXM_OK;
   k_select<<<grid_for(mx), 256, 0, st>>>(p);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
+int pxm_launch_philox_normal(double* out, size_t n, size_t nchains, unsigned long long seed, unsigned long long step,
+                             const unsigned long long* d_step, unsigned int stream0, cudaStream_t st) {
+  if (!n || !nchains) return PXM_OK;
+  k_philox_normal<<<grid_for(((n + 1) / 2) * nchains), 256, 0, st>>>(out, n, nchains, seed, step, d_step, stream0);
   PXM_LAUNCHED();
   return PXM_OK;
 }

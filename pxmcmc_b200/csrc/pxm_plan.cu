@@ -1247,6 +1247,13 @@ int pxm_select_if(const double* d_flag, void* const* d_dst, const void* const* d
   return pxm_launch_select(d_flag, d_dst, d_src, n, narrays, (cudaStream_t)stream);
 }
 
+int pxm_philox_normal(double* d_out, long long n, long long nchains, unsigned long long seed, unsigned long long step,
+                      const unsigned long long* d_step, unsigned int stream0, void* stream) {
+  ProfScope _ps(2, (cudaStream_t)stream);
+  PXM_REQUIRE(d_out != nullptr && n >= 0 && nchains >= 0, "philox_normal: bad argument");
+  return pxm_launch_philox_normal(d_out, (size_t)n, (size_t)nchains, seed, step, d_step, stream0, (cudaStream_t)stream);
+}
+
 int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void* stream) {
   PXM_REQUIRE(d_counter != nullptr, "null counter");
   return pxm_launch_counter_add(d_counter, inc, (cudaStream_t)stream);

@@ -261,6 +261,13 @@ def select_if_dev(flag, dsts, srcs):
     check(lib.pxm_select_if(ptr(flag), d, sr, cnt, k, stream_ptr()))
 
 
+def philox_normal_dev(nchains, n, seed, step=0, stream0=0, dstep=None):
+    """[nchains, n] float64 standard normals from the library's Philox streams (step from `dstep` when given)"""
+    out = torch.empty((nchains, n), dtype=FDT, device=dev())
+    check(lib.pxm_philox_normal(ptr(out), n, nchains, int(seed), int(step), ptr(dstep), int(stream0), stream_ptr()))
+    return out
+
+
 def gradlogpi_dev(X, prox, Tvec, Tscalar, gradg, lmda):
     X2, was1 = batch2d(X)
     out = torch.empty_like(X2)

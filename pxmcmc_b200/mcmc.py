@@ -607,6 +607,38 @@ class PxMALA(MYULA):
         self.delta = min(max(delta, self.lmda * 1e-8), self.lmda / 2)
 
 
+class _GraphedSkrock:
+    def __init__(self, sampler, X):
+        self.sampler = sampler
+        self.X = sampler._state(X).clone()
+        for _ in range(2):  # warm-up (tables, lazy uploads, allocator pools) before the capture
+            x = sampler._chain_step_dev(self.X)
+            p = D.to_dev_c(sampler._forward_dev(x))
+        self.P = p.clone()
+        torch.cuda.synchronize()
+        # the graph reads (and advances) this counter on every replay: it must stay alive with the graph
+        self.dstep = sampler._dstep = torch.full((1,), sampler._step_counter + 1, dtype=torch.int64, device=self.X.device)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        self.graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(self.graph, stream=side):
+                    x = sampler._chain_step_dev(self.X)
+                    self.P.copy_(D.to_dev_c(sampler._forward_dev(x)))
+                    self.X.copy_(x)
+        finally:
+            sampler._dstep = None
+        torch.cuda.current_stream().wait_stream(side)
+
+    def step(self):
+        self.graph.replay()
+        self.sampler._step_counter += 1
+
+    def state(self):
+        return self.X, self.P
+
+
 class SKROCK(PxMCMC):
     """Stochastic orthogonal Runge-Kutta-Chebyshev sampler (pxmcmc/mcmc.py:292-383).
     The reference evaluates K_s by naive recursion (4 059 gradient evaluations at
@@ -624,9 +656,14 @@ class SKROCK(PxMCMC):
         i = 0
         j = 0
         X_curr, curr_preds = self._initial_sample(start_point)
+        graphed = self.capture(X_curr) if (self.noise == "device" and not self.complex) else None
         while j < self.nsamples:
-            X_curr = self._chain_step_dev(X_curr)
-            curr_preds = D.to_dev_c(self._forward_dev(X_curr))
+            if graphed is not None:  # the whole step (s gradient evaluations + predictions) as one CUDA graph
+                graphed.step()
+                X_curr, curr_preds = graphed.state()
+            else:
+                X_curr = self._chain_step_dev(X_curr)
+                curr_preds = D.to_dev_c(self._forward_dev(X_curr))
             if i >= self.nburn:
                 if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
                     logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
@@ -644,8 +681,23 @@ class SKROCK(PxMCMC):
         if Z is None:
             if self.complex:
                 raise NotImplementedError("complex SKROCK noise is not implemented on the device path")
-            Z = D.to_dev_f(np.random.randn(n * Xd.shape[0])).reshape(Xd.shape)
+            if self.noise == "device":  # Philox normals, step counter on the host or (graph replays) on the device
+                dstep = getattr(self, "_dstep", None)
+                if dstep is None:
+                    self._step_counter += 1
+                Z = D.philox_normal_dev(Xd.shape[0], n, self.seed, self._step_counter, self.stream0, dstep=dstep)
+                if dstep is not None:
+                    D.check(D.lib.pxm_counter_add(D.ptr(dstep), 1, D.stream_ptr()))
+            else:
+                Z = D.to_dev_f(np.random.randn(n * Xd.shape[0])).reshape(Xd.shape)
         return self._K_recursion(Xd, self.s, Z)
+
+    def capture(self, X_curr):
+        """One SKROCK step (s gradient evaluations, ~14 s launches) and its predictions as ONE CUDA graph; needs
+        noise="device".  Returns an object with .step() and .state() -> (X, preds)."""
+        if self.noise != "device":
+            raise ValueError("capture() needs noise='device' (host RNG draws cannot be recorded)")
+        return _GraphedSkrock(self, X_curr)
 
     def chain_step(self, X):
         """one SKROCK step (pxmcmc/mcmc.py:338-347)"""

@@ -108,6 +108,10 @@ if "3" in which:
         st[0] = m._chain_step_dev(st[0])
     dt, nl = timeit(f, 20)
     out["config3 SKROCK s=10 PathIntegral 1e4x32640 (nnz %d) L=128 B=2" % A.nnz] = {"ms_per_step": dt * 1e3, "steps_per_s": 1 / dt, "gradient_evaluations_per_step": s, "launches": nl}
+    mg = SKROCK(op, reg, prm, noise="device", seed=5)
+    gr = mg.capture(st[0])
+    dtg, _ = timeit(gr.step, 50)
+    out["config3 SKROCK s=10 PathIntegral 1e4x32640 (nnz %d) L=128 B=2" % A.nnz].update({"graph_ms_per_step": dtg * 1e3, "graph_steps_per_s": 1 / dtg})
     print(out, flush=True)
 
 if "4" in which:

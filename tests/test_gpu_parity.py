@@ -730,3 +730,45 @@ def test_pxmala_device_resident_loop_equals_the_host_synchronised_loop(px, setti
     assert np.allclose(a.deltas_trace, b.deltas_trace, rtol=1e-12, atol=0)
     assert rel_l2(a.chain, b.chain) < TOL and rel_l2(a.preds, b.preds) < TOL
     assert rel_l2(a.logPi, b.logPi) < TOL and rel_l2(a.L2s, b.L2s) < TOL and rel_l2(a.priors, b.priors) < TOL
+
+
+def test_skrock_device_noise_graph_replay_equals_eager_steps(px):
+    """SKROCK with Philox normals: the step captured as one CUDA graph (device-side step counter) reproduces the
+    eagerly launched step bit for bit, and the Philox normals are those of the update kernel's stream"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J, s_ = 12, 2.0, 2, 4
+    rng = np.random.default_rng(8)
+    npix = L * (2 * L - 1)
+    A = sparse.random(40, npix, density=0.05, random_state=3, format="csr")
+    y = rng.standard_normal(40)
+    prm = px.mcmc.PxMCMCParams(delta=1e-7, lmda=5e-8, mu=1.0, s=s_, verbosity=0, nsamples=3, nburn=1, ngap=1,
+                               track=["logposterior", "L2", "prior", "chain"])
+
+    def make():
+        op = px.forward.PathIntegralOperator(A, y, 0.1, "synthesis", L, B, J)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 5e-8, L=L, B=B, J_min=J)
+        return px.mcmc.SKROCK(op, reg, prm, noise="device", seed=11, stream0=1), op
+
+    m1, op = make()
+    m2, _ = make()
+    X0 = D.to_dev_c(rng.laplace(size=(1, op.nparams)) * 0.01)
+    g = m2.capture(X0)
+    xs = X0
+    for _ in range(3):
+        m1._step_counter = m2._step_counter
+        xs = m1._chain_step_dev(xs)
+        g.step()
+        assert torch.equal(g.state()[0], xs)
+        assert torch.equal(g.state()[1], D.to_dev_c(m1._forward_dev(xs)))
+    # element e of the normal vector = normal (e & 1) of pair e >> 1 of the step's stream
+    z = D.philox_normal_dev(2, 7, 11, step=5, stream0=1)
+    z2 = D.philox_normal_dev(1, 7, 11, step=5, stream0=2)
+    assert torch.equal(z[1], z2[0]) and not torch.equal(z[0], z[1])
+    assert abs(float(D.philox_normal_dev(1, 200000, 3, step=1).mean())) < 0.01
+    # run() with device noise uses the graph and fills the tracked arrays
+    m3, _ = make()
+    m3.run(D.to_host(X0[0]).real)
+    assert np.isfinite(m3.logPi).all() and m3.chain.shape == (3, op.nparams)
