@@ -388,6 +388,11 @@ def test_multichain_device_noise(px):
     m2 = px.mcmc.MYULA(op, reg, p, noise="device", nchains=nb, seed=7)
     m2.run(np.zeros(op.nparams))
     assert np.array_equal(m.chain, m2.chain)
+    # run() replays the iteration as a CUDA graph when the noise is generated on the device: same chain as the eager loop
+    m3 = px.mcmc.MYULA(op, reg, p, noise="device", nchains=nb, seed=7)
+    m3.graph_run = False
+    m3.run(np.zeros(op.nparams))
+    assert np.array_equal(m.chain, m3.chain) and np.array_equal(m.logPi, m3.logPi)
     # first increment is sqrt(2 delta) * N(0,1) to leading order
     z = m.chain[:, 0, :].ravel() / np.sqrt(2e-6)
     assert abs(z.std() - np.sqrt(1.0)) < 0.2
