@@ -148,9 +148,10 @@ int pxm_counter_add(unsigned long long* d_counter, unsigned long long inc, void*
  * the device (CUDA-graph replays).  The numbers the update kernel draws in its real-noise mode (SKROCK's Z, mcmc.py:344). */
 int pxm_philox_normal(double* d_out, long long n, long long nchains, unsigned long long seed, unsigned long long step,
                       const unsigned long long* d_step, unsigned int stream0, void* stream);
-/* PxMALA (pxmcmc/mcmc.py:218-289) without a host round trip per iteration.  d_state: 16 doubles
+/* PxMALA (pxmcmc/mcmc.py:218-289) without a host round trip per iteration.  d_state: 16 doubles PER CHAIN
  *   {delta, 1-delta/lmda, delta/lmda, sqrt(2 delta), log pi(Xc) re, im, L2(Xc) re, im, prior(Xc), accepted, log u,
- *    log alpha re, im, -, -, -}
+ *    log alpha re, im, iteration, Philox step, -}
+ * (every chain tunes its own step size; chain c draws its uniform from the Philox stream stream_id + c).
  * pxm_myula_update_dpar / pxm_reduce_dpar: the proposal and the kind-2 reduction with the step size read from
  * d_state; pxm_pxmala_accept: log alpha from the four reductions, uniform from the step's Philox stream, decision,
  * traces (acceptances int8[i], deltas[i+1]) and -- tune != 0 -- the new step size, all written on the device;
@@ -166,8 +167,11 @@ int pxm_reduce_dpar(int kind, const void* a, const void* b, const void* c, const
                     void* stream);
 int pxm_pxmala_accept(double* d_state, const void* d_s1, const void* d_s2, const void* d_L2p, const void* d_priorp,
                       double mu, double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
-                      unsigned int stream_id, signed char* d_acc_trace, double* d_delta_trace, void* stream);
-int pxm_select_if(const double* d_flag, void* const* d_dst, const void* const* d_src, const long long* counts,
+                      unsigned int stream_id, signed char* d_acc_trace /* [nchains][trace_stride] */,
+                      double* d_delta_trace /* [nchains][trace_stride + 1] */, long long trace_stride, int nchains,
+                      void* stream);
+int pxm_select_if(const double* d_flag /* chain c: d_flag[flag_stride c] */, long long flag_stride, long long nchains,
+                  void* const* d_dst, const void* const* d_src, const long long* counts /* elements per chain */,
                   int narrays, void* stream);
 /* pxm_resid_invcov: invcov @ (preds - data) of ForwardOperator._gradg_analysis
  * (pxmcmc/forward.py:66-69) for a diagonal, possibly complex, inverse covariance. */

@@ -68,8 +68,8 @@ SIGNATURES = {
     "pxm_philox_normal": (_i, [_vp, _ll, _ll, _u64, _u64, _vp, _u32, _vp]),
     "pxm_myula_update_dpar": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _ll, _ll, _vp, _i, _u64, _u64, _u32, _vp]),
     "pxm_reduce_dpar": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _ll, _ll, _vp, _vp, _vp]),
-    "pxm_pxmala_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _i, _ll, _u64, _u64, _u32, _vp, _vp, _vp]),
-    "pxm_select_if": (_i, [_vp, _vp, _vp, _vp, _i, _vp]),
+    "pxm_pxmala_accept": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _i, _ll, _u64, _u64, _u32, _vp, _vp, _ll, _i, _vp]),
+    "pxm_select_if": (_i, [_vp, _ll, _ll, _vp, _vp, _vp, _i, _vp]),
     "pxm_resid_invcov": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _vp]),
     "pxm_reduce_scratch_elems": (_i, []),
     "pxm_reduce": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _d, _d, _ll, _ll, _vp, _vp, _vp]),

@@ -112,17 +112,28 @@ struct MyulaArgs {
   int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex)
   unsigned long long seed, step;
   const unsigned long long* step_ptr;  // may be null; otherwise the step is read from the device (CUDA-graph replays)
-  const double* dpar;  // may be null; otherwise {delta, 1 - delta/lmda, delta/lmda, sqrt(2 delta)} live on the device (PxMALA's tuned step)
+  const double* dpar;  // may be null; otherwise chain c reads {delta, 1 - delta/lmda, delta/lmda, sqrt(2 delta)} from
+                       // dpar[16 c ..] (PxMALA tunes the step of every chain on the device)
   unsigned int stream0;
 };
+constexpr int PXM_STATE_DOUBLES = 16;  // per-chain state block of the device-resident PxMALA loop (k_pxmala_accept)
 __device__ __forceinline__ void myula_device_params(MyulaArgs& p) {
   if (p.step_ptr) p.step = *p.step_ptr;
+  if (p.dpar && p.step == 0) p.step = (unsigned long long)p.dpar[14];  // CUDA-graph replays: the step lives in the state block
+}
+__device__ __forceinline__ void myula_chain_params(const MyulaArgs& p, size_t chain, double* a, double* b, double* delta,
+                                                   double* sq2d) {
   if (p.dpar) {
-    p.delta = p.dpar[0];
-    p.a = p.dpar[1];
-    p.b = p.dpar[2];
-    p.sq2d = p.dpar[3];
-    if (p.step == 0) p.step = (unsigned long long)p.dpar[14];  // CUDA-graph replays: the step lives in the state block
+    const double* d = p.dpar + chain * PXM_STATE_DOUBLES;
+    *delta = d[0];
+    *a = d[1];
+    *b = d[2];
+    *sq2d = d[3];
+  } else {
+    *a = p.a;
+    *b = p.b;
+    *delta = p.delta;
+    *sq2d = p.sq2d;
   }
 }
 
@@ -157,9 +168,11 @@ __global__ void k_myula_update(MyulaArgs p) {
       }
     }
     // same association order as the reference expression
+    double ca, cb, cd, cs;
+    myula_chain_params(p, i / p.n, &ca, &cb, &cd, &cs);
     cplx o;
-    o.x = ((p.a * x.x + p.b * px.x) - p.delta * g.x) + p.sq2d * wr;
-    o.y = ((p.a * x.y + p.b * px.y) - p.delta * g.y) + p.sq2d * wi;
+    o.x = ((ca * x.x + cb * px.x) - cd * g.x) + cs * wr;
+    o.y = ((ca * x.y + cb * px.y) - cd * g.y) + cs * wi;
     p.Xout[i] = o;
   }
 }
@@ -176,6 +189,8 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
     const size_t chain = q / npairs, pr = q - chain * npairs;
     double z[2];
     philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, pr, &z[0], &z[1]);
+    double ca, cb, cd, cs;
+    myula_chain_params(p, chain, &ca, &cb, &cd, &cs);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const size_t e = 2 * pr + h;
@@ -186,8 +201,8 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
       if (p.prox_out) p.prox_out[i] = px;
       const cplx g = p.gradg[i];
       cplx o;
-      o.x = ((p.a * x.x + p.b * px.x) - p.delta * g.x) + p.sq2d * z[h];
-      o.y = ((p.a * x.y + p.b * px.y) - p.delta * g.y) + p.sq2d * 0.0;
+      o.x = ((ca * x.x + cb * px.x) - cd * g.x) + cs * z[h];
+      o.y = ((ca * x.y + cb * px.y) - cd * g.y) + cs * 0.0;
       p.Xout[i] = o;
     }
   }
@@ -250,8 +265,8 @@ __device__ __forceinline__ cplx block_sum(cplx v) {
 }
 
 __global__ void k_reduce_stage1(ReduceArgs p) {
-  if (p.dpar) p.delta = p.dpar[0];
   const size_t chain = blockIdx.y;
+  if (p.dpar) p.delta = p.dpar[chain * PXM_STATE_DOUBLES];
   const size_t off = chain * p.n;
   cplx acc = make_double2(0.0, 0.0);
   for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < p.n; e += (size_t)gridDim.x * blockDim.x) {
@@ -515,12 +530,22 @@ struct AcceptArgs {
   long long i;         // iteration index
   unsigned long long seed, step;
   unsigned int stream;
-  signed char* acc_trace;   // [>= i+1]
-  double* delta_trace;      // [>= i+2]; entry 0 = initial delta
+  signed char* acc_trace;   // [nchains][trace_stride], entries 0..i
+  double* delta_trace;      // [nchains][trace_stride + 1], entries 0..i+1; entry 0 = initial delta
+  long long trace_stride;
+  int nchains;
 };
 __global__ void k_pxmala_accept(AcceptArgs p) {
-  if (threadIdx.x || blockIdx.x) return;
-  double* S = p.S;
+  const int chain = blockIdx.x * blockDim.x + threadIdx.x;  // one thread per chain
+  if (chain >= p.nchains) return;
+  double* S = p.S + (size_t)chain * PXM_STATE_DOUBLES;
+  p.s1 += chain;
+  p.s2 += chain;
+  p.L2p += chain;
+  p.priorp += chain;
+  p.stream += (unsigned int)chain;
+  p.acc_trace += (size_t)chain * p.trace_stride;
+  p.delta_trace += (size_t)chain * (p.trace_stride + 1);
   const bool counters_on_device = p.i < 0;
   if (counters_on_device) {
     p.i = (long long)S[13];
@@ -573,17 +598,20 @@ __global__ void k_pxmala_accept(AcceptArgs p) {
 }
 // the accepted proposal becomes the current state: up to four arrays copied when S[9] != 0
 struct SelectArgs {
-  const double* flag;
+  const double* flag;   // chain c: flag[flag_stride c]
+  size_t flag_stride;
+  size_t nchains;
   cplx* dst[4];
   const cplx* src[4];
-  size_t n[4];
+  size_t n[4];          // elements per chain
 };
 __global__ void k_select(SelectArgs p) {
-  if (*p.flag == 0.0) return;
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < p.n[a]; i += (size_t)gridDim.x * blockDim.x)
-      p.dst[a][i] = p.src[a][i];
+  for (int a = 0; a < 4; ++a) {
+    const size_t tot = p.n[a] * p.nchains;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x)
+      if (p.flag[(i / p.n[a]) * p.flag_stride] != 0.0) p.dst[a][i] = p.src[a][i];
+  }
 }
 
 // standard normals from the Philox stream (seed, stream0 + chain, step): element e of a chain is normal (e & 1) of
@@ -829,8 +857,11 @@ int pxm_launch_quantile_columns(const double* chain, long long nsamples, long lo
 
 int pxm_launch_pxmala_accept(double* S, const void* s1, const void* s2, const void* L2p, const void* priorp, double mu,
                              double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
-                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, cudaStream_t st) {
+                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, long long trace_stride,
+                             int nchains, cudaStream_t st) {
   AcceptArgs p;
+  p.trace_stride = trace_stride;
+  p.nchains = nchains;
   p.S = S;
   p.s1 = (const cplx*)s1;
   p.s2 = (const cplx*)s2;
@@ -845,15 +876,17 @@ int pxm_launch_pxmala_accept(double* S, const void* s1, const void* s2, const vo
   p.stream = stream_id;
   p.acc_trace = acc_trace;
   p.delta_trace = delta_trace;
-  k_pxmala_accept<<<1, 32, 0, st>>>(p);
+  k_pxmala_accept<<<(nchains + 63) / 64, 64, 0, st>>>(p);
   PXM_LAUNCHED();
   return PXM_OK;
 }
 
-int pxm_launch_select(const double* flag, void* const* dst, const void* const* src, const size_t* counts, int narrays,
-                      cudaStream_t st) {
+int pxm_launch_select(const double* flag, size_t flag_stride, size_t nchains, void* const* dst, const void* const* src,
+                      const size_t* counts, int narrays, cudaStream_t st) {
   SelectArgs p;
   p.flag = flag;
+  p.flag_stride = flag_stride;
+  p.nchains = nchains;
   size_t mx = 0;
   for (int a = 0; a < 4; ++a) {
     p.dst[a] = a < narrays ? (cplx*)dst[a] : nullptr;
@@ -862,7 +895,7 @@ int pxm_launch_select(const double* flag, void* const* dst, const void* const* s
     mx = p.n[a] > mx ? p.n[a] : mx;
   }
   if (!mx) return PXM_OK;
-  k_select<<<grid_for(mx), 256, 0, st>>>(p);
+  k_select<<<grid_for(mx * nchains), 256, 0, st>>>(p);
   PXM_LAUNCHED();
   return PXM_OK;
 }

@@ -1232,19 +1232,21 @@ int pxm_reduce_dpar(int kind, const void* a, const void* b, const void* c, const
 }
 int pxm_pxmala_accept(double* d_state, const void* d_s1, const void* d_s2, const void* d_L2p, const void* d_priorp,
                       double mu, double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
-                      unsigned int stream_id, signed char* d_acc_trace, double* d_delta_trace, void* stream) {
+                      unsigned int stream_id, signed char* d_acc_trace, double* d_delta_trace, long long trace_stride,
+                      int nchains, void* stream) {
   ProfScope _ps(2, (cudaStream_t)stream);
-  PXM_REQUIRE(d_state && d_s1 && d_s2 && d_L2p && d_priorp && d_acc_trace && d_delta_trace, "pxmala_accept: null argument");
+  PXM_REQUIRE(d_state && d_s1 && d_s2 && d_L2p && d_priorp && d_acc_trace && d_delta_trace && nchains >= 1 && trace_stride >= 1,
+              "pxmala_accept: bad argument");
   return pxm_launch_pxmala_accept(d_state, d_s1, d_s2, d_L2p, d_priorp, mu, lmda, tune, i, seed, step, stream_id,
-                                  d_acc_trace, d_delta_trace, (cudaStream_t)stream);
+                                  d_acc_trace, d_delta_trace, trace_stride, nchains, (cudaStream_t)stream);
 }
-int pxm_select_if(const double* d_flag, void* const* d_dst, const void* const* d_src, const long long* counts,
-                  int narrays, void* stream) {
+int pxm_select_if(const double* d_flag, long long flag_stride, long long nchains, void* const* d_dst,
+                  const void* const* d_src, const long long* counts, int narrays, void* stream) {
   ProfScope _ps(2, (cudaStream_t)stream);
-  PXM_REQUIRE(d_flag != nullptr && narrays >= 1 && narrays <= 4, "select_if: 1 to 4 arrays");
+  PXM_REQUIRE(d_flag != nullptr && narrays >= 1 && narrays <= 4 && nchains >= 1 && flag_stride >= 0, "select_if: 1 to 4 arrays");
   size_t n[4] = {0, 0, 0, 0};
   for (int a = 0; a < narrays; ++a) n[a] = (size_t)counts[a];
-  return pxm_launch_select(d_flag, d_dst, d_src, n, narrays, (cudaStream_t)stream);
+  return pxm_launch_select(d_flag, (size_t)flag_stride, (size_t)nchains, d_dst, d_src, n, narrays, (cudaStream_t)stream);
 }
 
 int pxm_philox_normal(double* d_out, long long n, long long nchains, unsigned long long seed, unsigned long long step,

@@ -119,11 +119,12 @@ int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, con
                       const double* d_par = nullptr);
 int pxm_launch_pxmala_accept(double* S, const void* s1, const void* s2, const void* L2p, const void* priorp, double mu,
                              double lmda, int tune, long long i, unsigned long long seed, unsigned long long step,
-                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, cudaStream_t st);
+                             unsigned int stream_id, signed char* acc_trace, double* delta_trace, long long trace_stride,
+                             int nchains, cudaStream_t st);
 int pxm_launch_philox_normal(double* out, size_t n, size_t nchains, unsigned long long seed, unsigned long long step,
                              const unsigned long long* d_step, unsigned int stream0, cudaStream_t st);
-int pxm_launch_select(const double* flag, void* const* dst, const void* const* src, const size_t* counts, int narrays,
-                      cudaStream_t st);
+int pxm_launch_select(const double* flag, size_t flag_stride, size_t nchains, void* const* dst, const void* const* src,
+                      const size_t* counts, int narrays, cudaStream_t st);
 int pxm_launch_lincomb(int nx, const void* const* xs, const double* as, const double* z, double cz, double c0,
                        void* out, size_t total, cudaStream_t st);
 int pxm_launch_gradlogpi(const void* X, const void* prox, const double* Tv, double Ts, const void* gradg, double lmda,

@@ -248,17 +248,21 @@ def reduce_dpar_dev(a, b, c, d, dpar, lmda):
 
 
 def pxmala_accept_dev(state, s1, s2, L2p, priorp, mu, lmda, tune, i, seed, step, stream_id, acc_trace, delta_trace):
+    """state [nchains, 16]; acc_trace int8 [nchains, cap]; delta_trace float64 [nchains, cap + 1]"""
+    nch, cap = acc_trace.shape
     check(lib.pxm_pxmala_accept(ptr(state), ptr(s1), ptr(s2), ptr(L2p), ptr(priorp), float(mu), float(lmda), int(bool(tune)),
-                                int(i), int(seed), int(step), int(stream_id), ptr(acc_trace), ptr(delta_trace), stream_ptr()))
+                                int(i), int(seed), int(step), int(stream_id), ptr(acc_trace), ptr(delta_trace), cap, nch,
+                                stream_ptr()))
 
 
-def select_if_dev(flag, dsts, srcs):
-    """dst_k <- src_k (complex tensors of equal sizes) when the device double *flag is non-zero"""
+def select_if_dev(state, dsts, srcs):
+    """dst_k[c] <- src_k[c] ([nchains, n_k] complex tensors) for the chains whose state block says `accepted`"""
     k = len(dsts)
+    nch = state.shape[0]
     d = (C.c_void_p * 4)(*([t.data_ptr() for t in dsts] + [0] * (4 - k)))
     sr = (C.c_void_p * 4)(*([t.data_ptr() for t in srcs] + [0] * (4 - k)))
-    cnt = (C.c_longlong * 4)(*([t.numel() for t in dsts] + [0] * (4 - k)))
-    check(lib.pxm_select_if(ptr(flag), d, sr, cnt, k, stream_ptr()))
+    cnt = (C.c_longlong * 4)(*([t.numel() // nch for t in dsts] + [0] * (4 - k)))
+    check(lib.pxm_select_if(C.c_void_p(state.data_ptr() + 9 * 8), state.shape[1], nch, d, sr, cnt, k, stream_ptr()))
 
 
 def philox_normal_dev(nchains, n, seed, step=0, stream0=0, dstep=None):

@@ -461,9 +461,10 @@ class PxMALA(MYULA):
 
     def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), tune_delta=True, **kw):
         super().__init__(forward, prox, mcmcparams, **kw)
-        if self.nchains != 1:
-            raise NotImplementedError("PxMALA runs one chain per sampler object")
         self.tune_delta = tune_delta
+        if self.nchains != 1 and not self._device_resident():
+            raise NotImplementedError("batched PxMALA chains need the device-resident loop: noise='device', a native "
+                                      "operator with a diagonal covariance and an L1 prior")
 
     def _logtrans_dev(self, X1, X2, proxf, gradg):
         s = complex(D.to_host(D.reduce_dev(2, X1, b=X2, c=proxf, d=gradg, delta=self.delta, lmda=self.lmda))[0])
@@ -477,7 +478,7 @@ class PxMALA(MYULA):
     def _device_resident(self):
         """True when an iteration can run without a host round trip: Philox noise, a native operator with a
         diagonal covariance and a native L1 prior, one chain"""
-        return (self.noise == "device" and self.nchains == 1 and getattr(self.forward, "_pxm_native", False)
+        return (self.noise == "device" and getattr(self.forward, "_pxm_native", False)
                 and getattr(self.forward, "_diag", None) is not None and isinstance(self.prior, L1)
                 and getattr(self.prior, "_pxm_native", False) and getattr(self.forward, "_pxm_allreduce", None) is None)
 
@@ -486,24 +487,25 @@ class PxMALA(MYULA):
         traces live in device memory, the accepted proposal is copied over the state by a predicated kernel, and the
         host reads the decision only on the thinning grid (where the reference stores accepted samples)."""
         dv = D.dev()
+        nch = self.nchains
         X_curr, curr_preds = self._initial_sample(start_point)
         X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
         gradg_curr = D.to_dev_c(self._gradg_dev(curr_preds)).clone()
         proxf_curr = D.to_dev_c(self._proxf_dev(X_curr)).clone()
         lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
-        S = torch.zeros(16, dtype=D.FDT)
-        S[0], S[1], S[2], S[3] = self.delta, 1 - self.delta / self.lmda, self.delta / self.lmda, np.sqrt(2 * self.delta)
-        S[4], S[5], S[6], S[7], S[8] = np.real(lp[0]), np.imag(lp[0]), np.real(l2[0]), np.imag(l2[0]), pr[0]
-        S = S.to(dv)
+        S = np.zeros((nch, 16))
+        S[:, 0], S[:, 1], S[:, 2], S[:, 3] = self.delta, 1 - self.delta / self.lmda, self.delta / self.lmda, np.sqrt(2 * self.delta)
+        S[:, 4], S[:, 5], S[:, 6], S[:, 7], S[:, 8] = np.real(lp), np.imag(lp), np.real(l2), np.imag(l2), pr
+        S = torch.from_numpy(S).to(dv)
         cap = 1 << 16
-        acc = torch.zeros(cap, dtype=torch.int8, device=dv)
-        dl = torch.zeros(cap + 1, dtype=D.FDT, device=dv)
-        dl[0] = self.delta
+        acc = torch.zeros((nch, cap), dtype=torch.int8, device=dv)
+        dl = torch.zeros((nch, cap + 1), dtype=D.FDT, device=dv)
+        dl[:, 0] = self.delta
         mode = 3 if self.complex else 2
         cur = [X_curr, curr_preds, gradg_curr, proxf_curr]
 
         def body(i_arg, step_arg):
-            """one iteration; (i_arg, step_arg) = (-1, 0): iteration index and Philox step come from S[13], S[14]"""
+            """one iteration; (i_arg, step_arg) = (-1, 0): iteration index and Philox step come from S[:, 13], S[:, 14]"""
             X_prop = D.myula_update_dpar_dev(cur[0], cur[3], cur[2], None, 0.0, S, mode, self.seed, step_arg, self.stream0)
             prop_preds = D.to_dev_c(self._forward_dev(X_prop))
             gradg_prop = D.to_dev_c(self._gradg_dev(prop_preds))
@@ -514,32 +516,56 @@ class PxMALA(MYULA):
             # priorp is the real view of a complex reduction result: same address, the kernel reads its real part
             D.pxmala_accept_dev(S, s1, s2, L2p, priorp, self.mu, self.lmda, self.tune_delta, i_arg, self.seed, step_arg,
                                 self.stream0, acc, dl)
-            D.select_if_dev(S[9:], cur, [X_prop, prop_preds, gradg_prop, proxf_prop])
+            D.select_if_dev(S, cur, [X_prop, prop_preds, gradg_prop, proxf_prop])
 
-        # One CUDA graph per iteration (~30 launches otherwise issued one by one from Python): warm up eagerly on a
-        # side stream as CUDA graphs require (these ARE the first iterations of the chain), then capture with the
-        # counters in the state block
+        # One CUDA graph per iteration (~30 launches otherwise issued one by one from Python): the first iterations
+        # run eagerly (they warm up tables, lazy uploads and allocator pools, and ARE iterations of the chain), then the
+        # iteration is captured with its counters in the state blocks
         graph = None
-        i = j = 0
+        i = 0
+        js = np.zeros(nch, dtype=np.int64)  # tracked samples per chain (accepted proposals on the thinning grid)
+
+        def put(arr, c, j, val):
+            val = np.asarray(val)
+            if not np.iscomplexobj(arr):
+                val = val.real
+            if nch > 1:
+                arr[c, j] = val
+            else:
+                arr[j] = val
 
         def after(i):
-            nonlocal j
             on_grid = i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
             verbose = self.verbosity > 0 and (i + 1) % self.verbosity == 0
             if on_grid or verbose:
                 st = S.cpu().numpy()  # the only host synchronisation
-                if on_grid and st[9] != 0.0:
-                    self._tracking(j, cur[0], cur[1], [complex(st[4], st[5])], [complex(st[6], st[7])], [st[8]])
-                    j += 1
+                take = [c for c in range(nch) if on_grid and st[c, 9] != 0.0 and js[c] < self.nsamples]
+                if take:
+                    Xh = D.to_host(cur[0]) if hasattr(self, "chain") else None
+                    Ph = D.to_host(cur[1]) if hasattr(self, "preds") else None
+                    for c in take:
+                        j = int(js[c])
+                        if hasattr(self, "logPi"):
+                            put(self.logPi, c, j, complex(st[c, 4], st[c, 5]))
+                        if hasattr(self, "L2s"):
+                            put(self.L2s, c, j, complex(st[c, 6], st[c, 7]))
+                        if hasattr(self, "priors"):
+                            put(self.priors, c, j, st[c, 8])
+                        if Ph is not None:
+                            put(self.preds, c, j, Ph[c])
+                        if Xh is not None:
+                            put(self.chain, c, j, Xh[c])
+                        js[c] += 1
                 if verbose:
-                    self._print_progress(j - 1, st[4], L2=st[6], prior=st[8], acceptanceRate=float(acc[: i + 1].double().mean().item()))
+                    self._print_progress(int(js[0]) - 1, st[0, 4], L2=st[0, 6], prior=st[0, 8],
+                                         acceptanceRate=float(acc[:, : i + 1].double().mean().item()))
 
-        while j < self.nsamples:
+        while js.min() < self.nsamples:
             if i + 1 >= cap:
                 raise RuntimeError(f"PxMALA: more than {cap} iterations in one run(); split the run")
             self._step_counter += 1
             if graph is None and i >= 2 and self.use_graph:
-                S[13], S[14] = float(i), float(self._step_counter)
+                S[:, 13], S[:, 14] = float(i), float(self._step_counter)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
                 graph = torch.cuda.CUDAGraph()
@@ -554,10 +580,14 @@ class PxMALA(MYULA):
             after(i)
             i += 1
         X_curr, curr_preds = cur[0], cur[1]
-        self.acceptance_trace = [int(v) for v in acc[:i].cpu().numpy()]
-        self.deltas_trace = [float(v) for v in dl[: (i + 1 if self.tune_delta else 1)].cpu().numpy()]
-        self.delta = float(S[0].item())
-        self._final_state = (X_curr, curr_preds)
+        at = acc[:, :i].cpu().numpy().astype(int)
+        dt = dl[:, : (i + 1 if self.tune_delta else 1)].cpu().numpy()
+        # one chain: the reference's flat lists; several chains: arrays with a leading chain axis
+        self.acceptance_trace = [int(v) for v in at[0]] if nch == 1 else at
+        self.deltas_trace = [float(v) for v in dt[0]] if nch == 1 else dt
+        self.delta = float(S[0, 0].item())
+        self.deltas = S[:, 0].cpu().numpy()
+        self._final_state = (X_curr.clone(), curr_preds.clone())
         print("\nDONE")
 
     def run(self, start_point=None):

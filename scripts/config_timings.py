@@ -87,6 +87,25 @@ if "2" in which:
         out[f"config2 PxMALA L=256 B=1.5 analysis ({tag}, ngap=100)"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "iterations": nit, "acceptance": float(np.mean(m.acceptance_trace))}
     print(out, flush=True)
 
+if "2b" in which:
+    # 64 PxMALA chains as one batch (analysis prior, L=256): the device-resident loop with per-chain step sizes
+    L, B, nch = 256, 1.5, 64
+    op = SphericalWaveletTransformOperator(data_map(L), 0.1, "analysis", L, B, 2, nchains=nch)
+    prm = PxMCMCParams(delta=1e-7, lmda=1e-6, mu=1.0, verbosity=0, nsamples=3, nburn=0, ngap=100, track=["logposterior"])
+    reg = L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, 1e-6)
+    m = PxMALA(op, reg, prm, tune_delta=True, noise="device", seed=3, nchains=nch)
+    m.run(np.zeros(op.nparams))  # plans, tables, graph capture
+    prm.nsamples = 11
+    m = PxMALA(op, reg, prm, tune_delta=True, noise="device", seed=3, nchains=nch)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.run(np.zeros(op.nparams))
+    torch.cuda.synchronize()
+    nit = m.acceptance_trace.shape[1]
+    dt = (time.perf_counter() - t0) / nit
+    out["64 PxMALA chains L=256 B=1.5 analysis (device-resident loop)"] = {"ms_per_step": dt * 1e3, "chain_iterations_per_s": nch / dt, "iterations": nit, "acceptance": float(m.acceptance_trace.mean())}
+    print(out, flush=True)
+
 if "3" in which:
     L, B, s = 128, 2, 10
     rng = np.random.default_rng(7)

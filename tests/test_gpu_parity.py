@@ -777,3 +777,35 @@ def test_skrock_device_noise_graph_replay_equals_eager_steps(px):
     m3, _ = make()
     m3.run(D.to_host(X0[0]).real)
     assert np.isfinite(m3.logPi).all() and m3.chain.shape == (3, op.nparams)
+
+
+def test_pxmala_batched_chains_equal_single_chain_samplers(px):
+    """several PxMALA chains as one batch (per-chain step size, accept flag and uniform on the device): chain c is the
+    chain a single-chain sampler with Philox stream stream0 + c produces"""
+    L, B, J, nch = 16, 2.0, 2, 3
+    rng = np.random.default_rng(43)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    p = px.mcmc.PxMCMCParams(nsamples=4, nburn=3, ngap=2, delta=2e-3, lmda=1e-2, mu=2.0, verbosity=0,
+                             track=["logposterior", "L2", "prior", "chain"])
+    start = np.random.default_rng(3).laplace(size=L * (2 * L - 1)) * 0.1
+
+    def sampler(nchains, stream0):
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.05, "analysis", L, B, J, nchains=nchains)
+        reg = px.prior.L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu)
+        return px.mcmc.PxMALA(op, reg, p, tune_delta=True, noise="device", seed=5, stream0=stream0, nchains=nchains)
+
+    batch = sampler(nch, 10)
+    batch.run(start)
+    assert batch.chain.shape == (nch, 4, start.size) and batch.acceptance_trace.shape[0] == nch
+    traces = set()
+    for c in range(nch):
+        one = sampler(1, 10 + c)
+        one.run(start)
+        n = len(one.acceptance_trace)
+        assert list(batch.acceptance_trace[c][:n]) == one.acceptance_trace
+        assert np.allclose(batch.deltas_trace[c][: n + 1], one.deltas_trace, rtol=1e-13, atol=0)
+        assert rel_l2(batch.chain[c], one.chain) < TOL and rel_l2(batch.logPi[c], one.logPi) < TOL
+        traces.add(tuple(one.acceptance_trace[:6]))
+    assert not np.allclose(batch.chain[0], batch.chain[1])
+    with pytest.raises(NotImplementedError):
+        px.mcmc.PxMALA(batch.forward, batch.prior, p, nchains=2)  # host-noise parity mode is single-chain
