@@ -234,6 +234,42 @@ class PxMCMC:
         if hasattr(self, "chain"):
             put(self.chain, D.to_host(X_curr) if D.is_dev(X_curr) else X_curr)
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    _TRACKED = ("logPi", "L2s", "priors", "preds", "chain")
+
+    def save_checkpoint(self, path, i, j, X_curr, curr_preds):
+        """Everything `run(resume=path)` needs to continue the chain exactly where it stands after iteration
+        i - 1: state and predictions, loop counters, the Philox step, numpy's global RNG state (host-noise mode)
+        and the tracked arrays filled so far.  One .npz; written to a temporary name and renamed."""
+        import os
+
+        d = {"i": i, "j": j, "step_counter": self._step_counter, "X": D.to_host(X_curr), "P": D.to_host(curr_preds),
+             "nchains": self.nchains, "noise": self.noise, "delta": self.delta}
+        for name in self._TRACKED:
+            if hasattr(self, name):
+                d["track_" + name] = getattr(self, name)
+        kind, keys, pos, has_gauss, cached = np.random.get_state()
+        d.update(rng_keys=keys, rng_pos=pos, rng_has_gauss=has_gauss, rng_cached=cached)
+        tmp = path + ".tmp.npz"
+        np.savez(tmp, **d)
+        os.replace(tmp, path if path.endswith(".npz") else path + ".npz")
+
+    def load_checkpoint(self, path):
+        """-> (i, j, X, preds) as device tensors; restores the tracked arrays, the Philox step and numpy's RNG state"""
+        with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
+            if int(f["nchains"]) != self.nchains or str(f["noise"]) != self.noise:
+                raise ValueError("checkpoint was written by a sampler with another chain count / noise mode")
+            for name in self._TRACKED:
+                if "track_" + name in f.files and hasattr(self, name):
+                    arr = f["track_" + name]
+                    if arr.shape != getattr(self, name).shape:
+                        raise ValueError(f"checkpoint array {name} has shape {arr.shape}, expected {getattr(self, name).shape}")
+                    getattr(self, name)[...] = arr
+            self._step_counter = int(f["step_counter"])
+            self.delta = float(f["delta"])
+            np.random.set_state(("MT19937", f["rng_keys"], int(f["rng_pos"]), int(f["rng_has_gauss"]), float(f["rng_cached"])))
+            return int(f["i"]), int(f["j"]), self._state(f["X"]), self._state(f["P"])
+
     def _on_grid(self, i):
         return i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
 
@@ -279,11 +315,16 @@ class MYULA(PxMCMC):
                                      stream0=self.stream0 + (off or 0))
         return out
 
-    def run(self, start_point=None):
-        """the loop of pxmcmc/mcmc.py:150-183"""
+    def run(self, start_point=None, *, checkpoint=None, checkpoint_every=0, resume=None):
+        """the loop of pxmcmc/mcmc.py:150-183.  Extensions (keyword-only): `checkpoint` = file written every
+        `checkpoint_every` iterations (and at the end); `resume` = such a file: the chain continues exactly as if it
+        had never stopped (same Philox steps / same numpy RNG stream, tracked arrays restored)."""
         i = 0
         j = 0
-        X_curr, curr_preds = self._initial_sample(start_point)
+        if resume is not None:
+            i, j, X_curr, curr_preds = self.load_checkpoint(resume)
+        else:
+            X_curr, curr_preds = self._initial_sample(start_point)
         # Philox noise and a native operator: the iteration is replayed as one CUDA graph (small bandlimits are
         # launch-latency bound: 85 -> 63 us per iteration at L = 32); the noise stream is the eager one
         graphed = None
@@ -307,6 +348,10 @@ class MYULA(PxMCMC):
                 if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
                     print("Burning in...")
             i += 1
+            if checkpoint is not None and checkpoint_every and i % checkpoint_every == 0:
+                self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
+        if checkpoint is not None:
+            self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
         if graphed is not None:
             X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
             graphed.release()

@@ -809,3 +809,36 @@ def test_pxmala_batched_chains_equal_single_chain_samplers(px):
     assert not np.allclose(batch.chain[0], batch.chain[1])
     with pytest.raises(NotImplementedError):
         px.mcmc.PxMALA(batch.forward, batch.prior, p, nchains=2)  # host-noise parity mode is single-chain
+
+
+@pytest.mark.parametrize("noise", ["host", "device"])
+def test_myula_checkpoint_resume_continues_the_same_chain(px, noise, tmp_path):
+    """a run interrupted after a checkpoint and resumed by a NEW sampler object gives the chain of the uninterrupted
+    run bit for bit: Philox steps (device noise, CUDA-graph replay) or numpy's global RNG stream (host noise)"""
+    L, B, J = 12, 2.0, 2
+    rng = np.random.default_rng(9)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    track = ["logposterior", "L2", "prior", "chain", "predictions"]
+
+    def sampler(nsamples):
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.2, "synthesis", L, B, J)
+        p = px.mcmc.PxMCMCParams(nsamples=nsamples, nburn=2, ngap=3, delta=1e-5, lmda=2e-5, mu=1.0, verbosity=0, track=track)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda, L=L, B=B, J_min=J)
+        return px.mcmc.MYULA(op, reg, p, noise=noise, seed=21, stream0=4)
+
+    start = np.random.default_rng(1).laplace(size=sampler(1).forward.nparams)
+    np.random.seed(77)
+    full = sampler(6)
+    full.run(start)
+    # the same run, stopped after 3 samples (checkpoint at the end of the shorter run) ...
+    np.random.seed(77)
+    first = sampler(6)
+    first.nsamples = 3  # stop early; the tracked arrays keep their full length
+    ck = str(tmp_path / "ck.npz")
+    first.run(start, checkpoint=ck, checkpoint_every=4)
+    # ... and continued by a new object from the file alone (the global RNG is clobbered in between)
+    np.random.seed(12345)
+    second = sampler(6)
+    second.run(resume=ck)
+    assert np.array_equal(second.chain, full.chain) and np.array_equal(second.logPi, full.logPi)
+    assert np.array_equal(second.preds, full.preds) and np.array_equal(second.L2s, full.L2s)
