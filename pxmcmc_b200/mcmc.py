@@ -745,7 +745,9 @@ class SKROCK(PxMCMC):
         i = 0
         j = 0
         X_curr, curr_preds = self._initial_sample(start_point)
-        graphed = self.capture(X_curr) if (self.noise == "device" and not self.complex) else None
+        # a CUDA graph needs every operation of the step on the device: native operator and prior only
+        graphed = self.capture(X_curr) if (self.noise == "device" and not self.complex and self._native()
+                                           and getattr(self.forward, "_pxm_allreduce", None) is None) else None
         while j < self.nsamples:
             if graphed is not None:  # the whole step (s gradient evaluations + predictions) as one CUDA graph
                 graphed.step()
