@@ -187,22 +187,35 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
   myula_device_params(p);
   for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
     const size_t chain = q / npairs, pr = q - chain * npairs;
+    const size_t e0 = 2 * pr, i0 = chain * p.n + e0;
+    const bool two = e0 + 1 < p.n;
+    // every input of the pair is requested before any arithmetic: one exposed DRAM latency per iteration, not three
+    cplx x[2], g[2], px[2];
+    double T[2];
+    x[0] = p.X[i0];
+    g[0] = p.gradg[i0];
+    x[1] = two ? p.X[i0 + 1] : make_double2(0.0, 0.0);
+    g[1] = two ? p.gradg[i0 + 1] : make_double2(0.0, 0.0);
+    if (p.prox) {
+      px[0] = p.prox[i0];
+      px[1] = two ? p.prox[i0 + 1] : make_double2(0.0, 0.0);
+    } else {
+      T[0] = p.Tv ? p.Tv[e0] : p.Ts;
+      T[1] = (p.Tv && two) ? p.Tv[e0 + 1] : p.Ts;
+    }
     double z[2];
     philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, pr, &z[0], &z[1]);
     double ca, cb, cd, cs;
     myula_chain_params(p, chain, &ca, &cb, &cd, &cs);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const size_t e = 2 * pr + h;
-      if (e >= p.n) break;
-      const size_t i = chain * p.n + e;
-      const cplx x = p.X[i];
-      const cplx px = p.prox ? p.prox[i] : soft_c(x, p.Tv ? p.Tv[e] : p.Ts);
-      if (p.prox_out) p.prox_out[i] = px;
-      const cplx g = p.gradg[i];
+      if (h == 1 && !two) break;
+      const size_t i = i0 + h;
+      if (!p.prox) px[h] = soft_c(x[h], T[h]);
+      if (p.prox_out) p.prox_out[i] = px[h];
       cplx o;
-      o.x = ((ca * x.x + cb * px.x) - cd * g.x) + cs * z[h];
-      o.y = ((ca * x.y + cb * px.y) - cd * g.y) + cs * 0.0;
+      o.x = ((ca * x[h].x + cb * px[h].x) - cd * g[h].x) + cs * z[h];
+      o.y = ((ca * x[h].y + cb * px[h].y) - cd * g[h].y) + cs * 0.0;
       p.Xout[i] = o;
     }
   }
