@@ -842,3 +842,31 @@ def test_myula_checkpoint_resume_continues_the_same_chain(px, noise, tmp_path):
     second.run(resume=ck)
     assert np.array_equal(second.chain, full.chain) and np.array_equal(second.logPi, full.logPi)
     assert np.array_equal(second.preds, full.preds) and np.array_equal(second.L2s, full.L2s)
+
+
+def test_skrock_batched_chains_equal_single_chain_steps(px):
+    """SKROCK steps of a batch of chains (Philox normals, stream stream0 + c per chain) = the single-chain steps"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J, s_, nch = 12, 2.0, 2, 3, 3
+    rng = np.random.default_rng(18)
+    npix = L * (2 * L - 1)
+    A = sparse.random(30, npix, density=0.05, random_state=4, format="csr")
+    y = rng.standard_normal(30)
+    prm = px.mcmc.PxMCMCParams(delta=1e-7, lmda=5e-8, mu=1.0, s=s_, verbosity=0, nsamples=1)
+
+    def make(nchains, stream0):
+        op = px.forward.PathIntegralOperator(A, y, 0.1, "synthesis", L, B, J, nchains=nchains)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 5e-8, L=L, B=B, J_min=J)
+        return px.mcmc.SKROCK(op, reg, prm, noise="device", seed=2, stream0=stream0, nchains=nchains), op
+
+    mb, op = make(nch, 20)
+    X0 = D.to_dev_c(rng.laplace(size=(nch, op.nparams)) * 0.01)
+    mb._step_counter = 6
+    Xb = mb._chain_step_dev(X0)
+    for c in range(nch):
+        m1, _ = make(1, 20 + c)
+        m1._step_counter = 6
+        assert torch.equal(m1._chain_step_dev(X0[c:c + 1])[0], Xb[c])
