@@ -69,6 +69,7 @@ class ForwardOperator:
     def _fused(self):
         t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
         return (self.fuse_harmonic and self.setting == "synthesis" and getattr(m, "_pxm_harmonic_input", False)
+                and (type(m).forward, type(m).adjoint) == getattr(type(m), "_pxm_fused_methods", None)  # not overridden
                 and hasattr(t, "_inverse_harmonic") and getattr(t, "spin", 0) == 0 and getattr(t, "L", None) == getattr(m, "L", -1))
 
     def _forward_synthesis(self, X):

@@ -251,3 +251,8 @@ class WeakLensing(WeakLensingHarmonic):
         nb = 1 if y.dim() == 1 else y.shape[0]
         g = D.scatter_dev(y, idx, w, self.npix)
         return D.like_input(D.ShtPlan.get(self.L, 2, nb).inverse_adjoint(g, gl=gl), gamma)
+
+
+# the harmonic-space composition in ForwardOperator bypasses `forward` / `adjoint`: it is only taken while a
+# (sub)class still uses these very implementations
+WeakLensing._pxm_fused_methods = (WeakLensing.forward, WeakLensing.adjoint)

@@ -399,3 +399,8 @@ def allreduce_sum(group=None):
         return t
 
     return f
+
+
+# the harmonic-space composition in ForwardOperator bypasses `forward` / `adjoint`: it is only taken while a
+# (sub)class still uses these very implementations
+ShardedWeakLensing._pxm_fused_methods = (ShardedWeakLensing.forward, ShardedWeakLensing.adjoint)

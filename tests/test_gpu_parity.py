@@ -246,6 +246,14 @@ def test_weaklensing_golden(px):
     # ... and the reference's literal composition through pixel space
     fo.fuse_harmonic = False
     assert not fo._fused()
+
+    class Doubled(px.measurements.WeakLensing):  # a user subclass that overrides forward must not be bypassed
+        def forward(self, kappa):
+            return 2 * super().forward(kappa)
+
+    fo2 = px.forward.ForwardOperator(g["gdata"], 1 / wl.inv_cov, "synthesis", transform=t, nparams=t.ncoefs,
+                                     measurement=Doubled(L, mask=g["mask"], ngal=g["ngal"]))
+    assert not fo2._fused() and rel_l2(fo2.forward(g["X"]), 2 * g["op_forward"]) < TOL
     assert rel_l2(fo.forward(g["X"]), g["op_forward"]) < TOL
     assert rel_l2(fo.calc_gradg(g["op_forward"]), g["op_gradg"]) < TOL
     with pytest.raises(ValueError):
