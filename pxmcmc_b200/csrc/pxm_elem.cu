@@ -594,7 +594,9 @@ __global__ void k_pxmala_accept(AcceptArgs p) {
     S[7] = L2p.y;
     S[8] = priorp;
   }
-  p.acc_trace[p.i] = accept ? 1 : 0;
+  // the traces are rings of trace_stride slots: the host drains them every trace_stride iterations
+  const long long slot = p.i % (long long)p.trace_stride;
+  p.acc_trace[slot] = accept ? 1 : 0;
   if (p.tune) {
     double d = delta * (1 + ((accept ? 1.0 : 0.0) - 0.5) / pow((double)(p.i + 1), 0.75));
     d = fmin(fmax(d, p.lmda * 1e-8), p.lmda / 2);
@@ -602,7 +604,7 @@ __global__ void k_pxmala_accept(AcceptArgs p) {
     S[1] = 1 - d / p.lmda;
     S[2] = d / p.lmda;
     S[3] = sqrt(2 * d);
-    p.delta_trace[p.i + 1] = d;
+    p.delta_trace[slot + 1] = d;
   }
   if (counters_on_device) {
     S[13] = (double)(p.i + 1);

@@ -62,6 +62,50 @@ def like_input(result, template):
     return result if is_dev(template) else to_host(result)
 
 
+# ---------------------------------------------------------------------------
+# output placement: a captured iteration must leave its results in the buffers it
+# started from (state X, predictions P).  The samplers ask for that with
+# `with output_into(buf): ...`; the next result tensor of exactly that shape
+# allocated through `new_c` below IS `buf` (no copy kernel, no ATen op).  Callers
+# check the returned tensor and fall back to `copy_into` when an operator they do
+# not know allocated its result some other way.
+# ---------------------------------------------------------------------------
+_out_hint = [None]
+
+
+class output_into:
+    def __init__(self, buf):
+        self.buf = buf
+
+    def __enter__(self):
+        self.prev = _out_hint[0]
+        _out_hint[0] = self.buf
+        return self
+
+    def __exit__(self, *exc):
+        _out_hint[0] = self.prev
+        return False
+
+
+def new_c(shape, device):
+    """uninitialised complex128 result tensor (or the pending `output_into` buffer of that shape)"""
+    h = _out_hint[0]
+    if h is not None and tuple(h.shape) == tuple(shape) and h.device == device:
+        _out_hint[0] = None
+        return h
+    return torch.empty(tuple(shape), dtype=CDT, device=device)
+
+
+def copy_into(dst, src):
+    """dst <- src (complex128, same shape) with the library's own kernel; no-op when they are the same buffer"""
+    if dst.data_ptr() == src.data_ptr():
+        return dst
+    arr = (C.c_void_p * 4)(src.data_ptr(), 0, 0, 0)
+    cf = (C.c_double * 4)(1.0, 0.0, 0.0, 0.0)
+    check(lib.pxm_lincomb(1, arr, cf, None, 0.0, 0.0, ptr(dst), dst.numel(), stream_ptr()))
+    return dst
+
+
 def batch2d(t):
     """view a [n] or [nb, n] tensor as ([nb, n], was_1d)"""
     if t.dim() == 1:
@@ -107,7 +151,7 @@ class WaveletPlan:
             raise ValueError(f"expected vectors of length {n_in}, got {x2.shape[1]}")
         if nb > self.nbatch:
             raise ValueError("batch larger than the plan's")
-        out = torch.empty((nb, n_out), dtype=CDT, device=x2.device)
+        out = new_c((nb, n_out), x2.device)
         check(fn(self.h, ptr(x2), ptr(out), nb, stream_ptr()))
         return out[0] if was1 else out
 
@@ -158,7 +202,7 @@ class ShtPlan:
         nb = x2.shape[0]
         if x2.shape[1] != n_in:
             raise ValueError(f"expected vectors of length {n_in}, got {x2.shape[1]}")
-        out = torch.empty((nb, n_out), dtype=CDT, device=x2.device)
+        out = new_c((nb, n_out), x2.device)
         check(fn(self.h, ptr(x2), ptr(out), nb, ptr(gl), stream_ptr()))
         return out[0] if was1 else out
 
@@ -199,12 +243,13 @@ def soft_dev(x, Tvec, Tscalar):
 
 
 def myula_update_dev(X, prox, gradg, Tvec, Tscalar, delta, lmda, w_re=None, w_im=None, noise_mode=0, seed=0, step=0,
-                     stream0=0, want_prox=False, dstep=None):
+                     stream0=0, want_prox=False, dstep=None, out=None):
     """dstep: int64 device tensor holding the Philox step (read by the kernel, then advanced by one):
-    the form a captured CUDA graph can replay"""
+    the form a captured CUDA graph can replay.  `out` may be X itself (every thread reads its elements before it
+    writes them)."""
     X2, was1 = batch2d(X)
     nb, n = X2.shape
-    out = torch.empty_like(X2)
+    out = torch.empty_like(X2) if out is None else batch2d(out)[0]
     pout = torch.empty_like(X2) if want_prox else None
     if dstep is not None:
         check(lib.pxm_myula_update_dstep(ptr(X2), ptr(prox), ptr(gradg), ptr(Tvec), Tscalar, ptr(out), ptr(pout), n, nb,
@@ -238,7 +283,7 @@ def reduce_dpar_dev(a, b, c, d, dpar, lmda):
     """kind-2 reduction (PxMALA transition) with the step size read from the device block `dpar`"""
     a2, _ = batch2d(a)
     nb, n = a2.shape
-    key = (nb, a2.device)
+    key = (nb, a2.device, torch.cuda.current_stream().cuda_stream)  # concurrent reductions on different streams do not share scratch
     if key not in _scratch:
         _scratch[key] = torch.empty(nb * lib.pxm_reduce_scratch_elems(), dtype=CDT, device=a2.device)
     out = torch.empty(nb, dtype=CDT, device=a2.device)
@@ -291,7 +336,7 @@ def reduce_dev(kind, a, b=None, c=None, d=None, w=None, delta=0.0, lmda=1.0):
     """per-chain complex reductions; returns a [nchains] complex128 device tensor"""
     a2, _ = batch2d(a)
     nb, n = a2.shape
-    key = (nb, a2.device)
+    key = (nb, a2.device, torch.cuda.current_stream().cuda_stream)  # concurrent reductions on different streams do not share scratch
     if key not in _scratch:
         _scratch[key] = torch.empty(nb * lib.pxm_reduce_scratch_elems(), dtype=CDT, device=a2.device)
     out = torch.empty(nb, dtype=CDT, device=a2.device)
@@ -300,20 +345,21 @@ def reduce_dev(kind, a, b=None, c=None, d=None, w=None, delta=0.0, lmda=1.0):
     return out
 
 
-def lincomb_dev(terms, z=None, cz=0.0, c0=0.0):
-    """sum_k coef_k * x_k (+ cz*z real, + c0 real), complex128 device tensors of equal shape"""
+def lincomb_dev(terms, z=None, cz=0.0, c0=0.0, out=None):
+    """sum_k coef_k * x_k (+ cz*z real, + c0 real), complex128 device tensors of equal shape; `out` may alias a term"""
     xs = [t for _, t in terms]
     n = len(xs)
     arr = (C.c_void_p * 4)(*([x.data_ptr() for x in xs] + [0] * (4 - n)))
     cf = (C.c_double * 4)(*([float(c) for c, _ in terms] + [0.0] * (4 - n)))
-    out = torch.empty_like(xs[0])
+    if out is None:
+        out = torch.empty_like(xs[0])
     check(lib.pxm_lincomb(n, arr, cf, ptr(z), float(cz), float(c0), ptr(out), out.numel(), stream_ptr()))
     return out
 
 
 def gather_dev(full, idx, w, nsel):
     f2, was1 = batch2d(full)
-    out = torch.empty((f2.shape[0], nsel), dtype=CDT, device=f2.device)
+    out = new_c((f2.shape[0], nsel), f2.device)
     check(lib.pxm_masked_gather(ptr(f2), ptr(idx), ptr(w), ptr(out), nsel, f2.shape[1], f2.shape[0], stream_ptr()))
     return out[0] if was1 else out
 
@@ -329,6 +375,6 @@ def csr_spmv_dev(indptr, indices, vals, x, nrows, ncols):
     x2, was1 = batch2d(x)
     if x2.shape[1] != ncols:
         raise ValueError("vector length does not match the matrix")
-    out = torch.empty((x2.shape[0], nrows), dtype=CDT, device=x2.device)
+    out = new_c((x2.shape[0], nrows), x2.device)
     check(lib.pxm_csr_spmv(ptr(indptr), ptr(indices), ptr(vals), ptr(x2), ptr(out), nrows, ncols, x2.shape[0], stream_ptr()))
     return out[0] if was1 else out

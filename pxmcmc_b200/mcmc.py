@@ -17,7 +17,7 @@ import torch
 from scipy.stats import laplace
 
 from . import device as D
-from .prior import L1
+from .prior import L1, is_library_l1
 from .utils import cheb1der, chebyshev1
 
 
@@ -76,12 +76,12 @@ class PxMCMC:
 
     # ------------------------------------------------------------------ helpers
     def _native(self):
-        return bool(getattr(self.forward, "_pxm_native", False)) and isinstance(self.prior, L1)
+        return bool(getattr(self.forward, "_pxm_native", False)) and is_library_l1(self.prior)
 
     def _fused_prox(self):
         """(Tvec, Tscalar) when the prox is a plain soft threshold that the update
         kernel can fuse, else None"""
-        if isinstance(self.prior, L1) and self.prior.setting == "synthesis":
+        if is_library_l1(self.prior) and self.prior.setting == "synthesis":
             return self.prior._T_args()
         return None
 
@@ -91,20 +91,27 @@ class PxMCMC:
         return x.unsqueeze(0) if x.dim() == 1 else x
 
     def _prior_dev(self, Xd):
-        if isinstance(self.prior, L1):
+        if is_library_l1(self.prior):
             return D.reduce_dev(0, Xd, w=self.prior._weights_dev()).real
         vals = [self.prior.prior(D.to_host(Xd[c])) for c in range(Xd.shape[0])]
         return torch.as_tensor(np.real(vals), device=Xd.device)
 
     def _proxf_dev(self, Xd):
-        if getattr(self.prior, "_pxm_native", False):
+        if is_library_l1(self.prior):
             return D.to_dev_c(self.prior.proxf(Xd))
         return torch.stack([D.to_dev_c(self.prior.proxf(D.to_host(Xd[c]))) for c in range(Xd.shape[0])])
 
-    def _forward_dev(self, Xd):
+    def _forward_dev(self, Xd, out=None):
+        """predictions of the state(s); `out`: buffer the result must end up in (captured graphs: the operator's last
+        kernel writes straight into it, see device.output_into)"""
         if getattr(self.forward, "_pxm_native", False):
-            return self.forward.forward(Xd)
-        return torch.stack([D.to_dev_c(self.forward.forward(D.to_host(Xd[c]))) for c in range(Xd.shape[0])])
+            if out is None:
+                return self.forward.forward(Xd)
+            with D.output_into(out):
+                r = D.to_dev_c(self.forward.forward(Xd))
+            return D.copy_into(out, r.reshape(out.shape))
+        r = torch.stack([D.to_dev_c(self.forward.forward(D.to_host(Xd[c]))) for c in range(Xd.shape[0])])
+        return r if out is None else D.copy_into(out, r.reshape(out.shape))
 
     def _gradg_dev(self, Pd):
         if getattr(self.forward, "_pxm_native", False):
@@ -127,7 +134,7 @@ class PxMCMC:
     def _logpi_terms_dev(self, Xd, Pd):
         """(L2, prior) as DEVICE tensors [nchains] (complex, real), or None when the operator has a
         general covariance (host path)"""
-        if getattr(self.forward, "_diag", None) is None or not isinstance(self.prior, L1):
+        if getattr(self.forward, "_diag", None) is None or not is_library_l1(self.prior):
             return None
         red = getattr(self.forward, "_pxm_allreduce", None)
         data_d, ic_d = self.forward._upload()
@@ -237,14 +244,15 @@ class PxMCMC:
     # ------------------------------------------------------------------ checkpoint / resume
     _TRACKED = ("logPi", "L2s", "priors", "preds", "chain")
 
-    def save_checkpoint(self, path, i, j, X_curr, curr_preds):
-        """Everything `run(resume=path)` needs to continue the chain exactly where it stands after iteration
-        i - 1: state and predictions, loop counters, the Philox step, numpy's global RNG state (host-noise mode)
-        and the tracked arrays filled so far.  One .npz; written to a temporary name and renamed."""
+    def _save_ckpt(self, path, **fields):
+        """One .npz (written to a temporary name, then renamed) with `fields` plus everything every sampler needs to
+        continue exactly where it stands: the Philox step, the step size, numpy's global RNG state (host-noise mode)
+        and the tracked arrays filled so far."""
         import os
 
-        d = {"i": i, "j": j, "step_counter": self._step_counter, "X": D.to_host(X_curr), "P": D.to_host(curr_preds),
-             "nchains": self.nchains, "noise": self.noise, "delta": self.delta}
+        d = dict(fields)
+        d.update(step_counter=self._step_counter, nchains=self.nchains, noise=self.noise, delta=self.delta,
+                 sampler=type(self).__name__)
         for name in self._TRACKED:
             if hasattr(self, name):
                 d["track_" + name] = getattr(self, name)
@@ -254,11 +262,13 @@ class PxMCMC:
         np.savez(tmp, **d)
         os.replace(tmp, path if path.endswith(".npz") else path + ".npz")
 
-    def load_checkpoint(self, path):
-        """-> (i, j, X, preds) as device tensors; restores the tracked arrays, the Philox step and numpy's RNG state"""
+    def _load_ckpt(self, path):
+        """-> dict of the saved fields; restores the tracked arrays, the Philox step, the step size and numpy's RNG state"""
         with np.load(path if path.endswith(".npz") else path + ".npz", allow_pickle=False) as f:
             if int(f["nchains"]) != self.nchains or str(f["noise"]) != self.noise:
                 raise ValueError("checkpoint was written by a sampler with another chain count / noise mode")
+            if "sampler" in f.files and str(f["sampler"]) != type(self).__name__:
+                raise ValueError(f"checkpoint was written by {f['sampler']}, not {type(self).__name__}")
             for name in self._TRACKED:
                 if "track_" + name in f.files and hasattr(self, name):
                     arr = f["track_" + name]
@@ -268,7 +278,17 @@ class PxMCMC:
             self._step_counter = int(f["step_counter"])
             self.delta = float(f["delta"])
             np.random.set_state(("MT19937", f["rng_keys"], int(f["rng_pos"]), int(f["rng_has_gauss"]), float(f["rng_cached"])))
-            return int(f["i"]), int(f["j"]), self._state(f["X"]), self._state(f["P"])
+            return {k: f[k] for k in f.files if not k.startswith(("track_", "rng_"))}
+
+    def save_checkpoint(self, path, i, j, X_curr, curr_preds):
+        """Everything `run(resume=path)` needs to continue the chain exactly where it stands after iteration
+        i - 1: state and predictions, loop counters, and the common fields of `_save_ckpt`."""
+        self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(curr_preds))
+
+    def load_checkpoint(self, path):
+        """-> (i, j, X, preds) as device tensors"""
+        f = self._load_ckpt(path)
+        return int(f["i"]), int(f["j"]), self._state(f["X"]), self._state(f["P"])
 
     def _on_grid(self, i):
         return i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
@@ -288,9 +308,9 @@ class MYULA(PxMCMC):
     def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), **kw):
         super().__init__(forward, prox, mcmcparams, **kw)
 
-    def _propose_dev(self, Xd, proxd, gradgd):
+    def _propose_dev(self, Xd, proxd, gradgd, out=None):
         """X' = (1-d/l) X + (d/l) prox - d gradg + sqrt(2d) w, one fused kernel;
-        proxd None -> the soft threshold is evaluated inside the kernel"""
+        proxd None -> the soft threshold is evaluated inside the kernel; `out` (may be Xd itself) receives X'"""
         n = self.forward.nparams
         if proxd is None:
             Tv, Ts = self._fused_prox()
@@ -298,12 +318,12 @@ class MYULA(PxMCMC):
             Tv, Ts = None, 0.0
         if self.noise == "host":
             w_re, w_im = self._host_noise(n)
-            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im, noise_mode=1)
+            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im, noise_mode=1, out=out)
         elif getattr(self, "_dstep", None) is not None:
             # graph mode: the step lives on the device and is advanced by the captured graph itself
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
                                      noise_mode=3 if self.complex else 2, seed=self.seed, stream0=self.stream0,
-                                     dstep=self._dstep)
+                                     dstep=self._dstep, out=out)
         else:
             # chain-group calls of one iteration (iterate_host) share a step; their Philox streams are
             # offset so that chain c always uses stream stream0 + c, whatever the grouping
@@ -312,7 +332,7 @@ class MYULA(PxMCMC):
                 self._step_counter += 1
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
                                      noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter,
-                                     stream0=self.stream0 + (off or 0))
+                                     stream0=self.stream0 + (off or 0), out=out)
         return out
 
     def run(self, start_point=None, *, checkpoint=None, checkpoint_every=0, resume=None):
@@ -358,13 +378,18 @@ class MYULA(PxMCMC):
         self._final_state = (X_curr, curr_preds)
         print("\nDONE")
 
-    def iterate(self, X_curr, curr_preds):
+    def iterate(self, X_curr, curr_preds, out=None):
         """One pass of the loop body (pxmcmc/mcmc.py:158-164) on device tensors
-        [nchains, .]: gradg -> prox -> proposal -> new predictions."""
+        [nchains, .]: gradg -> prox -> proposal -> new predictions.  `out = (X_buf, P_buf)`: where the new state and
+        predictions are written; the input buffers themselves are allowed (the update is elementwise and the old
+        predictions are consumed before the new ones are produced), which is how captured graphs advance in place."""
         gradg = D.to_dev_c(self._gradg_dev(curr_preds))
         proxf = None if self._fused_prox() is not None else self._proxf_dev(X_curr)
-        X_new = self._propose_dev(X_curr, proxf, gradg)
-        return X_new, D.to_dev_c(self._forward_dev(X_new))
+        if out is None:
+            X_new = self._propose_dev(X_curr, proxf, gradg)
+            return X_new, D.to_dev_c(self._forward_dev(X_new))
+        X_new = self._propose_dev(X_curr, proxf, gradg, out=out[0])
+        return X_new, self._forward_dev(X_new, out=out[1])
 
     def capture(self, X_curr, curr_preds, iterations=1):
         """Record `iterations` passes of the loop body as ONE CUDA graph on private copies of the
@@ -479,11 +504,10 @@ class GraphedChain:
         sampler._dstep.fill_(sampler._step_counter + 1)  # the warm-up did not happen as far as the chain is concerned
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            x, p = self.X, self.P
+            # the chain advances IN PLACE: the update kernel and the operator's last kernel write into X / P
+            # (no copy-back, no ATen kernel inside the graph)
             for _ in range(self.iterations):
-                x, p = sampler.iterate(x, p)
-            self.X.copy_(x)
-            self.P.copy_(p)
+                sampler.iterate(self.X, self.P, out=(self.X, self.P))
 
     def step(self):
         """advance the chain by `iterations` iterations (asynchronous, like any kernel launch)"""
@@ -512,7 +536,7 @@ class PxMALA(MYULA):
                                       "operator with a diagonal covariance and an L1 prior")
 
     def _logtrans_dev(self, X1, X2, proxf, gradg):
-        s = complex(D.to_host(D.reduce_dev(2, X1, b=X2, c=proxf, d=gradg, delta=self.delta, lmda=self.lmda))[0])
+        s = complex(D.to_host(self._transition_sums(X1, X2, proxf, gradg))[0])
         return -(1 / 2 * self.delta) * s ** 2
 
     def calc_logtransition(self, X1, X2, proxf, gradg):
@@ -524,30 +548,59 @@ class PxMALA(MYULA):
         """True when an iteration can run without a host round trip: Philox noise, a native operator with a
         diagonal covariance and a native L1 prior, one chain"""
         return (self.noise == "device" and getattr(self.forward, "_pxm_native", False)
-                and getattr(self.forward, "_diag", None) is not None and isinstance(self.prior, L1)
-                and getattr(self.prior, "_pxm_native", False) and getattr(self.forward, "_pxm_allreduce", None) is None)
+                and getattr(self.forward, "_diag", None) is not None and is_library_l1(self.prior)
+                and getattr(self.forward, "_pxm_allreduce", None) is None)
 
-    def _run_device(self, start_point=None):
+    trace_ring = 1 << 16  # slots of the device-side acceptance / step-size trace rings (drained to the host when full)
+
+    def _run_device(self, start_point=None, checkpoint=None, checkpoint_every=0, resume=None):
         """The same loop with the accept test on the device (`pxm_pxmala_accept`): the step size, log pi(Xc) and the
         traces live in device memory, the accepted proposal is copied over the state by a predicated kernel, and the
-        host reads the decision only on the thinning grid (where the reference stores accepted samples)."""
+        host reads the decision only on the thinning grid (where the reference stores accepted samples).  The traces
+        are rings of `trace_ring` slots drained to the host every `trace_ring` iterations, so a run may be as long as
+        the reference's (nburn = 10^7 in experiments/weaklensing/main.py:110-119)."""
         dv = D.dev()
         nch = self.nchains
-        X_curr, curr_preds = self._initial_sample(start_point)
+        cap = int(self.trace_ring)
+        acc_chunks, dl_chunks = [], []  # drained parts of the traces: [nch, cap] each
+        i = 0
+        js = np.zeros(nch, dtype=np.int64)  # tracked samples per chain (accepted proposals on the thinning grid)
+        if resume is not None:
+            ck = self._load_ckpt(resume)
+            i, js = int(ck["i"]), ck["js"].astype(np.int64)
+            X_curr, curr_preds = self._state(ck["X"]), self._state(ck["P"])
+            acc_chunks, dl_chunks = [ck["acc_done"]], [ck["dl_done"]]
+            delta0 = float(ck["delta0"])
+        else:
+            X_curr, curr_preds = self._initial_sample(start_point)
+            delta0 = self.delta
         X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
+        # gradient, prox and log pi of the current state are functions of (X, preds): recomputed (bit-identical) on resume
         gradg_curr = D.to_dev_c(self._gradg_dev(curr_preds)).clone()
         proxf_curr = D.to_dev_c(self._proxf_dev(X_curr)).clone()
-        lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
-        S = np.zeros((nch, 16))
-        S[:, 0], S[:, 1], S[:, 2], S[:, 3] = self.delta, 1 - self.delta / self.lmda, self.delta / self.lmda, np.sqrt(2 * self.delta)
-        S[:, 4], S[:, 5], S[:, 6], S[:, 7], S[:, 8] = np.real(lp), np.imag(lp), np.real(l2), np.imag(l2), pr
-        S = torch.from_numpy(S).to(dv)
-        cap = 1 << 16
+        if resume is not None:
+            S = torch.from_numpy(np.ascontiguousarray(ck["S"])).to(dv)
+        else:
+            lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
+            S = np.zeros((nch, 16))
+            S[:, 0], S[:, 1], S[:, 2], S[:, 3] = self.delta, 1 - self.delta / self.lmda, self.delta / self.lmda, np.sqrt(2 * self.delta)
+            S[:, 4], S[:, 5], S[:, 6], S[:, 7], S[:, 8] = np.real(lp), np.imag(lp), np.real(l2), np.imag(l2), pr
+            S = torch.from_numpy(S).to(dv)
         acc = torch.zeros((nch, cap), dtype=torch.int8, device=dv)
         dl = torch.zeros((nch, cap + 1), dtype=D.FDT, device=dv)
-        dl[:, 0] = self.delta
         mode = 3 if self.complex else 2
         cur = [X_curr, curr_preds, gradg_curr, proxf_curr]
+
+        def drain(upto):
+            """move the first `upto` ring slots (iterations i - upto .. i - 1) to the host lists"""
+            if upto:
+                acc_chunks.append(acc[:, :upto].cpu().numpy())
+                dl_chunks.append(dl[:, 1: upto + 1].cpu().numpy())
+
+        def traces():
+            a = np.concatenate(acc_chunks, axis=1) if acc_chunks else np.zeros((nch, 0), dtype=np.int8)
+            d = np.concatenate(dl_chunks, axis=1) if dl_chunks else np.zeros((nch, 0))
+            return a, d
 
         def body(i_arg, step_arg):
             """one iteration; (i_arg, step_arg) = (-1, 0): iteration index and Philox step come from S[:, 13], S[:, 14]"""
@@ -567,8 +620,7 @@ class PxMALA(MYULA):
         # run eagerly (they warm up tables, lazy uploads and allocator pools, and ARE iterations of the chain), then the
         # iteration is captured with its counters in the state blocks
         graph = None
-        i = 0
-        js = np.zeros(nch, dtype=np.int64)  # tracked samples per chain (accepted proposals on the thinning grid)
+        i_start = i
 
         def put(arr, c, j, val):
             val = np.asarray(val)
@@ -602,14 +654,32 @@ class PxMALA(MYULA):
                             put(self.chain, c, j, Xh[c])
                         js[c] += 1
                 if verbose:
+                    done = sum(int(a.sum()) for a in acc_chunks) + int(acc[:, : (i % cap) + 1].sum().item())
                     self._print_progress(int(js[0]) - 1, st[0, 4], L2=st[0, 6], prior=st[0, 8],
-                                         acceptanceRate=float(acc[:, : i + 1].double().mean().item()))
+                                         acceptanceRate=done / float(nch * (i + 1)))
+
+        def save(i_next):
+            a, d = traces()
+            part = i_next % cap
+            if part:
+                a = np.concatenate([a, acc[:, :part].cpu().numpy()], axis=1)
+                d = np.concatenate([d, dl[:, 1: part + 1].cpu().numpy()], axis=1)
+            self._save_ckpt(checkpoint, i=i_next, js=js, X=D.to_host(cur[0]), P=D.to_host(cur[1]), S=S.cpu().numpy(),
+                            acc_done=a, dl_done=d, delta0=delta0)
+
+        if resume is not None and i % cap:
+            # the ring is addressed by i mod cap: put the undrained tail of the restored traces back in its slots
+            part = i % cap
+            a, d = acc_chunks.pop(), dl_chunks.pop()
+            acc[:, :part] = torch.from_numpy(np.ascontiguousarray(a[:, a.shape[1] - part:])).to(dv)
+            dl[:, 1: part + 1] = torch.from_numpy(np.ascontiguousarray(d[:, d.shape[1] - part:])).to(dv)
+            if a.shape[1] > part:
+                acc_chunks.append(a[:, : a.shape[1] - part])
+                dl_chunks.append(d[:, : d.shape[1] - part])
 
         while js.min() < self.nsamples:
-            if i + 1 >= cap:
-                raise RuntimeError(f"PxMALA: more than {cap} iterations in one run(); split the run")
             self._step_counter += 1
-            if graph is None and i >= 2 and self.use_graph:
+            if graph is None and i >= i_start + 2 and self.use_graph:
                 S[:, 13], S[:, 14] = float(i), float(self._step_counter)
                 side = torch.cuda.Stream()
                 side.wait_stream(torch.cuda.current_stream())
@@ -624,9 +694,18 @@ class PxMALA(MYULA):
                 body(i, self._step_counter)
             after(i)
             i += 1
+            if i % cap == 0:
+                drain(cap)
+            if checkpoint is not None and checkpoint_every and i % checkpoint_every == 0:
+                save(i)
+        if checkpoint is not None:
+            save(i)
+        drain(i % cap)
         X_curr, curr_preds = cur[0], cur[1]
-        at = acc[:, :i].cpu().numpy().astype(int)
-        dt = dl[:, : (i + 1 if self.tune_delta else 1)].cpu().numpy()
+        at, dt = traces()
+        at = at.astype(int)
+        first = np.full((nch, 1), delta0)
+        dt = np.concatenate([first, dt], axis=1) if self.tune_delta else first
         # one chain: the reference's flat lists; several chains: arrays with a leading chain axis
         self.acceptance_trace = [int(v) for v in at[0]] if nch == 1 else at
         self.deltas_trace = [float(v) for v in dt[0]] if nch == 1 else dt
@@ -635,19 +714,50 @@ class PxMALA(MYULA):
         self._final_state = (X_curr.clone(), curr_preds.clone())
         print("\nDONE")
 
-    def run(self, start_point=None):
-        """the loop of pxmcmc/mcmc.py:218-275"""
+    def _shared_uniform(self):
+        """the uniform of the accept test; the ranks of an m-sharded chain must all use rank 0's draw"""
+        u = np.random.rand()
+        red = getattr(self.forward, "_pxm_allreduce", None)
+        if red is not None:
+            import torch.distributed as dist
+
+            mine = u if (not dist.is_initialized() or dist.get_rank() == 0) else 0.0
+            u = float(red(torch.tensor([mine], dtype=D.FDT, device=D.dev())).item())
+        return u
+
+    def _transition_sums(self, X1, X2, proxf, gradg):
+        """sum (X2 - X1 - (delta/2) grad log pi(X1))^2 per chain as a device tensor, summed over the ranks of an m-sharded
+        operator BEFORE it is squared again (pxmcmc/mcmc.py:286-289)"""
+        s = D.reduce_dev(2, X1, b=X2, c=proxf, d=gradg, delta=self.delta, lmda=self.lmda)
+        red = getattr(self.forward, "_pxm_allreduce", None)
+        return red(s) if red else s
+
+    def run(self, start_point=None, *, checkpoint=None, checkpoint_every=0, resume=None):
+        """the loop of pxmcmc/mcmc.py:218-275.  `checkpoint` / `checkpoint_every` / `resume` as in `MYULA.run`."""
         if self._device_resident():
-            return self._run_device(start_point)
+            return self._run_device(start_point, checkpoint, checkpoint_every, resume)
         self.acceptance_trace = []
         self.deltas_trace = [self.delta]
         i = 0
         j = 0
-        X_curr, curr_preds = self._initial_sample(start_point)
+        if resume is not None:
+            ck = self._load_ckpt(resume)
+            i, j = int(ck["i"]), int(ck["j"])
+            X_curr, curr_preds = self._state(ck["X"]), self._state(ck["P"])
+            self.acceptance_trace = [int(v) for v in ck["acc_done"]]
+            self.deltas_trace = [float(v) for v in ck["dl_done"]]
+        else:
+            X_curr, curr_preds = self._initial_sample(start_point)
+        # functions of (X, preds): recomputed (bit-identical) on resume
         gradg_curr = D.to_dev_c(self._gradg_dev(curr_preds))
         proxf_curr = self._proxf_dev(X_curr)
         lp, l2, pr = self._logpi_dev(X_curr, curr_preds)
         logpiXc, L2Xc, priorXc = lp[0], l2[0], pr[0]
+
+        def save(i_next):
+            self._save_ckpt(checkpoint, i=i_next, j=j, X=D.to_host(X_curr), P=D.to_host(curr_preds),
+                            acc_done=np.asarray(self.acceptance_trace, dtype=np.int8), dl_done=np.asarray(self.deltas_trace))
+
         while j < self.nsamples:
             X_prop = self._propose_dev(X_curr, proxf_curr, gradg_curr)
             prop_preds = D.to_dev_c(self._forward_dev(X_prop))
@@ -656,8 +766,8 @@ class PxMALA(MYULA):
             terms = self._logpi_terms_dev(X_prop, prop_preds)
             if terms is not None:
                 # the four reductions of the accept test leave the device in ONE copy (one host sync per iteration)
-                s1 = D.reduce_dev(2, X_curr, b=X_prop, c=proxf_curr, d=gradg_curr, delta=self.delta, lmda=self.lmda)
-                s2 = D.reduce_dev(2, X_prop, b=X_curr, c=proxf_prop, d=gradg_prop, delta=self.delta, lmda=self.lmda)
+                s1 = self._transition_sums(X_curr, X_prop, proxf_curr, gradg_curr)
+                s2 = self._transition_sums(X_prop, X_curr, proxf_prop, gradg_prop)
                 v = torch.cat([s1, s2, terms[0], terms[1].to(D.CDT)]).cpu().numpy()
                 logtransXcXp = -(1 / 2 * self.delta) * complex(v[0]) ** 2
                 logtransXpXc = -(1 / 2 * self.delta) * complex(v[1]) ** 2
@@ -669,7 +779,7 @@ class PxMALA(MYULA):
                 lp, l2, pr = self._logpi_dev(X_prop, prop_preds)
                 logpiXp, L2Xp, priorXp = lp[0], l2[0], pr[0]
             logalpha = logtransXpXc + logpiXp - logtransXcXp - logpiXc
-            accept = _cplx_lt(np.log(np.random.rand()), logalpha)
+            accept = _cplx_lt(np.log(self._shared_uniform()), logalpha)
             if accept:
                 X_curr, curr_preds, gradg_curr, proxf_curr = X_prop, prop_preds, gradg_prop, proxf_prop
                 logpiXc, L2Xc, priorXc = logpiXp, L2Xp, priorXp
@@ -687,6 +797,10 @@ class PxMALA(MYULA):
                 self._print_progress(j - 1, np.real(logpiXc), L2=np.real(L2Xc), prior=priorXc,
                                      acceptanceRate=np.mean(self.acceptance_trace))
             i += 1
+            if checkpoint is not None and checkpoint_every and i % checkpoint_every == 0:
+                save(i)
+        if checkpoint is not None:
+            save(i)
         self._final_state = (X_curr, curr_preds)
         print("\nDONE")
 
@@ -700,9 +814,11 @@ class _GraphedSkrock:
     def __init__(self, sampler, X):
         self.sampler = sampler
         self.X = sampler._state(X).clone()
+        counter = sampler._step_counter
         for _ in range(2):  # warm-up (tables, lazy uploads, allocator pools) before the capture
             x = sampler._chain_step_dev(self.X)
             p = D.to_dev_c(sampler._forward_dev(x))
+        sampler._step_counter = counter  # the warm-up is not part of the chain: graphed and eager runs draw the same Philox steps
         self.P = p.clone()
         torch.cuda.synchronize()
         # the graph reads (and advances) this counter on every replay: it must stay alive with the graph
@@ -713,9 +829,9 @@ class _GraphedSkrock:
         try:
             with torch.cuda.stream(side):
                 with torch.cuda.graph(self.graph, stream=side):
-                    x = sampler._chain_step_dev(self.X)
-                    self.P.copy_(D.to_dev_c(sampler._forward_dev(x)))
-                    self.X.copy_(x)
+                    # in place: the last stage of the recursion writes X, the operator's last kernel writes P
+                    sampler._chain_step_dev(self.X, out=self.X)
+                    sampler._forward_dev(self.X, out=self.P)
         finally:
             sampler._dstep = None
         torch.cuda.current_stream().wait_stream(side)
@@ -740,13 +856,16 @@ class SKROCK(PxMCMC):
         self.omega_1 = chebyshev1(self.omega_0, self.s) / cheb1der(self.omega_0, self.s)
         self._recursion_coefs()
 
-    def run(self, start_point=None):
-        """the loop of pxmcmc/mcmc.py:308-336"""
+    def run(self, start_point=None, *, checkpoint=None, checkpoint_every=0, resume=None):
+        """the loop of pxmcmc/mcmc.py:308-336.  `checkpoint` / `checkpoint_every` / `resume` as in `MYULA.run`."""
         i = 0
         j = 0
-        X_curr, curr_preds = self._initial_sample(start_point)
+        if resume is not None:
+            i, j, X_curr, curr_preds = self.load_checkpoint(resume)
+        else:
+            X_curr, curr_preds = self._initial_sample(start_point)
         # a CUDA graph needs every operation of the step on the device: native operator and prior only
-        graphed = self.capture(X_curr) if (self.noise == "device" and not self.complex and self._native()
+        graphed = self.capture(X_curr) if (self.noise == "device" and self._native()
                                            and getattr(self.forward, "_pxm_allreduce", None) is None) else None
         while j < self.nsamples:
             if graphed is not None:  # the whole step (s gradient evaluations + predictions) as one CUDA graph
@@ -764,24 +883,37 @@ class SKROCK(PxMCMC):
                 self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
                                      prior=np.ravel(self.priors)[j - 1])
             i += 1
+            if checkpoint is not None and checkpoint_every and i % checkpoint_every == 0:
+                self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
+        if checkpoint is not None:
+            self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
+        if graphed is not None:
+            X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
         self._final_state = (X_curr, curr_preds)
         print("\nDONE")
 
-    def _chain_step_dev(self, Xd, Z=None):
+    def _chain_step_dev(self, Xd, Z=None, out=None):
+        """Z: real [nchains, n] normals, or a (real, imaginary) pair when `complex` (pxmcmc/mcmc.py:344-347)"""
         n = Xd.shape[-1]
+        nch = Xd.shape[0]
         if Z is None:
-            if self.complex:
-                raise NotImplementedError("complex SKROCK noise is not implemented on the device path")
             if self.noise == "device":  # Philox normals, step counter on the host or (graph replays) on the device
                 dstep = getattr(self, "_dstep", None)
                 if dstep is None:
                     self._step_counter += 1
-                Z = D.philox_normal_dev(Xd.shape[0], n, self.seed, self._step_counter, self.stream0, dstep=dstep)
+                if self.complex:
+                    # one draw of 2n normals per chain: the first n are the real, the last n the imaginary parts
+                    z2 = D.philox_normal_dev(nch, 2 * n, self.seed, self._step_counter, self.stream0, dstep=dstep)
+                    Z = (z2[:, :n].contiguous(), z2[:, n:].contiguous())
+                else:
+                    Z = D.philox_normal_dev(nch, n, self.seed, self._step_counter, self.stream0, dstep=dstep)
                 if dstep is not None:
                     D.check(D.lib.pxm_counter_add(D.ptr(dstep), 1, D.stream_ptr()))
             else:
-                Z = D.to_dev_f(np.random.randn(n * Xd.shape[0])).reshape(Xd.shape)
-        return self._K_recursion(Xd, self.s, Z)
+                Z = D.to_dev_f(np.random.randn(n * nch)).reshape(Xd.shape)
+                if self.complex:  # the reference's order: real part, then imaginary part
+                    Z = (Z, D.to_dev_f(np.random.randn(n * nch)).reshape(Xd.shape))
+        return self._K_recursion(Xd, self.s, Z, out=out)
 
     def capture(self, X_curr):
         """One SKROCK step (s gradient evaluations, ~14 s launches) and its predictions as ONE CUDA graph; needs
@@ -795,17 +927,26 @@ class SKROCK(PxMCMC):
         out = self._chain_step_dev(self._state(X))
         return out if D.is_dev(X) else D.to_host(out[0])
 
-    def _K_recursion(self, Xd, s, Z):
-        """K_s of pxmcmc/mcmc.py:349-368, memoised"""
+    def _K_recursion(self, Xd, s, Z, out=None):
+        """K_s of pxmcmc/mcmc.py:349-368, memoised.  `out` (may be Xd) receives K_s."""
         sq = np.sqrt(2 * self.delta)
         K_prev2 = Xd
         if s == 0:
-            return Xd
-        Y = D.lincomb_dev([(1.0, Xd)], z=Z, cz=self.nus[1] * sq)
-        K_prev = D.lincomb_dev([(1.0, Xd), (self.mus[1] * self.delta, self._gradlogpi_dev(Y))], z=Z, cz=self.ks[1] * sq)
+            return Xd if out is None else D.copy_into(out, Xd)
+        if isinstance(Z, tuple):  # complex noise: the imaginary part rides as a term with an imaginary unit folded in
+            Zc = torch.complex(Z[0], Z[1])
+            zterm = lambda c: ([(c, Zc)], None, 0.0)  # noqa: E731
+        else:
+            zterm = lambda c: ([], Z, c)  # noqa: E731
+        t, z, cz = zterm(self.nus[1] * sq)
+        Y = D.lincomb_dev([(1.0, Xd)] + t, z=z, cz=cz)
+        t, z, cz = zterm(self.ks[1] * sq)
+        K_prev = D.lincomb_dev([(1.0, Xd), (self.mus[1] * self.delta, self._gradlogpi_dev(Y))] + t, z=z, cz=cz,
+                               out=out if s == 1 else None)
         for j in range(2, s + 1):
             g = self._gradlogpi_dev(K_prev)
-            K = D.lincomb_dev([(self.mus[j] * self.delta, g), (self.nus[j], K_prev), (-1.0, K_prev2)], c0=self.ks[j])
+            K = D.lincomb_dev([(self.mus[j] * self.delta, g), (self.nus[j], K_prev), (-1.0, K_prev2)], c0=self.ks[j],
+                              out=out if j == s else None)
             K_prev2, K_prev = K_prev, K
         return K_prev
 

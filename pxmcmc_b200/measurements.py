@@ -204,8 +204,9 @@ class WeakLensing(WeakLensingHarmonic):
     def _forward(self, kappa, masking=False, cov_weighting=False):
         idx, w, gl = self._upload()
         x = D.to_dev_c(kappa)
-        x = x.reshape(-1) if x.numel() == self.npix else x.reshape(-1, self.npix)
-        nb = 1 if x.dim() == 1 else x.shape[0]
+        if x.shape[-1] != self.npix:  # a map given as an (L, 2L-1) array, as the reference's np.reshape accepts
+            x = x.reshape(-1) if x.numel() == self.npix else x.reshape(-1, self.npix)
+        nb = 1 if x.dim() == 1 else x.shape[0]  # a [nchains, npix] batch stays a batch (also for one chain)
         klm = D.ShtPlan.get(self.L, 0, nb).forward(x)
         gamma = D.ShtPlan.get(self.L, 2, nb).inverse(klm, gl=gl)
         if masking:
@@ -217,13 +218,15 @@ class WeakLensing(WeakLensingHarmonic):
     def _adjoint(self, gamma, masking=False, cov_weighting=False):
         idx, w, gl = self._upload()
         y = D.to_dev_c(gamma)
-        nb = 1 if (y.dim() == 1 or (not masking and y.numel() == self.npix)) else y.shape[0]
         if masking:
             g = D.scatter_dev(y, idx, w if cov_weighting else None, self.npix)
         else:
-            g = y.reshape(-1) if y.numel() == self.npix else y.reshape(-1, self.npix)
+            g = y
+            if g.shape[-1] != self.npix:
+                g = y.reshape(-1) if y.numel() == self.npix else y.reshape(-1, self.npix)
             if cov_weighting:
                 g = g * w
+        nb = 1 if g.dim() == 1 else g.shape[0]
         glm = D.ShtPlan.get(self.L, 2, nb).inverse_adjoint(g, gl=gl)
         kappa = D.ShtPlan.get(self.L, 0, nb).forward_adjoint(glm)
         return D.like_input(kappa, gamma)

@@ -58,6 +58,18 @@ class L1:
         return D.like_input(D.lincomb_dev([(1.0, x), (1.0, back)]), X)
 
 
+def is_library_l1(prior):
+    """True when `prior` is an L1 (sub)class whose prox / prior are still the library's implementations.  The samplers
+    take their fused device paths (soft threshold inside the update kernel, sum |w X| as a device reduction) only
+    then; a user subclass that overrides `proxf`, `_proxf_synthesis`, `_proxf_analysis` or `prior` -- the reference's
+    extension pattern -- is called through its own methods instead."""
+    if not isinstance(prior, L1):
+        return False
+    t = type(prior)
+    return (t.proxf is L1.proxf and t._proxf_synthesis is L1._proxf_synthesis and t._proxf_analysis is L1._proxf_analysis
+            and t.prior in _LIBRARY_PRIOR_METHODS and t._weights_dev in _LIBRARY_WEIGHT_METHODS)
+
+
 class S2_Wavelets_L1(L1):
     """L1 on spherical wavelet coefficients weighted by the exact MW quadrature
     weights of every scale (pxmcmc/prior.py:56-84)."""
@@ -137,3 +149,7 @@ class S2_Wavelets_L1_Power_Weights(S2_Wavelets_L1):
             nsamples = int(effective_L) * (2 * int(effective_L) - 1)
             out.append(self._ring_weights(int(effective_L), (2 * np.pi ** 2) * (peak_l ** self.eta) / (power * nsamples)))
         return out
+
+
+_LIBRARY_PRIOR_METHODS = (L1.prior, S2_Wavelets_L1.prior)
+_LIBRARY_WEIGHT_METHODS = (L1._weights_dev, S2_Wavelets_L1._weights_dev)

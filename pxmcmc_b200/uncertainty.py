@@ -43,6 +43,11 @@ def _quantile_pair_dev(chain_d, qa, qb):
     return out_a, out_b
 
 
+def _host_range(chain, qa, qb):
+    """what the reference itself evaluates (pxmcmc/uncertainty.py:14-16)"""
+    return np.quantile(chain, qb, axis=0) - np.quantile(chain, qa, axis=0)
+
+
 def credible_interval_range(chain, alpha=0.05, max_bytes=2 << 30):
     """Range of the (1 - alpha) credible interval of every parameter: the difference of the
     1 - alpha/2 and alpha/2 quantiles over the samples (pxmcmc/uncertainty.py:7-16).
@@ -53,6 +58,10 @@ def credible_interval_range(chain, alpha=0.05, max_bytes=2 << 30):
     if D.is_dev(chain):
         if chain.is_complex():
             raise TypeError("a must be an array of real numbers")
+        if chain.shape[0] > lib.pxm_quantile_columns_max_samples():
+            # longer than the shared-memory sort holds: numpy's own quantile on the host (rare: the kernel takes 16 384
+            # samples per parameter; the reference's default of 10^6 saved samples would not fit the GPU anyway)
+            return torch.from_numpy(_host_range(D.to_host(chain), qa, qb)).to(chain.device)
         lo, hi = _quantile_pair_dev(chain.to(torch.float64), qa, qb)
         return hi - lo
     chain = np.asarray(chain)
@@ -62,7 +71,7 @@ def credible_interval_range(chain, alpha=0.05, max_bytes=2 << 30):
         raise ValueError("expected an nsamples x nparams array")
     n, npar = chain.shape
     if n > lib.pxm_quantile_columns_max_samples():
-        raise NotImplementedError(f"chains longer than {lib.pxm_quantile_columns_max_samples()} samples: thin the chain first")
+        return _host_range(chain, qa, qb)
     D.dev()
     out = np.empty(npar, dtype=np.float64)
     step = max(32, int(max_bytes // (8 * max(n, 1))) // 32 * 32)  # columns per upload

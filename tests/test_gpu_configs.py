@@ -404,11 +404,12 @@ def test_config4_weaklensing_myula_L512_iteration(px, pool):
         m = px.mcmc.MYULA(op, reg, prm)
         Xd = m._state(X)
         Pd = op.forward(Xd)
-        gd = op.calc_gradg(Pd).cpu().numpy()[0]
-        proxd = reg.proxf(Xd).cpu().numpy()[0]
+        assert Pd.shape == (1, wl.ndata)  # a one-chain batch stays a batch through both compositions
+        gd = op.calc_gradg(Pd).cpu().numpy().ravel()
+        proxd = reg.proxf(Xd).cpu().numpy().ravel()
         np.random.seed(12)
         Xn, Pn = m.iterate(Xd, Pd)
-        res[fuse] = (Pd.cpu().numpy()[0], gd, proxd, Xn.cpu().numpy()[0], Pn.cpu().numpy()[0], op._diag)
+        res[fuse] = (Pd.cpu().numpy().ravel(), gd, proxd, Xn.cpu().numpy().ravel(), Pn.cpu().numpy().ravel(), op._diag)
     P, gd, proxd, Xn, Pn, diag = res[True]
     # oracle: the three O(L^3) evaluations are independent given the device's X, P and X' (all of them compared below)
     invcov = R.inverse_covariance(data, sig)

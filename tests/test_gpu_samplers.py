@@ -1,0 +1,291 @@
+"""GPU tests of the sampler machinery added in round 2 (run on the B200 box: `pytest -m gpu`): PxMALA runs longer than
+its device-side trace rings, checkpoint / resume of every sampler, CUDA graphs that advance the chain in place, user
+subclasses of the prior, complex SKROCK noise, quantiles of long chains."""
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def px():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pxmcmc_b200 import forward, mcmc, measurements, prior, sht, transforms, uncertainty, utils
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.forward, ns.mcmc, ns.measurements, ns.prior, ns.sht, ns.transforms, ns.utils, ns.uncertainty = (
+        forward, mcmc, measurements, prior, sht, transforms, utils, uncertainty)
+    return ns
+
+
+def _pxmala(px, nsamples, nburn, ngap, noise="device", L=10, nchains=1, track=("logposterior", "chain")):
+    B, J = 2.0, 2
+    rng = np.random.default_rng(41)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.05, "analysis", L, B, J, nchains=nchains)
+    p = px.mcmc.PxMCMCParams(nsamples=nsamples, nburn=nburn, ngap=ngap, delta=2e-3, lmda=1e-2, mu=2.0, verbosity=0,
+                             track=list(track))
+    reg = px.prior.L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu)
+    return px.mcmc.PxMALA(op, reg, p, tune_delta=True, noise=noise, seed=77, stream0=2, nchains=nchains)
+
+
+def test_pxmala_trace_rings_wrap_and_drain(px):
+    """the device-resident loop keeps its acceptance / step-size traces in rings that are drained to the host when
+    full: a run with 37-slot rings (several wraps, a partial last ring) gives the traces of a run that never wraps"""
+    start = np.random.default_rng(3).laplace(size=190) * 0.1
+    a = _pxmala(px, 6, 150, 5)
+    a.run(start)
+    b = _pxmala(px, 6, 150, 5)
+    b.trace_ring = 37
+    b.run(start)
+    assert len(a.acceptance_trace) > 4 * 37
+    assert a.acceptance_trace == b.acceptance_trace and a.deltas_trace == b.deltas_trace
+    assert len(a.deltas_trace) == len(a.acceptance_trace) + 1
+    assert np.array_equal(a.chain, b.chain) and np.array_equal(a.logPi, b.logPi)
+
+
+def test_pxmala_seventy_thousand_iterations(px):
+    """more iterations than one trace ring holds (65 536): the reference's drivers run nburn = 10^7
+    (experiments/weaklensing/main.py:110-119); round 1 aborted here"""
+    m = _pxmala(px, 2, 70000, 1, track=("logposterior",))
+    assert m._device_resident() and m.trace_ring == 1 << 16
+    m.run(np.random.default_rng(3).laplace(size=190) * 0.1)
+    n = len(m.acceptance_trace)
+    assert n > 70000 and len(m.deltas_trace) == n + 1
+    assert 0.05 < np.mean(m.acceptance_trace) < 0.99
+    assert set(m.acceptance_trace) == {0, 1} and all(np.isfinite(m.deltas_trace)) and np.isfinite(m.logPi).all()
+    # the tuned step stays in the reference's clip interval (mcmc.py:277-279)
+    assert min(m.deltas_trace) >= m.lmda * 1e-8 and max(m.deltas_trace) <= m.lmda / 2
+
+
+@pytest.mark.parametrize("noise", ["device", "host"])
+def test_pxmala_checkpoint_resume_continues_the_same_chain(px, noise, tmp_path):
+    """both PxMALA loops (device-resident with Philox noise; host-synchronised with numpy's RNG): a run stopped at a
+    checkpoint and resumed by a NEW sampler object reproduces the uninterrupted run bit for bit -- state, traces,
+    step size, tracked samples"""
+    start = np.random.default_rng(3).laplace(size=190) * 0.1
+    np.random.seed(5)
+    full = _pxmala(px, 8, 6, 3, noise=noise)
+    full.trace_ring = 16
+    full.run(start)
+    np.random.seed(5)
+    first = _pxmala(px, 8, 6, 3, noise=noise)
+    first.trace_ring = 16
+    first.nsamples = 4
+    ck = str(tmp_path / "pxmala.npz")
+    first.run(start, checkpoint=ck, checkpoint_every=7)
+    np.random.seed(999)
+    second = _pxmala(px, 8, 6, 3, noise=noise)
+    second.trace_ring = 16
+    second.run(resume=ck)
+    assert list(second.acceptance_trace) == list(full.acceptance_trace)
+    assert list(second.deltas_trace) == list(full.deltas_trace)
+    assert np.array_equal(second.chain, full.chain) and np.array_equal(second.logPi, full.logPi)
+    assert second.delta == full.delta
+    with pytest.raises(ValueError):
+        px.mcmc.MYULA(full.forward, full.prior, px.mcmc.PxMCMCParams(nsamples=1, verbosity=0), noise=noise).run(resume=ck)
+
+
+@pytest.mark.parametrize("noise", ["device", "host"])
+def test_skrock_checkpoint_resume_continues_the_same_chain(px, noise, tmp_path):
+    L, B, J, s_ = 12, 2.0, 2, 3
+    rng = np.random.default_rng(8)
+    npix = L * (2 * L - 1)
+    A = sparse.random(40, npix, density=0.05, random_state=3, format="csr")
+    y = rng.standard_normal(40)
+
+    def make(nsamples):
+        prm = px.mcmc.PxMCMCParams(delta=1e-7, lmda=5e-8, mu=1.0, s=s_, verbosity=0, nsamples=nsamples, nburn=1, ngap=2,
+                                   track=["logposterior", "L2", "prior", "chain", "predictions"])
+        op = px.forward.PathIntegralOperator(A, y, 0.1, "synthesis", L, B, J)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 5e-8, L=L, B=B, J_min=J)
+        return px.mcmc.SKROCK(op, reg, prm, noise=noise, seed=11, stream0=1)
+
+    start = rng.laplace(size=make(1).forward.nparams) * 0.01
+    np.random.seed(3)
+    full = make(5)
+    full.run(start)
+    np.random.seed(3)
+    first = make(5)
+    first.nsamples = 2
+    ck = str(tmp_path / "skrock.npz")
+    first.run(start, checkpoint=ck, checkpoint_every=2)
+    np.random.seed(4242)
+    second = make(5)
+    second.run(resume=ck)
+    assert np.array_equal(second.chain, full.chain) and np.array_equal(second.logPi, full.logPi)
+    assert np.array_equal(second.preds, full.preds)
+
+
+def test_graphed_chains_advance_in_place(px):
+    """CUDA-graph replays write the new state and predictions straight into the buffers they started from (update
+    kernel and the operator's last kernel): same chain as the eager loop, no copy-back kernels in the graph"""
+    import torch
+
+    from pxmcmc_b200 import device as D
+
+    L, B, J, nch = 24, 1.5, 2, 3
+    rng = np.random.default_rng(10)
+    data = rng.standard_normal(L * (2 * L - 1)) + 1j * rng.standard_normal(L * (2 * L - 1))
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.3, "synthesis", L, B, J, nchains=nch)
+    prm = px.mcmc.PxMCMCParams(delta=1e-5, lmda=2e-5, mu=1.0, verbosity=0, nsamples=1, track=[])
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 2e-5, L=L, B=B, J_min=J)
+    X0 = D.to_dev_c(rng.laplace(size=(nch, op.nparams)))
+    P0 = D.to_dev_c(op.forward(X0))
+    eager = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
+    graphed = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
+    chain = graphed.capture(X0, P0, iterations=2)
+    ptrs = (chain.X.data_ptr(), chain.P.data_ptr())
+    x, p = X0, P0
+    for _ in range(3):
+        for _ in range(2):
+            x, p = eager.iterate(x, p)
+        chain.step()
+        assert torch.equal(chain.state()[0], x) and torch.equal(chain.state()[1], p)
+    assert (chain.X.data_ptr(), chain.P.data_ptr()) == ptrs
+    # kernels of one replay: only libpxmcmc_b200 kernels (no ATen copy / fill kernels)
+    try:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            chain.step()
+            torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+    except Exception as exc:  # noqa: BLE001  (no CUPTI on the box: the equality above still holds)
+        pytest.skip(f"kernel names unavailable: {exc}")
+    kernels = [n for n in names if "memcpy" not in n.lower() and "memset" not in n.lower()]
+    assert kernels, names
+    assert not [n for n in names if "at::" in n or "memcpy" in n.lower()], names
+
+
+def test_output_placement_falls_back_to_a_copy(px):
+    """`_forward_dev(out=...)` with an operator whose result does not come from the library's allocator (here: a user
+    measurement in numpy) still leaves the predictions in `out`"""
+    from pxmcmc_b200 import device as D
+
+    class Twice(px.measurements.Measurement):
+        def forward(self, X):
+            return 2 * X
+
+        def adjoint(self, Y):
+            return 2 * Y
+
+    n = 50
+    op = px.forward.ForwardOperator(np.zeros(n), 1.0, "analysis", transform=px.transforms.IdentityTransform(),
+                                    measurement=Twice(n, n), nparams=n)
+    m = px.mcmc.MYULA(op, px.prior.L1("analysis", lambda v: v, lambda v: v, 0.1),
+                      px.mcmc.PxMCMCParams(nsamples=1, verbosity=0, track=[]))
+    X = D.to_dev_c(np.arange(n, dtype=float)[None, :])
+    out = D.to_dev_c(np.zeros((1, n)))
+    r = m._forward_dev(X, out=out)
+    assert r.data_ptr() == out.data_ptr() and np.array_equal(out.cpu().numpy()[0], 2.0 * np.arange(n))
+
+
+def test_user_prior_subclass_is_not_bypassed(px):
+    """a subclass of L1 that overrides `proxf` / `prior` (the reference's extension pattern) is called through its own
+    methods: the fused soft threshold and the device reduction are only taken for the library's implementations"""
+    from pxmcmc_b200.prior import is_library_l1
+
+    L, B, J = 10, 2.0, 2
+    rng = np.random.default_rng(6)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.5, "synthesis", L, B, J)
+
+    class HalfProx(px.prior.L1):
+        def proxf(self, X):
+            return 0.5 * np.asarray(X)
+
+        def prior(self, X):
+            return 3.0 * float(np.sum(np.abs(X) ** 2))
+
+    prm = px.mcmc.PxMCMCParams(delta=1e-3, lmda=2e-3, mu=1.5, verbosity=0, nsamples=1, track=[])
+    lib_prior = px.prior.L1("synthesis", None, None, 0.1)
+    mine = HalfProx("synthesis", None, None, 0.1)
+    assert is_library_l1(lib_prior) and not is_library_l1(mine)
+    assert is_library_l1(px.prior.S2_Wavelets_L1_Power_Weights("synthesis", None, None, 0.1, L=L, B=B, J_min=J))
+    m = px.mcmc.MYULA(op, mine, prm)
+    assert m._fused_prox() is None and not m._native()
+    X = rng.laplace(size=op.nparams)
+    P = op.forward(X)
+    np.random.seed(2)
+    w = np.random.randn(op.nparams)
+    np.random.seed(2)
+    Xn, _ = m.iterate(m._state(X), m._state(P))
+    expect = (1 - 0.5) * X + 0.5 * (0.5 * X) - 1e-3 * op.calc_gradg(P) + np.sqrt(2e-3) * w
+    assert rel_l2(Xn.cpu().numpy()[0], expect) < 1e-13
+    lp, l2, pr = m.logpi(X, P)
+    assert np.isclose(pr, 3.0 * np.sum(np.abs(X) ** 2), rtol=1e-13) and np.isclose(lp, -1.5 * pr - l2, rtol=1e-13)
+    # PxMALA with such a prior runs the host-synchronised loop
+    pm = px.mcmc.PxMALA(op, mine, prm, noise="device")
+    assert not pm._device_resident()
+
+
+def test_skrock_complex_noise(px):
+    """`complex=True`: Z = randn + 1j randn drawn real part first (pxmcmc/mcmc.py:344-347); host-noise step against the
+    oracle recursion, and the device-noise step runs"""
+    from oracle import pxmcmc_ref as R
+
+    L, B, J, s_ = 10, 2.0, 2, 3
+    rng = np.random.default_rng(12)
+    data = rng.standard_normal(L * (2 * L - 1)) + 1j * rng.standard_normal(L * (2 * L - 1))
+    op = px.forward.SphericalWaveletTransformOperator(data, 0.2, "synthesis", L, B, J)
+    prm = px.mcmc.PxMCMCParams(delta=1e-6, lmda=5e-7, mu=1.0, s=s_, complex=True, verbosity=0, nsamples=1, track=[])
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 5e-7, L=L, B=B, J_min=J)
+    m = px.mcmc.SKROCK(op, reg, prm)
+    X = rng.laplace(size=op.nparams) + 1j * rng.laplace(size=op.nparams)
+    np.random.seed(4)
+    Z = np.random.randn(op.nparams) + 1j * np.random.randn(op.nparams)
+    np.random.seed(4)
+    Xn = m.chain_step(X)
+    t = R.WaveletTransform(L, B, J)
+    oop = R.ForwardOperator(data, 0.2, "synthesis", t, R.IdentityMeasurement(data.size, data.size), t.ncoefs)
+    oprior = R.S2WaveletsL1("synthesis", t.inverse, t.inverse_adjoint, 5e-7, L, B, J)
+    assert rel_l2(Xn, R.skrock_step(oop, oprior, 1e-6, 5e-7, s_, X, Z)) < TOL
+    md = px.mcmc.SKROCK(op, reg, prm, noise="device", seed=1)
+    out = md.chain_step(X)
+    assert np.isfinite(out).all() and np.abs(out.imag - X.imag).max() > 0
+
+
+def test_pxmala_transition_sums_are_reduced_over_ranks_before_squaring(px):
+    """m-sharded operators: every rank holds a partial sum of (X2 - X1 - (delta/2) grad log pi)^2; the reference squares
+    the TOTAL again (mcmc.py:286-289), and the accept test must use one uniform on all ranks"""
+    import torch
+
+    m = _pxmala(px, 1, 0, 1, noise="host")
+    rng = np.random.default_rng(2)
+    X1, X2, pr, g = (rng.standard_normal(190) + 1j * rng.standard_normal(190) for _ in range(4))
+    plain = m.calc_logtransition(X1, X2, pr, g)
+    m.forward._pxm_allreduce = lambda t: 2 * t  # two ranks holding identical halves
+    try:
+        assert np.isclose(m.calc_logtransition(X1, X2, pr, g), 4 * plain, rtol=1e-14)
+        np.random.seed(1)
+        u = np.random.rand()
+        np.random.seed(1)
+        assert m._shared_uniform() == 2 * u  # the (fake) reduction was applied to the draw
+        assert not torch.distributed.is_initialized()
+    finally:
+        del m.forward._pxm_allreduce
+
+
+def test_credible_interval_of_a_long_chain(px):
+    """more samples than the shared-memory sort holds (16 384): same values as numpy's quantile"""
+    rng = np.random.default_rng(5)
+    chain = rng.standard_normal((20000, 37))
+    ours = px.uncertainty.credible_interval_range(chain, alpha=0.1)
+    ref = np.quantile(chain, 0.95, axis=0) - np.quantile(chain, 0.05, axis=0)
+    assert np.array_equal(ours, ref)
+    import torch
+
+    ours_d = px.uncertainty.credible_interval_range(torch.from_numpy(chain).cuda(), alpha=0.1)
+    assert np.allclose(ours_d.cpu().numpy(), ref, rtol=1e-14, atol=0)
