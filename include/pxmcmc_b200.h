@@ -207,6 +207,21 @@ int pxm_real_to_complex(const double* d_x, void* d_out, long long total, void* s
 int pxm_csr_spmv(const int* d_indptr, const int* d_indices, const double* d_vals, const void* d_x, void* d_y,
                  int nrows, long long ncols, long long nchains, void* stream);
 
+/* ---- great-circle path matrix (data preparation of the phase-velocity experiment) ----------
+ * Replaces greatcirclepaths.GreatCirclePath(start, stop, "MW", L=L, weighting="average", latlon=True)
+ * .get_points(points_per_rad).fill() of experiments/phasevel/main.py:40-47.  d_start / d_stop: [npaths][2]
+ * (latitude, longitude) in degrees.  pxm_gc_count_points: points per path = max(2, ceil(points_per_rad *
+ * distance)).  pxm_gc_rasterise: one CTA per path; row r of d_cols / d_w ([npaths][cap], cap a power of two >=
+ * every point count) receives the sorted distinct MW pixels t (2L-1) + p the path visits and their share of the
+ * path's points (a row sums to one), padded with -1; d_nnz[r] = number of pixels.  pxm_gc_compact packs the
+ * padded rows into CSR arrays given the exclusive prefix sum d_indptr[npaths + 1] of d_nnz. */
+int pxm_gc_count_points(const double* d_start, const double* d_stop, long long npaths, double points_per_rad,
+                        int* d_npoints, void* stream);
+int pxm_gc_rasterise(const double* d_start, const double* d_stop, long long npaths, int L, double points_per_rad,
+                     int cap, int* d_cols, double* d_w, int* d_nnz, void* stream);
+int pxm_gc_compact(const long long* d_indptr, const int* d_cols, const double* d_w, int cap, long long npaths,
+                   int* d_indices, double* d_data, void* stream);
+
 /* ---- uncertainty quantification ---------------------------------------------
  * credible_interval_range (pxmcmc/uncertainty.py:7-16): two quantiles of every column of a stored
  * chain [nsamples][ld] of doubles, numpy's default "linear" method.  The caller passes, for each

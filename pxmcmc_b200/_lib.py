@@ -79,6 +79,9 @@ SIGNATURES = {
     "pxm_masked_scatter": (_i, [_vp, _vp, _vp, _vp, _ll, _ll, _ll, _vp]),
     "pxm_real_to_complex": (_i, [_vp, _vp, _ll, _vp]),
     "pxm_csr_spmv": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _vp]),
+    "pxm_gc_count_points": (_i, [_vp, _vp, _ll, _d, _vp, _vp]),
+    "pxm_gc_rasterise": (_i, [_vp, _vp, _ll, _i, _d, _i, _vp, _vp, _vp, _vp]),
+    "pxm_gc_compact": (_i, [_vp, _vp, _vp, _i, _ll, _vp, _vp, _vp]),
     "pxm_quantile_columns": (_i, [_vp, _ll, _ll, _ll, _ll, _d, _ll, _d, _vp, _vp, _vp]),
     "pxm_quantile_columns_max_samples": (_i, []),
     "pxm_profile_begin": (_i, [_i]),

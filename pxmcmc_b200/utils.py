@@ -355,3 +355,10 @@ def alm2map(alm, nside, **kwargs):
     L = lmax + 1
     plan = _HealpixPlan.get(int(nside), L)
     return D.to_host(plan.synth(D.to_dev_c(lm_hp2lm(alm, L)))).real.copy()
+
+
+def build_mask(L, size=20):
+    """galactic-plane + ecliptic mask on the MW grid (pxmcmc/utils.py:320-349); see ``ingest.build_mask``"""
+    from .ingest import build_mask as _bm
+
+    return _bm(L, size)
