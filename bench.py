@@ -162,7 +162,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value_at_L, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * mean_it * scale, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MYULA L={args.L} B={args.B} J_min={args.J_min} synthesis, S2_Wavelets_L1, CPU oracle port"},
+        "config": {"workload": f"MYULA L={args.L} B={args.B} J_min={args.J_min} synthesis, Identity measurement, S2_Wavelets_L1 (CPU: numpy port of the reference Python layer over a restatement of ssht/s2let)"},
         "cpu_baseline": {"value": value_at_L, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value_at_L, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
@@ -186,45 +186,110 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
-def run_ours(args):
+def csrc_sha():
+    """hash of the kernel sources: ncu-derived numbers quoted by the bench line say which sources they were measured on"""
+    import hashlib
+
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "pxmcmc_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def load_traffic():
+    """DRAM traffic per launch of the dominant kernels from the tracked ncu summary profiles/traffic_r2.json
+    (regenerated by scripts/refresh_traffic.py under ncu); `current` says whether the kernels have changed since"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r2.json")))
+    except Exception:  # noqa: BLE001
+        return {}, {"file": None, "current": False}
+    return t, {"file": "profiles/traffic_r2.json", "csrc_sha": t.get("csrc_sha"), "current": t.get("csrc_sha") == csrc_sha()}
+
+
+class Ctx:
+    """rank bookkeeping + the collectives the measurement itself needs (barrier, max over ranks)"""
+
+    def __init__(self):
+        import torch
+
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.cpus = bind_to_gpu_numa_node(self.local)
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+
+            # stdout carries ONE JSON line: NCCL's own log (version banner, NCCL_DEBUG=INFO topology / comm lines) goes to
+            # stderr instead of being switched off
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor([float(v) for v in vals], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+def release_plans():
+    """drop the cached plans (Legendre tables) of a finished workload"""
+    import gc
+
     import torch
-    import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    cpus = bind_to_gpu_numa_node(local)
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout at VERSION/WARN level: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pxmcmc_b200 import device as D
 
+    D.WaveletPlan._cache.clear()
+    D.ShtPlan._cache.clear()
+    D._scratch.clear()
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=100, e2e_steps=0):
+    """`steps` MYULA iterations of `nch` chains on this GPU (config 5 / the BASELINE metric): device-resident value, per-stage
+    device times, optional sustained blocks and the end-to-end figure through host buffers.  Chain c of the job draws
+    Philox stream c whatever the sharding."""
+    import ctypes as C
+
+    torch = ctx.torch
     from pxmcmc_b200 import _lib, device as D, sht
     from pxmcmc_b200.forward import SphericalWaveletTransformOperator
     from pxmcmc_b200.mcmc import MYULA, PxMCMCParams
     from pxmcmc_b200.prior import S2_Wavelets_L1
-    import ctypes as C
+    from pxmcmc_b200.sharding import philox_stream0
 
-    L, B, J_min, nch = args.L, args.B, args.J_min, args.chains
+    L, B, J_min = args.L, args.B, args.J_min
     data = sht.inverse(synthetic_flm(L), L).ravel()
     data = data / np.sqrt(np.mean(np.abs(data) ** 2))  # complex, as on the reference's HEALPix path
     op = SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J_min, nchains=nch)
     prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, track=[])
     reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J_min)
-    from pxmcmc_b200.sharding import philox_stream0
-    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234, stream0=philox_stream0(nch * world, world, rank))
+    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234, stream0=philox_stream0(total_chains, ctx.world, ctx.rank))
     ncoef, npix = op.nparams, L * (2 * L - 1)
-    rng = np.random.default_rng(7 + rank)
+    rng = np.random.default_rng(7 + ctx.rank)
     X = D.to_dev_c(rng.laplace(size=(nch, ncoef)))
     P = D.to_dev_c(op.forward(X))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput -----------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         X, P = m.iterate(X, P)
     # the GPU leaves its idle clocks only after some tens of ms of load: keep iterating (untimed)
     # until 0.3 s have passed so that the timed region starts at the sustained clock
@@ -232,131 +297,333 @@ def run_ours(args):
     while time.perf_counter() - t_w < 0.3:
         X, P = m.iterate(X, P)
         torch.cuda.synchronize()
-    barrier()
-    sampler = ClockSampler(local)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     l0 = _lib.lib.pxm_launch_count()
-    _lib.check(_lib.lib.pxm_profile_begin(16 * args.steps + 64))
+    _lib.check(_lib.lib.pxm_profile_begin(16 * steps + 64))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         X, P = m.iterate(X, P)
     e1.record()
-    barrier()
+    ctx.barrier()
     ms = e0.elapsed_time(e1)
     ms_kind = (C.c_double * 3)()
     cnt_kind = (C.c_longlong * 3)()
     _lib.check(_lib.lib.pxm_profile_end(ms_kind, cnt_kind))
     launches = _lib.lib.pxm_launch_count() - l0
+    ms, leg, fft, el = ctx.reduce([ms, ms_kind[0], ms_kind[1], ms_kind[2]])
+    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches),
+           "stage_ms": {"legendre": leg / steps, "ring_fft": fft / steps, "elementwise": el / steps},
+           "counts": [int(c) for c in cnt_kind], "table_bytes": int(op.transform._plan(nch).table_bytes)}
+    # sustained rate: `blocks` blocks of `block_iters` iterations, each timed on the device; median over blocks of the
+    # max over ranks (>= 1000 iterations, median of 5)
+    if blocks:
+        per_block = []
+        for _ in range(blocks):
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.barrier()
+            b0.record()
+            for _ in range(block_iters):
+                X, P = m.iterate(X, P)
+            b1.record()
+            ctx.barrier()
+            per_block.append(ctx.reduce([b0.elapsed_time(b1)])[0] / block_iters)
+        out["sustained_ms_per_step"] = float(np.median(per_block))
+        out["sustained_blocks_ms_per_step"] = [round(v, 5) for v in per_block]
     sampler.stop_flag = True
     sampler.join(timeout=2)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    finite = bool(torch.isfinite(torch.view_as_real(X)).all().item())
+    out["clocks"] = sampler.summary()
+    out["finite"] = bool(torch.isfinite(torch.view_as_real(X)).all().item())
+    # ---- end to end through pinned host buffers, rank-local -------------------------------------------------
+    if e2e_steps:
+        Xh = torch.empty((nch, ncoef), dtype=torch.complex128).pin_memory()
+        Ph = torch.empty((nch, npix), dtype=torch.complex128).pin_memory()
+        Xh.copy_(X.cpu())
+        Ph.copy_(P.cpu())
+        Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
+        m.iterate_host(Xh, Ph, Xo, Po)  # warm-up
+        ctx.barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        w0.record()
+        for _ in range(e2e_steps):
+            m.iterate_host(Xh, Ph, Xo, Po)
+            Xh, Xo = Xo, Xh
+            Ph, Po = Po, Ph
+        w1.record()
+        torch.cuda.synchronize()
+        e2e_s = max(w0.elapsed_time(w1) / 1e3, time.perf_counter() - t0)
+        out["e2e_s"] = ctx.reduce([e2e_s])[0]
+        out["e2e_steps"] = e2e_steps
+        out["e2e_bytes"] = (ncoef + npix) * nch * 16
+        del Xh, Ph, Xo, Po
+    del m, op, reg, X, P
+    return out
 
-    # ---- FP64 peak for the roofline: cuBLAS DGEMM measured right here ------------------------
-    def dgemm_peak():
-        n = 6144
-        a = torch.randn(n, n, dtype=torch.float64, device="cuda")
-        b = torch.randn(n, n, dtype=torch.float64, device="cuda")
-        torch.matmul(a, b)
-        best = 1e9
-        for _ in range(4):
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s0.record()
-            torch.matmul(a, b)
-            s1.record()
-            torch.cuda.synchronize()
-            best = min(best, s0.elapsed_time(s1))
-        return 2.0 * n ** 3 / best / 1e9  # TFLOP/s
 
-    # ---- end-to-end through host buffers (pinned), rank-local ----------------------------------
-    e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    Xh = torch.empty((nch, ncoef), dtype=torch.complex128).pin_memory()
-    Ph = torch.empty((nch, npix), dtype=torch.complex128).pin_memory()
-    Xh.copy_(X.cpu())
-    Ph.copy_(P.cpu())
-    Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
-    m.iterate_host(Xh, Ph, Xo, Po)  # warm-up
-    barrier()
-    w0 = torch.cuda.Event(enable_timing=True)
-    w1 = torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    w0.record()
-    for _ in range(e2e_steps):
-        m.iterate_host(Xh, Ph, Xo, Po)
-        Xh, Xo = Xo, Xh
-        Ph, Po = Po, Ph
-    w1.record()
+def measure_single_chain(ctx, args, iters=500):
+    """per-chain latency: ONE MYULA chain at the bench bandlimit, the iteration replayed as one CUDA graph
+    (`MYULA.run`'s path for device noise) -- the "per chain" half of the BASELINE metric"""
+    torch = ctx.torch
+    from pxmcmc_b200 import device as D, sht
+    from pxmcmc_b200.forward import SphericalWaveletTransformOperator
+    from pxmcmc_b200.mcmc import MYULA, PxMCMCParams
+    from pxmcmc_b200.prior import S2_Wavelets_L1
+
+    L, B, J_min = args.L, args.B, args.J_min
+    data = sht.inverse(synthetic_flm(L), L).ravel()
+    data = data / np.sqrt(np.mean(np.abs(data) ** 2))
+    op = SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J_min)
+    prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, track=[])
+    reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 1e-6, L=L, B=B, J_min=J_min)
+    m = MYULA(op, reg, prm, noise="device", seed=99)
+    X = D.to_dev_c(np.random.default_rng(0).laplace(size=(1, op.nparams)))
+    P = D.to_dev_c(op.forward(X))
+    chain = m.capture(X, P, iterations=1)
+    for _ in range(50):
+        chain.step()
     torch.cuda.synchronize()
-    e2e_s = max(w0.elapsed_time(w1) / 1e3, time.perf_counter() - t0)
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    h2d = (ncoef + npix) * nch * 16
-    d2h = (ncoef + npix) * nch * 16
+    per = []
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters // 5):
+            chain.step()
+        b.record()
+        torch.cuda.synchronize()
+        per.append(a.elapsed_time(b) / (iters // 5))
+    ms_it = float(np.median(per))
+    tb = int(op.transform._plan(1).table_bytes)
+    chain.release()
+    del chain, m, op
+    return {"iterations_per_s": 1e3 / ms_it, "ms_per_iteration": ms_it, "iterations_timed": iters,
+            "mode": "one chain, iteration replayed as one CUDA graph (in-place state), Philox noise; median of 5 blocks",
+            "table_bytes_streamed_per_iteration": 2 * tb}
 
-    if rank == 0:
-        peak = dgemm_peak()
-        try:
-            hbm_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-        except Exception:  # noqa: BLE001
-            hbm_peak = 6650.0  # fallback stated in B200_PROFILING.md
+
+def measure_configs(ctx, args):
+    """the BASELINE.json configurations that are parity-test cases (tests/test_gpu_configs.py) timed on one GPU:
+    config 1 (MYULA L=32), config 2 (PxMALA, analysis prior, L=256), config 3 (SKROCK s=10, great-circle CSR, L=128)"""
+    torch = ctx.torch
+    from pxmcmc_b200 import _lib, device as D, paths, sht
+    from pxmcmc_b200.forward import PathIntegralOperator, SphericalWaveletTransformOperator
+    from pxmcmc_b200.mcmc import MYULA, PxMALA, SKROCK, PxMCMCParams
+    from pxmcmc_b200.prior import L1, S2_Wavelets_L1, S2_Wavelets_L1_Power_Weights
+
+    def data_map(L):
+        d = sht.inverse(synthetic_flm(L), L).ravel()
+        return d / np.sqrt(np.mean(np.abs(d) ** 2))
+
+    def timed(fn, n, warm=10):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    out = {}
+    # config 1
+    L, B = 32, 1.5
+    op = SphericalWaveletTransformOperator(data_map(L), 1.0, "synthesis", L, B, 2)
+    prm = PxMCMCParams(delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, nsamples=1, track=[])
+    reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 1e-6, L=L, B=B, J_min=2)
+    m = MYULA(op, reg, prm, noise="device")
+    X = D.to_dev_c(np.random.default_rng(0).laplace(size=(1, op.nparams)))
+    chain = m.capture(X, D.to_dev_c(op.forward(X)), iterations=1)
+    ms_it = timed(chain.step, 2000)
+    chain.release()
+    out["config1_myula_L32"] = {"ms_per_iteration": ms_it, "iterations_per_s": 1e3 / ms_it, "mode": "CUDA graph replay"}
+    # config 2
+    L, B = 256, 1.5
+    op = SphericalWaveletTransformOperator(data_map(L), 0.1, "analysis", L, B, 2)
+    prm = PxMCMCParams(delta=1e-7, lmda=1e-6, mu=1.0, verbosity=0, nsamples=5, nburn=0, ngap=100, track=["logposterior"])
+    reg = L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, 1e-6)
+    PxMALA(op, reg, PxMCMCParams(delta=1e-7, lmda=1e-6, mu=1.0, verbosity=0, nsamples=1, nburn=0, ngap=1, track=[]),
+           tune_delta=True, noise="device", seed=3).run(np.zeros(op.nparams))  # plans, tables
+    m = PxMALA(op, reg, prm, tune_delta=True, noise="device", seed=3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.run(np.zeros(op.nparams))
+    torch.cuda.synchronize()
+    nit = len(m.acceptance_trace)
+    dt = (time.perf_counter() - t0) / nit
+    out["config2_pxmala_analysis_L256"] = {"ms_per_iteration": dt * 1e3, "iterations_per_s": 1 / dt, "iterations": nit,
+                                           "acceptance": float(np.mean(m.acceptance_trace)),
+                                           "mode": "device-resident loop (accept test, step-size tuning, traces on the device), CUDA graph, "
+                                                   "wall clock of run() incl. the host reads on the thinning grid"}
+    del m, op, reg
+    # config 3
+    L, B, s = 128, 2, 10
+    rng = np.random.default_rng(7)
+    z = rng.uniform(-1, 1, size=(10000, 2))
+    lon = rng.uniform(-180, 180, size=(10000, 2))
+    lat = np.degrees(np.arcsin(z))
+    t0 = time.perf_counter()
+    A, (ip_d, ix_d, v_d) = paths.get_path_matrix(np.stack([lat[:, 0], lon[:, 0]], 1), np.stack([lat[:, 1], lon[:, 1]], 1), L,
+                                                 device_csr=True)
+    t_raster = time.perf_counter() - t0
+    truth = data_map(L).real
+    y = A @ truth + 0.05 * rng.standard_normal(A.shape[0])
+    op = PathIntegralOperator(A, y, np.full(A.shape[0], 0.05), "synthesis", L, B, 2)
+    prm = PxMCMCParams(delta=1e-6, lmda=5e-7, mu=1.0, s=s, verbosity=0, nsamples=1, track=[])
+    reg = S2_Wavelets_L1_Power_Weights("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 5e-7, L=L, B=B, J_min=2, eta=1)
+    mg = SKROCK(op, reg, prm, noise="device", seed=5)
+    gr = mg.capture(D.to_dev_c(np.zeros((1, op.nparams))))
+    ms_step = timed(gr.step, 100)
+    # the path operator alone: warp-per-row CSR SpMV and its transpose, HBM roofline
+    xv = D.to_dev_c(rng.standard_normal(A.shape[1]) + 1j * rng.standard_normal(A.shape[1]))
+    yv = D.to_dev_c(rng.standard_normal(A.shape[0]) + 1j * rng.standard_normal(A.shape[0]))
+    ms_f = timed(lambda: op.measurement.forward(xv), 300)
+    ms_t = timed(lambda: op.measurement.adjoint(yv), 300)
+    nbytes = A.nnz * 12 + 16 * (A.shape[0] + A.shape[1]) + 4 * A.shape[0]
+    out["config3_skrock_pathintegral_L128"] = {
+        "ms_per_step": ms_step, "steps_per_s": 1e3 / ms_step, "gradient_evaluations_per_step": s, "mode": "one CUDA graph per step",
+        "path_matrix": {"shape": list(A.shape), "nnz": int(A.nnz), "rasterise_s": t_raster,
+                        "built_by": "pxm_gc_rasterise: 10^4 great circles between random end points (seed 7), 160 points/rad"},
+        "spmv": {"forward_us": ms_f * 1e3, "adjoint_us": ms_t * 1e3, "algorithmic_bytes": int(nbytes),
+                 "forward_GBps": nbytes / (ms_f / 1e3) / 1e9, "adjoint_GBps": nbytes / (ms_t / 1e3) / 1e9,
+                 "note": "nnz (8 + 4) + 16 (rows + cols) + 4 rows bytes; the matrix (11 MB) and both vectors are L2-resident "
+                         "between launches, so this is launch-latency / L2 bound, not an HBM stream"}}
+    del mg, gr, op, reg
+    return out
+
+
+def dgemm_peak(torch):
+    """FP64 peak for the Legendre roofline: cuBLAS DGEMM measured right here (MEASURED_PEAKS.json has no FP64 entry)"""
+    n = 6144
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    torch.matmul(a, b)
+    best = 1e9
+    for _ in range(4):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        torch.matmul(a, b)
+        s1.record()
+        torch.cuda.synchronize()
+        best = min(best, s0.elapsed_time(s1))
+    return 2.0 * n ** 3 / best / 1e9  # TFLOP/s
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback stated in B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def run_ours(args):
+    ctx = Ctx()
+    torch = ctx.torch
+    L, B, J_min, nch = args.L, args.B, args.J_min, args.chains
+    world = ctx.world
+    main = measure_chains(ctx, args, nch, nch * world, args.steps, blocks=args.blocks, block_iters=args.block_iters,
+                          e2e_steps=max(1, min(args.steps, args.e2e_steps)))
+    release_plans()
+    extras = {}
+    if world > 1 and not args.no_extras:
+        # config 5 as BASELINE.json words it: 64 chains in TOTAL, 64/N per GPU (strong scaling of the chain sweep)
+        total = args.strong_total
+        if total % world == 0:
+            st = measure_chains(ctx, args, total // world, total, args.steps, blocks=3, block_iters=args.block_iters)
+            release_plans()
+            ms_step = st.get("sustained_ms_per_step", st["ms"] / st["steps"])
+            extras["config5_strong"] = {
+                "workload": f"{total} MYULA chains in total at L={L} B={B}, {total // world} per GPU, no data-path collective",
+                "value": total / (ms_step / 1e3), "unit": UNIT, "scaling": "strong", "chains_per_gpu": total // world,
+                "ms_per_step": ms_step, "stage_ms_per_step_max_over_ranks": st["stage_ms"], "finite": st["finite"]}
+    if not args.no_extras:
+        # config 4: one weak-lensing chain at L=512 m-sharded over the GPUs of this launch (strong scaling)
+        a4 = argparse.Namespace(**vars(args))
+        a4.L, a4.B, a4.steps, a4.warmup = 512, 2.0, max(args.steps, 100), 3
+        wl = measure_msharded(ctx, a4, e2e=False)
+        release_plans()
+        if wl is not None:
+            extras["config4_msharded"] = {k: wl[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "config",
+                                                            "eager_ms_per_step", "stage_ms_per_step_max_over_ranks", "roofline",
+                                                            "finite", "peer_barrier_ok", "launch_mode")}
+    if ctx.rank == 0:
+        if world == 1 and not args.no_extras:
+            extras["per_chain_latency"] = measure_single_chain(ctx, args)
+            release_plans()
+            extras["configs"] = measure_configs(ctx, args)
+            release_plans()
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            try:
+                json.dump({k: extras[k] for k in ("per_chain_latency", "configs", "config4_msharded") if k in extras},
+                          open(os.path.join(ROOT, "gpurun_out", "config_timings.json"), "w"), indent=1)
+            except OSError:
+                pass
+        peak = dgemm_peak(torch)
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        traffic, tsrc = load_traffic()
+        default_wl = (L, B, J_min, nch) == (256, 1.5, 2, 64)
+        ncoef, npix, steps = main["ncoef"], main["npix"], main["steps"]
+        ms = main["ms"]
         flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
-        leg_ms, leg_n = ms_kind[0], cnt_kind[0]
-        achieved = flops_step * args.steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else None
-        fft_gbs = 2 * 32.0 * (ncoef + npix) * nch * args.steps / (ms_kind[1] / 1e3) / 1e9 if ms_kind[1] > 0 else None
+        st = main["stage_ms"]
+        leg_tf = flops_step / (st["legendre"] / 1e3) / 1e12 if st["legendre"] > 0 else None
+        fft_bytes_step = 2 * 32.0 * (ncoef + npix) * nch
+        fft_gbs = fft_bytes_step / (st["ring_fft"] / 1e3) / 1e9 if st["ring_fft"] > 0 else None
+        roof_fft = {"bound": "hbm", "kernel": "pxm_ring_fft3_kernel (persistent TMA-staged two-pass Bluestein ring FFT; 4 stages = "
+                                              "4 launches + 2 of pxm_ring_fft2_kernel<.,0> for lengths <= 256 per step)",
+                    "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
+                    # dram__bytes_read + dram__bytes_write per stage (mean of the 4 stages of one step), from the tracked ncu summary
+                    "traffic": traffic.get("ring_fft_bytes_per_stage") if default_wl else None,
+                    "launches_timed": main["counts"][1], "algorithmic_bytes_per_stage": fft_bytes_step / 4,
+                    "ms_per_step": st["ring_fft"], "peak_source": hbm_src,
+                    "note": "HBM class per SURVEY 8(d): algorithmic bytes = pixels or coefficients in + ring coefficients out = "
+                            "32 B x (ncoef + npix) per Psi per chain.  DRAM traffic = algorithmic bytes and HBM is ~20-25 % busy: the "
+                            "kernel is bound by the FP64 pipe (Bluestein: an odd ring length 2l-1 costs two power-of-two FFTs of length "
+                            ">= 2n), which DFMA shares with DMMA on this part (profiles/ubench_fp64_r1g.txt)"}
+        roof_leg = {"bound": "tensor", "achieved": leg_tf, "peak": peak, "unit": "TFLOP/s", "frac": (leg_tf / peak) if leg_tf else None,
+                    "traffic": traffic.get("legendre_bytes_per_launch") if default_wl else None,
+                    "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)", "launches_timed": main["counts"][0],
+                    "algorithmic_flops_per_launch": flops_step / 4, "ms_per_step": st["legendre"],
+                    "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"}
+        # `roofline` = the dominant kernel BY TIME of this run
+        fft_dominant = st["ring_fft"] >= st["legendre"]
         line = {
-            "metric": METRIC, "value": world * nch * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": world * nch * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"MYULA L={L} B={B} J_min={J_min} synthesis, Identity measurement, S2_Wavelets_L1, "
                                    f"{nch} independent chains per GPU (config 5 of BASELINE.json; per-chain it/s = value/(n_gpus*chains))",
                        "chains_per_gpu": nch, "ncoefs": ncoef, "npix": npix, "noise": "Philox4x32-10 in-kernel",
-                       "l2_note": f"per-step working set {(ncoef + npix) * nch * 16 * 3 / 2**20:.0f} MiB of state + "
-                                  f"{op.transform._plan(nch).table_bytes / 2**20:.0f} MiB of Legendre tables exceeds the 126 MB L2"},
-            "per_chain_iterations_per_s": args.steps / (ms / 1e3),
-            "gpu_launches": int(launches),
-            "finite": finite,
-            "stage_ms_per_step": {"legendre": leg_ms / args.steps, "ring_fft": ms_kind[1] / args.steps,
-                                  "elementwise": ms_kind[2] / args.steps},
-            # dominant kernel BY TIME: the ring FFT (HBM class per SURVEY 8(d): algorithmic bytes = pixels or
-            # coefficients in + ring coefficients out = 32 B x (ncoef + npix) per Psi per chain; 4 stages per step)
-            "roofline": {"bound": "hbm", "kernel": "pxm_ring_fft3_kernel (persistent TMA-staged two-pass Bluestein ring FFT; 4 stages = "
-                                                   "4 launches + 2 of pxm_ring_fft2_kernel<.,0> for lengths <= 256 per step)",
-                         "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
-                         # dram__bytes_read+write per stage (mean of the 4 stages of one step), ncu --set full capture
-                         # profiles/fft3_r1j_metrics.txt (only valid for the default workload)
-                         "traffic": 0.49e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
-                         "launches_timed": int(cnt_kind[1]),
-                         "algorithmic_bytes_per_stage": 32.0 * (ncoef + npix) * nch / 2,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)",
-                         "note": "DRAM traffic = algorithmic bytes, HBM ~20 % busy: the kernel is NOT memory bound. An odd ring length "
-                                 "2l-1 (511, 389, 259, ...) costs two power-of-two FFTs of length >= 2n (Bluestein) on the FP64 pipe, which DFMA "
-                                 "shares with DMMA on this part (profiles/ubench_fp64_r1g.txt): FP64 pipe 49-52 % busy at 2 warps per scheduler "
-                                 "(shared memory caps the kernel at 8 warps per SM); at 100 % of the pipe the stage would take ~0.6 ms = 0.55 "
-                                 "of the HBM roofline (profiles/fft3_r1j_metrics.txt)"},
-            # the O(L^3) stage: FP64 tensor-core (DMMA) Legendre contraction, against cuBLAS DGEMM measured in this run
-            "roofline_legendre": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                                  "frac": (achieved / peak) if achieved else None,
-                                  # dram__bytes_read+write per launch, mean of the 4 launches of one step (profiles/kernels_r1b_metrics.txt)
-                                  "traffic": 0.649e9 if (L, B, J_min, nch) == (256, 1.5, 2, 64) else None,
-                                  "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)",
-                                  "launches_timed": int(leg_n),
-                                  "algorithmic_flops_per_launch": flops_step / 4,
-                                  "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"},
-            "e2e": {"value": world * nch * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                       "l2_note": f"inputs larger than L2: per-step working set {(ncoef + npix) * nch * 16 * 3 / 2**20:.0f} MiB of state + "
+                                  f"{main['table_bytes'] / 2**20:.0f} MiB of Legendre tables exceeds the 126 MB L2"},
+            "per_chain_iterations_per_s": steps / (ms / 1e3),
+            "gpu_launches": main["launches"], "finite": main["finite"],
+            "stage_ms_per_step": st,
+            "roofline": dict(roof_fft if fft_dominant else roof_leg, dominant_by_time=True),
+            "roofline_ring_fft" if not fft_dominant else "roofline_legendre": roof_leg if fft_dominant else roof_fft,
+            "traffic_source": tsrc,
+            "e2e": {"value": world * nch * main["e2e_steps"] / main["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": main["e2e_bytes"],
+                    "d2h_bytes_per_step": main["e2e_bytes"], "steps": main["e2e_steps"],
                     "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host, "
-                           "chain groups pipelined over three streams (H2D | kernels | D2H); PCIe-bound"},
-            "clocks": sampler.summary(),
-            "host_cpus_rank0": f"{cpus[0]}-{cpus[-1]} ({len(cpus)})" if cpus else None,
+                           "chain groups pipelined over three streams (H2D | kernels | D2H); PCIe-bound" +
+                           ("; all ranks share the host's PCIe / memory bandwidth (one NUMA node): this figure does not scale with N" if world > 1 else "")},
+            "clocks": main["clocks"],
+            "host_cpus_rank0": f"{ctx.cpus[0]}-{ctx.cpus[-1]} ({len(ctx.cpus)})" if ctx.cpus else None,
         }
+        if "sustained_ms_per_step" in main:
+            line["sustained"] = {"value": world * nch / (main["sustained_ms_per_step"] / 1e3), "unit": UNIT,
+                                 "ms_per_step": main["sustained_ms_per_step"], "blocks": args.blocks, "iterations_per_block": args.block_iters,
+                                 "blocks_ms_per_step": main["sustained_blocks_ms_per_step"],
+                                 "note": "median over blocks of the max over ranks; the K-step `value` above is the contract's timed region"}
+        line.update(extras)
         if not args.no_cpu_baseline and world == 1:
             os.environ["PXM_ORACLE_REPS"] = "4"  # ~13 s of CPU work at L=256
             t_it = _oracle_one_iteration((args.ref_L, B, J_min, 0))
@@ -364,19 +631,16 @@ def run_ours(args):
             scale = algorithmic_flops_per_chain_iteration(L, B, J_min) / algorithmic_flops_per_chain_iteration(args.ref_L, B, J_min)
             line["cpu_baseline"] = {
                 "value": 1.0 / (t_it * scale), "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"4 consecutive chain-iterations of the numpy oracle at L={args.ref_L} ({t_it:.1f} s each on one core)"
+                "sample": f"4 consecutive chain-iterations of the numpy oracle (port of the reference's Python layer over a numpy "
+                          f"restatement of ssht / s2let; the real wheels are not installable here) at L={args.ref_L} ({t_it:.1f} s each on one core)"
                           + ("" if args.ref_L == L else f", scaled by the O(L^3) flop ratio {scale:.1f} to L={L}")}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.close()
 
 
 # ---------------------------------------------------------------------------------------
 # config 4 of BASELINE.json: ONE weak-lensing chain at L=512, m-sharded over the GPUs (strong scaling)
 # ---------------------------------------------------------------------------------------
-WL_TRAFFIC = 4.52e9  # dram bytes of the 4 Legendre launches of one iteration (profiles/legendre_wl_r1h_metrics.txt)
-
-
 def wl_mask(L):
     """equatorial band |90deg - theta| < 10deg plus the same band in a frame tilted by the
     ICRS->galactic pole angle (stand-in for utils.build_mask(L, 10))"""
@@ -397,19 +661,12 @@ def wl_flops_per_iteration(L, B, J_min):
     return algorithmic_flops_per_chain_iteration(L, B, J_min) + 2 * 4.0 * L * L * L + 2 * 4.0 * L * (L * L - 4)
 
 
-def run_msharded(args):
+def measure_msharded(ctx, args, e2e=True):
+    """-> the JSON line of the m-sharded weak-lensing workload on rank 0 (None elsewhere)"""
     import ctypes as C
 
-    import torch
-    import torch.distributed as dist
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    os.environ.pop("NCCL_DEBUG", None)  # NCCL prints its version banner on stdout at VERSION/WARN level: rank 0 prints ONE JSON line
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch = ctx.torch
+    world, rank = ctx.world, ctx.rank
     from pxmcmc_b200 import _lib, device as D
     from pxmcmc_b200 import msharded as ms
     from pxmcmc_b200.forward import ForwardOperator
@@ -436,31 +693,25 @@ def run_msharded(args):
     X = D.to_dev_c(np.zeros((1, op.nparams)))
     P = D.to_dev_c(op.forward(X))
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(args.warmup, 3)):
         X, P = m.iterate(X, P)
     # the GPU leaves its idle clocks only after some tens of ms of load: a fixed, rank-independent
     # number of extra untimed iterations (the ranks must issue identical call sequences)
     for _ in range(200):
         X, P = m.iterate(X, P)
-    barrier()
-    sampler = ClockSampler(local)
+    ctx.barrier()
+    sampler = ClockSampler(ctx.local)
     sampler.start()
     steps = args.steps
     l0 = _lib.lib.pxm_launch_count()
     _lib.check(_lib.lib.pxm_profile_begin(32 * steps + 64))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     e0.record()
     for _ in range(steps):
         X, P = m.iterate(X, P)
     e1.record()
-    barrier()
+    ctx.barrier()
     ms_total = e0.elapsed_time(e1)
     ms_kind = (C.c_double * 3)()
     cnt_kind = (C.c_longlong * 3)()
@@ -474,21 +725,18 @@ def run_msharded(args):
     chain = m.capture(X, P, iterations=1)
     for _ in range(20):
         chain.step()
-    barrier()
+    ctx.barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record()
     for _ in range(steps):
         chain.step()
     g1.record()
-    barrier()
+    ctx.barrier()
     ms_total = g0.elapsed_time(g1)
     X, P = chain.state()
     ok = tr.plan.barrier_ok() and wl.s0.barrier_ok() and wl.s2.barrier_ok()
     lp, l2, pr = m._logpi_dev(X, P)
-    stats = torch.tensor([ms_total, ms_kind[0], ms_kind[1], ms_kind[2], 0.0 if ok else 1.0, eager_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, leg_ms, fft_ms, el_ms, bad, eager_ms = [float(v) for v in stats.tolist()]
+    ms_total, leg_ms, fft_ms, el_ms, bad, eager_ms = ctx.reduce([ms_total, ms_kind[0], ms_kind[1], ms_kind[2], 0.0 if ok else 1.0, eager_ms])
     # Legendre tables streamed per iteration (harmonic-space composition of Phi o Psi): the kappa_j-weighted
     # quadrature tables W_j of the wavelet plan for Psi and again for Psi^dagger, the spin-2 Lambda table (half of
     # that SHT plan) for Phi and again for Phi^dagger; the wavelet plan's Lambda_L and the spin-0 plan are never read
@@ -496,27 +744,28 @@ def run_msharded(args):
     _lib.check(_lib.lib.pxm_wav_plan_table_bytes_by_family(tr.plan.h, fam))
     fused = op._fused()
     tab_bytes = 2 * fam[1] + wl.s2.table_bytes if fused else 2 * (fam[0] + fam[1]) + wl.s0.table_bytes + wl.s2.table_bytes
-    tab = torch.tensor([float(tab_bytes)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tab, op=dist.ReduceOp.SUM)
+    tab = ctx.reduce([float(tab_bytes)], op="sum")[0]
 
-    # end to end: the chain state travels host -> device -> host around every iteration
-    Xh, Ph = X.cpu().pin_memory(), P.cpu().pin_memory()
-    Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
-    m.iterate_host(Xh, Ph, Xo, Po)
-    barrier()
-    e2e_steps = max(1, min(steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    e2e_val, nbytes = None, 0.0
+    if e2e:
+        # end to end: the chain state travels host -> device -> host around every iteration
+        Xh, Ph = X.cpu().pin_memory(), P.cpu().pin_memory()
+        Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
         m.iterate_host(Xh, Ph, Xo, Po)
-        Xh, Xo, Ph, Po = Xo, Xh, Po, Ph
-    torch.cuda.synchronize()
-    e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    nbytes = torch.tensor([float((Xh.numel() + Ph.numel()) * 16)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-        dist.all_reduce(nbytes, op=dist.ReduceOp.SUM)
-
+        ctx.barrier()
+        e2e_steps = max(1, min(steps, 20))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            m.iterate_host(Xh, Ph, Xo, Po)
+            Xh, Xo, Ph, Po = Xo, Xh, Po, Ph
+        torch.cuda.synchronize()
+        e2e_s = ctx.reduce([time.perf_counter() - t0])[0]
+        nbytes = ctx.reduce([float((Xh.numel() + Ph.numel()) * 16)], op="sum")[0]
+        e2e_val = e2e_steps / e2e_s
+    chain.release()
+    hbm_peak, hbm_src = hbm_peak_gbs()
+    traffic, tsrc = load_traffic()
+    line = None
     if rank == 0:
         flops = wl_flops_per_iteration(L, B, J_min)
         line = {
@@ -528,33 +777,38 @@ def run_msharded(args):
                                    f"S2_Wavelets_L1, L={L} B={B} J_min={J_min}, ONE chain, azimuthal orders sharded over {world} GPU(s), "
                                    "theta<->m transposition fused into the Legendre contractions over NVLink peer memory",
                        "ncoefs": int(tr.ncoefs_global), "ndata": int(wl.ndata_global), "noise": "Philox4x32-10 in-kernel",
-                       "l2_note": f"Legendre tables streamed per iteration: {tab.item() / 2**20:.0f} MiB over all GPUs >> L2"},
+                       "l2_note": f"Legendre tables streamed per iteration: {tab / 2**20:.0f} MiB over all GPUs >> L2"},
             "gpu_launches": int(launches), "finite": bool(np.isfinite(lp).all() and abs(lp[0]) < 1e100), "peer_barrier_ok": bad == 0.0,
             "logposterior": float(np.real(lp[0])),
             "launch_mode": "one CUDA graph per iteration and rank (value); eager_ms_per_step = the same kernels launched one by one",
             "eager_ms_per_step": eager_ms / steps,
             "stage_ms_per_step_max_over_ranks": {"legendre": leg_ms / steps, "ring_fft": fft_ms / steps, "elementwise": el_ms / steps},
             "roofline": {"bound": "hbm", "kernel": "pxm_legendre_kernel (one right-hand side: table streaming bound)",
-                         "achieved": tab.item() * steps / (leg_ms / 1e3) / 1e9 if leg_ms > 0 else None,
-                         "peak": world * float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
-                         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else world * 6650.0,
-                         "unit": "GB/s", # dram__bytes_read+write summed over the 4 Legendre launches of one iteration, ncu --set full at N=1
-                         # (profiles/legendre_wl_r1h_metrics.txt); only valid for the default workload
-                         "traffic": WL_TRAFFIC if (L, B, J_min, world) == (512, 2.0, 2, 1) and fused else None,
+                         "achieved": tab * steps / (leg_ms / 1e3) / 1e9 if leg_ms > 0 else None,
+                         "peak": world * hbm_peak, "unit": "GB/s", "peak_source": hbm_src,
+                         # dram__bytes_read+write summed over the 4 Legendre launches of one iteration at N=1 (tracked ncu summary)
+                         "traffic": traffic.get("wl_legendre_bytes_per_iteration") if (L, B, J_min, world) == (512, 2.0, 2, 1) and fused else None,
                          "note": "per ITERATION (4 launches): algorithmic bytes = every Legendre table the iteration uses, read once "
                                  "(sum over GPUs); with ONE right-hand side the contraction is a table stream, not DMMA-bound; "
                                  f"algorithmic flops {flops:.3e} per iteration -> {flops * steps / (leg_ms / 1e3) / 1e12 if leg_ms > 0 else 0:.2f} TFLOP/s aggregate"},
-            "e2e": {"value": e2e_steps / e2e.item(), "unit": "iterations/s", "h2d_bytes_per_step": int(nbytes.item()),
-                    "d2h_bytes_per_step": int(nbytes.item()), "steps": e2e_steps,
-                    "api": "MYULA.iterate_host on every rank's local rows (pinned host buffers)"},
+            "traffic_source": tsrc,
             "clocks": sampler.summary(),
         }
+        if e2e_val is not None:
+            line["e2e"] = {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
+                           "steps": e2e_steps, "api": "MYULA.iterate_host on every rank's local rows (pinned host buffers)"}
         if line["roofline"]["achieved"]:
             line["roofline"]["frac"] = line["roofline"]["achieved"] / line["roofline"]["peak"]
+    del chain, m, op, reg, tr, wl
+    return line
+
+
+def run_msharded(args):
+    ctx = Ctx()
+    line = measure_msharded(ctx, args)
+    if line is not None:
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    ctx.close()
 
 
 def main():
@@ -568,6 +822,10 @@ def main():
     ap.add_argument("--B", type=float, default=B_DEF)
     ap.add_argument("--J_min", type=int, default=JMIN_DEF)
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--blocks", type=int, default=5, help="sustained-rate blocks after the K-step timed region (0: none)")
+    ap.add_argument("--block-iters", type=int, default=100)
+    ap.add_argument("--strong-total", type=int, default=64, help="chains in TOTAL of the strong-scaling split (config 5)")
+    ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no per-chain / config 1-4 / strong-split legs)")
     ap.add_argument("--ref-L", type=int, default=256, help="bandlimit of the bounded CPU sample")
     ap.add_argument("--ref-procs", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")

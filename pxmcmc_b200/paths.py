@@ -70,6 +70,6 @@ def path_points_count(start, stop, points_per_rad=160):
     stop = np.ascontiguousarray(np.asarray(stop, dtype=np.float64).reshape(-1, 2))
     dv = D.dev()
     out = torch.empty(start.shape[0], dtype=torch.int32, device=dv)
-    check(lib.pxm_gc_count_points(ptr(torch.from_numpy(start).to(dv)), ptr(torch.from_numpy(stop).to(dv)), start.shape[0],
-                                  float(points_per_rad), ptr(out), stream_ptr()))
+    s_d, e_d = torch.from_numpy(start).to(dv), torch.from_numpy(stop).to(dv)  # named: they must outlive the launch
+    check(lib.pxm_gc_count_points(ptr(s_d), ptr(e_d), start.shape[0], float(points_per_rad), ptr(out), stream_ptr()))
     return out.cpu().numpy()
