@@ -474,6 +474,42 @@ __global__ void k_csr_spmv(const int* __restrict__ indptr, const int* __restrict
   if (lane == 0) y[chain * (size_t)nrows + row] = make_double2(re, im);
 }
 
+// several chains per warp: the row's values and column indices are read ONCE for CH chains (a batch of chains
+// multiplies the same matrix; with one chain per grid.y slice the matrix was re-read per chain)
+template <int CH>
+__global__ void k_csr_spmv_multi(const int* __restrict__ indptr, const int* __restrict__ indices,
+                                 const double* __restrict__ vals, const cplx* __restrict__ x, cplx* __restrict__ y,
+                                 int nrows, size_t ncols, int nchains) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int c0 = blockIdx.y * CH;
+  if (row >= nrows) return;
+  double re[CH], im[CH];
+#pragma unroll
+  for (int c = 0; c < CH; ++c) re[c] = im[c] = 0.0;
+  const int nc = min(CH, nchains - c0);
+  for (int j = indptr[row] + lane; j < indptr[row + 1]; j += 32) {
+    const double v = vals[j];
+    const size_t col = (size_t)indices[j];
+#pragma unroll
+    for (int c = 0; c < CH; ++c)
+      if (c < nc) {
+        const cplx xv = x[(size_t)(c0 + c) * ncols + col];
+        re[c] += v * xv.x;
+        im[c] += v * xv.y;
+      }
+  }
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      re[c] += __shfl_down_sync(0xffffffffu, re[c], o);
+      im[c] += __shfl_down_sync(0xffffffffu, im[c], o);
+    }
+    if (lane == 0 && c < nc) y[(size_t)(c0 + c) * (size_t)nrows + row] = make_double2(re[c], im[c]);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Column quantiles of a stored chain [nsamples][ld] (np.quantile(chain, (q_a, q_b), axis=0), method
 // "linear": /root/reference/pxmcmc/uncertainty.py:7-16).  A CTA keeps C adjacent columns in shared
@@ -791,6 +827,7 @@ int pxm_elem_preload() {
   PXM_CUDA(cudaFuncGetAttributes(&a, k_scatter_w));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_r2c));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_csr_spmv));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_csr_spmv_multi<4>));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_counter_add));
   return PXM_OK;
 }
@@ -826,8 +863,14 @@ int pxm_launch_r2c(const double* x, void* out, size_t total, cudaStream_t st) {
 int pxm_launch_csr_spmv(const int* indptr, const int* indices, const double* vals, const void* x, void* y, int nrows,
                         size_t ncols, size_t nchains, cudaStream_t st) {
   if (!nrows || !nchains) return PXM_OK;
-  dim3 grid((unsigned)((nrows * 32 + 255) / 256), (unsigned)nchains);
-  k_csr_spmv<<<grid, 256, 0, st>>>(indptr, indices, vals, (const cplx*)x, (cplx*)y, nrows, ncols);
+  if (nchains == 1) {
+    dim3 grid((unsigned)(((size_t)nrows * 32 + 255) / 256), 1);
+    k_csr_spmv<<<grid, 256, 0, st>>>(indptr, indices, vals, (const cplx*)x, (cplx*)y, nrows, ncols);
+  } else {
+    constexpr int CH = 4;
+    dim3 grid((unsigned)(((size_t)nrows * 32 + 255) / 256), (unsigned)((nchains + CH - 1) / CH));
+    k_csr_spmv_multi<CH><<<grid, 256, 0, st>>>(indptr, indices, vals, (const cplx*)x, (cplx*)y, nrows, ncols, (int)nchains);
+  }
   PXM_LAUNCHED();
   return PXM_OK;
 }

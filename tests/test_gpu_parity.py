@@ -220,6 +220,16 @@ def test_pathintegral(px):
     assert np.isclose(pr.forward(np.ones(L * (2 * L - 1)))[0], 2 * np.pi)
     empty = px.measurements.PathIntegral(sparse.csr_matrix((5, L * (2 * L - 1))))   # rows without entries
     assert np.all(empty.forward(x) == 0)
+    # a batch of chains reads the matrix once per group of four chains: ragged batch sizes, both directions
+    from pxmcmc_b200 import device as D
+
+    for nb in (2, 4, 7):
+        xb = rng.standard_normal((nb, L * (2 * L - 1))) + 1j * rng.standard_normal((nb, L * (2 * L - 1)))
+        yb = rng.standard_normal((nb, 100)) + 1j * rng.standard_normal((nb, 100))
+        fb = p.forward(D.to_dev_c(xb)).cpu().numpy()
+        ab = p.adjoint(D.to_dev_c(yb)).cpu().numpy()
+        for c in range(nb):
+            assert np.array_equal(fb[c], p.forward(xb[c])) and np.array_equal(ab[c], p.adjoint(yb[c]))
 
 
 def test_weaklensing_golden(px):
