@@ -60,9 +60,16 @@ def _cplx_lt(a, b):
 class PxMCMC:
     """Common machinery (pxmcmc/mcmc.py:46-140)."""
 
-    def __init__(self, forward, prior, mcmcparams=PxMCMCParams(), *, noise="host", nchains=1, seed=0, stream0=0):
+    def __init__(self, forward, prior, mcmcparams=PxMCMCParams(), *, noise="host", nchains=1, seed=0, stream0=0,
+                 spill_dir=None, async_spill=True):
+        """`spill_dir`: directory in which the two large tracked arrays (`chain`, `preds`) live as .npy memory maps
+        instead of host RAM (5 000 x 1.22 M samples of config 4 are 49 GB).  `async_spill`: tracked
+        samples leave the device through pinned staging buffers on a copy stream while the chain keeps iterating
+        (the run loops never wait for a device -> host copy); False restores the synchronous copy."""
         self.forward = forward
         self.prior = prior
+        self.spill_dir = spill_dir
+        self.async_spill = bool(async_spill)
         for attr in mcmcparams.__dict__.keys():
             setattr(self, attr, getattr(mcmcparams, attr))
         if noise not in ("host", "device"):
@@ -208,10 +215,18 @@ class PxMCMC:
         lead = (self.nchains,) if self.nchains > 1 else ()
         if "logposterior" in self.track:
             self.logPi = np.zeros(lead + (self.nsamples,))
+        def big(name, shape, dtype):
+            if self.spill_dir is None:
+                return np.zeros(shape, dtype=dtype)
+            import os
+
+            os.makedirs(self.spill_dir, exist_ok=True)
+            return np.lib.format.open_memmap(os.path.join(self.spill_dir, name + ".npy"), mode="w+", dtype=dtype, shape=shape)
+
         if "predictions" in self.track:
-            self.preds = np.zeros(lead + (self.nsamples, len(self.forward.data)), dtype=float)
+            self.preds = big("predictions", lead + (self.nsamples, len(self.forward.data)), float)
         if "chain" in self.track:
-            self.chain = np.zeros(lead + (self.nsamples, self.forward.nparams), dtype=complex if self.complex else float)
+            self.chain = big("chain", lead + (self.nsamples, self.forward.nparams), complex if self.complex else float)
         if "L2" in self.track:
             self.L2s = np.zeros(lead + (self.nsamples,), dtype=float)
         if "prior" in self.track:
@@ -241,6 +256,24 @@ class PxMCMC:
         if hasattr(self, "chain"):
             put(self.chain, D.to_host(X_curr) if D.is_dev(X_curr) else X_curr)
 
+    def _track_dev(self, j, X_curr, curr_preds):
+        """sample j of a device-resident chain: log posterior terms and the tracked vectors.  With `async_spill` nothing
+        here waits for the device: the reductions stay device tensors, state and predictions are snapshotted on the
+        compute stream and leave through `_Spill`; the host arrays are filled when the slot is reused, on `flush`, or
+        before anything reads them (progress lines, checkpoints, the end of `run`)."""
+        terms = self._logpi_terms_dev(X_curr, curr_preds) if self.async_spill else None
+        if terms is None:
+            logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
+            self._tracking(j, X_curr, curr_preds, logPi, L2, prior)
+            return
+        if getattr(self, "_spill", None) is None:
+            self._spill = _Spill(self)
+        self._spill.push(j, X_curr, curr_preds, terms[0], terms[1])
+
+    def _track_flush(self):
+        if getattr(self, "_spill", None) is not None:
+            self._spill.flush()
+
     # ------------------------------------------------------------------ checkpoint / resume
     _TRACKED = ("logPi", "L2s", "priors", "preds", "chain")
 
@@ -250,6 +283,7 @@ class PxMCMC:
         and the tracked arrays filled so far."""
         import os
 
+        self._track_flush()
         d = dict(fields)
         d.update(step_counter=self._step_counter, nchains=self.nchains, noise=self.noise, delta=self.delta,
                  sampler=type(self).__name__)
@@ -298,6 +332,68 @@ class PxMCMC:
         w_re = D.to_dev_f(np.random.randn(n * self.nchains))
         w_im = D.to_dev_f(np.random.randn(n * self.nchains)) if self.complex else None
         return w_re, w_im
+
+
+class _Spill:
+    """Non-blocking device -> host spill of tracked samples.  Two slots; a slot holds a device
+    snapshot of (X, preds, L2, prior) taken on the compute stream -- the chain overwrites its state in place on the
+    next iteration -- and pinned host buffers filled by a copy stream.  The host arrays are written when a slot is
+    reused (two samples later: the copy has long finished) or on `flush`."""
+
+    def __init__(self, sampler):
+        self.s = sampler
+        self.stream = torch.cuda.Stream()
+        self.slots = [None, None]
+        self.want_chain, self.want_preds = hasattr(sampler, "chain"), hasattr(sampler, "preds")
+
+    def _alloc(self, X, P, L2):
+        def pair(t):
+            return torch.empty_like(t), torch.empty(t.shape, dtype=t.dtype).pin_memory()
+
+        d = {"L2": pair(L2), "prior": pair(L2.real.contiguous()), "done": torch.cuda.Event(), "j": None}
+        if self.want_chain:
+            d["X"] = pair(X)
+        if self.want_preds:
+            d["P"] = pair(P)
+        return d
+
+    def push(self, j, X, P, L2, prior):
+        k = j & 1
+        if self.slots[k] is None:
+            self.slots[k] = self._alloc(X, P, L2)
+        sl = self.slots[k]
+        self._write(sl)
+        cur = torch.cuda.current_stream()
+        items = [("L2", L2), ("prior", prior)] + ([("X", X)] if self.want_chain else []) + ([("P", P)] if self.want_preds else [])
+        for name, t in items:
+            sl[name][0].copy_(t.reshape(sl[name][0].shape))  # device snapshot, ordered after the iteration
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            for name, _ in items:
+                sl[name][1].copy_(sl[name][0], non_blocking=True)
+            sl["done"].record(self.stream)
+        # (the compute stream never waits for the spill: the next snapshot into this slot is two samples away and
+        # `_write` has synchronised on `done` by then)
+        sl["j"] = j
+
+    def _write(self, sl):
+        if sl is None or sl["j"] is None:
+            return
+        sl["done"].synchronize()
+        s, j = self.s, sl["j"]
+        L2 = sl["L2"][1].numpy()
+        pr = sl["prior"][1].numpy()
+        logPi = -s.mu * pr - L2
+        X = sl["X"][1].numpy() if self.want_chain else None
+        P = sl["P"][1].numpy() if self.want_preds else None
+        s._tracking(j, X, P, logPi, L2, pr)
+        sl["j"] = None
+
+    def flush(self):
+        for sl in sorted([x for x in self.slots if x is not None and x["j"] is not None], key=lambda x: x["j"]):
+            self._write(sl)
 
 
 class MYULA(PxMCMC):
@@ -358,10 +454,10 @@ class MYULA(PxMCMC):
                 X_curr, curr_preds = self.iterate(X_curr, curr_preds)
             if i >= self.nburn:
                 if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
-                    logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
-                    self._tracking(j, X_curr, curr_preds, logPi, L2, prior)
+                    self._track_dev(j, X_curr, curr_preds)
                     j += 1
                 if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                    self._track_flush()
                     self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
                                          prior=np.ravel(self.priors)[j - 1])
             else:
@@ -372,6 +468,7 @@ class MYULA(PxMCMC):
                 self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
         if checkpoint is not None:
             self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
+        self._track_flush()
         if graphed is not None:
             X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
             graphed.release()
@@ -876,10 +973,10 @@ class SKROCK(PxMCMC):
                 curr_preds = D.to_dev_c(self._forward_dev(X_curr))
             if i >= self.nburn:
                 if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
-                    logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
-                    self._tracking(j, X_curr, curr_preds, logPi, L2, prior)
+                    self._track_dev(j, X_curr, curr_preds)
                     j += 1
             if self.verbosity > 0 and (i + 1) % self.verbosity == 0 and j > 0:
+                self._track_flush()
                 self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
                                      prior=np.ravel(self.priors)[j - 1])
             i += 1
@@ -887,6 +984,7 @@ class SKROCK(PxMCMC):
                 self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
         if checkpoint is not None:
             self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
+        self._track_flush()
         if graphed is not None:
             X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
         self._final_state = (X_curr, curr_preds)

@@ -289,3 +289,40 @@ def test_credible_interval_of_a_long_chain(px):
 
     ours_d = px.uncertainty.credible_interval_range(torch.from_numpy(chain).cuda(), alpha=0.1)
     assert np.allclose(ours_d.cpu().numpy(), ref, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("noise,nchains", [("device", 1), ("device", 3), ("host", 1)])
+def test_async_spill_and_memmapped_chain_equal_the_synchronous_tracking(px, noise, nchains, tmp_path):
+    """tracked samples leave the device through pinned staging buffers on a copy stream while the (in-place, graphed)
+    chain keeps iterating; `spill_dir` keeps `chain` / `preds` in .npy memory maps: same arrays as the synchronous copy"""
+    L, B, J = 12, 2.0, 2
+    rng = np.random.default_rng(9)
+    data = rng.standard_normal(L * (2 * L - 1)) + 0j
+    track = ["logposterior", "L2", "prior", "chain", "predictions"]
+
+    def run(**kw):
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.2, "synthesis", L, B, J, nchains=nchains)
+        p = px.mcmc.PxMCMCParams(nsamples=7, nburn=3, ngap=2, delta=1e-5, lmda=2e-5, mu=1.0, verbosity=0, track=track)
+        reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda, L=L, B=B, J_min=J)
+        m = px.mcmc.MYULA(op, reg, p, noise=noise, seed=21, stream0=4, nchains=nchains, **kw)
+        np.random.seed(31)
+        m.run(np.random.default_rng(1).laplace(size=op.nparams))
+        return m
+
+    sync = run(async_spill=False)
+    spill = run(async_spill=True)
+    mm = run(async_spill=True, spill_dir=str(tmp_path / "spill"))
+    assert getattr(spill, "_spill", None) is not None and getattr(sync, "_spill", None) is None
+    for name in ("chain", "preds", "logPi", "L2s", "priors"):
+        assert np.array_equal(getattr(spill, name), getattr(sync, name)), name
+        assert np.array_equal(np.asarray(getattr(mm, name)), getattr(sync, name)), name
+    assert isinstance(mm.chain, np.memmap) and isinstance(mm.preds, np.memmap)
+    mm.chain.flush()
+    lead = (nchains,) if nchains > 1 else ()
+    on_disk = np.load(str(tmp_path / "spill" / "chain.npy"), mmap_mode="r")
+    assert on_disk.shape == lead + (7, sync.forward.nparams) and np.array_equal(on_disk, sync.chain)
+    # saving works on memory-mapped tracked arrays too
+    from pxmcmc_b200.saving import load_mcmc, save_mcmc
+
+    path = save_mcmc(mm, px.mcmc.PxMCMCParams(nsamples=7), str(tmp_path), "out")
+    assert np.array_equal(load_mcmc(path)[0]["chain"], sync.chain)
