@@ -28,110 +28,11 @@
 #include <tuple>
 
 #include "pxm_common.cuh"
+#include "pxm_dft.cuh"
 
 namespace {
 
-typedef double2 cplx;
-
-__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
-  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
-  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
-// multiply by -i (forward) or +i (inverse)
-template <bool INV>
-__device__ __forceinline__ cplx rot90(cplx a) {
-  return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
-}
-// multiply by exp(-+ i pi/4)
-template <bool INV>
-__device__ __forceinline__ cplx rot45(cplx a) {
-  const double h = 0.70710678118654752440;
-  return INV ? make_double2(h * (a.x - a.y), h * (a.x + a.y)) : make_double2(h * (a.x + a.y), h * (a.y - a.x));
-}
-template <bool INV>
-__device__ __forceinline__ cplx twc(cplx a, double c, double s) {  // a * (c -+ i s)
-  return INV ? make_double2(a.x * c - a.y * s, a.x * s + a.y * c) : make_double2(a.x * c + a.y * s, a.y * c - a.x * s);
-}
-
 __device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
-
-// ---- small DFTs in registers: y_q = sum_r x_r exp(-+ 2 pi i r q / R), natural order in and out
-template <bool INV>
-__device__ __forceinline__ void dft2(cplx& a, cplx& b) {
-  const cplx t = a;
-  a = cadd(t, b);
-  b = csub(t, b);
-}
-template <bool INV>
-__device__ __forceinline__ void dft4(cplx& x0, cplx& x1, cplx& x2, cplx& x3) {
-  const cplx a02 = cadd(x0, x2), s02 = csub(x0, x2), a13 = cadd(x1, x3), s13 = rot90<INV>(csub(x1, x3));
-  x0 = cadd(a02, a13);
-  x2 = csub(a02, a13);
-  x1 = cadd(s02, s13);
-  x3 = csub(s02, s13);
-}
-template <bool INV>
-__device__ __forceinline__ void dft8(cplx* x) {
-  // 8 = 2 x 4: r = 4 r1 + r2 (r1<2, r2<4), q = q1 + 2 q2
-  dft2<INV>(x[0], x[4]);
-  dft2<INV>(x[1], x[5]);
-  dft2<INV>(x[2], x[6]);
-  dft2<INV>(x[3], x[7]);
-  // twiddles w8^(r2 q1), q1 = 1 lives in x[4+r2]
-  x[5] = rot45<INV>(x[5]);
-  x[6] = rot90<INV>(x[6]);
-  x[7] = rot90<INV>(rot45<INV>(x[7]));
-  dft4<INV>(x[0], x[1], x[2], x[3]);  // q1 = 0 -> outputs q = 2 q2
-  dft4<INV>(x[4], x[5], x[6], x[7]);  // q1 = 1 -> outputs q = 1 + 2 q2
-  // reorder to natural q: currently x[q2] = X[2 q2], x[4+q2] = X[1+2 q2]
-  const cplx t1 = x[1], t2 = x[2], t3 = x[3], t4 = x[4], t5 = x[5], t6 = x[6];
-  x[1] = t4;
-  x[2] = t1;
-  x[3] = t5;
-  x[4] = t2;
-  x[5] = t6;
-  x[6] = t3;
-}
-template <bool INV>
-__device__ __forceinline__ void dft16(cplx* x) {
-  // 16 = 4 x 4: r = 4 r1 + r2, q = q1 + 4 q2
-  const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;  // cos, sin(pi/8)
-  const double h = 0.70710678118654752440;
-#pragma unroll
-  for (int r2 = 0; r2 < 4; ++r2) dft4<INV>(x[r2], x[4 + r2], x[8 + r2], x[12 + r2]);
-  // now x[4 q1 + r2] = t[r2][q1]; multiply by w16^(r2 q1)
-  x[5] = twc<INV>(x[5], c1, s1);     // k=1
-  x[6] = twc<INV>(x[6], h, h);       // k=2
-  x[7] = twc<INV>(x[7], s1, c1);     // k=3
-  x[9] = twc<INV>(x[9], h, h);       // k=2
-  x[10] = rot90<INV>(x[10]);         // k=4
-  x[11] = twc<INV>(x[11], -h, h);    // k=6
-  x[13] = twc<INV>(x[13], s1, c1);   // k=3
-  x[14] = twc<INV>(x[14], -h, h);    // k=6
-  x[15] = twc<INV>(x[15], -c1, -s1); // k=9
-#pragma unroll
-  for (int q1 = 0; q1 < 4; ++q1) dft4<INV>(x[4 * q1], x[4 * q1 + 1], x[4 * q1 + 2], x[4 * q1 + 3]);
-  // x[4 q1 + q2] = X[q1 + 4 q2] -> transpose to natural order
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = a + 1; b < 4; ++b) {
-      const cplx t = x[4 * a + b];
-      x[4 * a + b] = x[4 * b + a];
-      x[4 * b + a] = t;
-    }
-}
-template <int R, bool INV>
-__device__ __forceinline__ void dftR(cplx* x) {
-  if (R == 2) dft2<INV>(x[0], x[1]);
-  if (R == 4) dft4<INV>(x[0], x[1], x[2], x[3]);
-  if (R == 8) dft8<INV>(x);
-  if (R == 16) dft16<INV>(x);
-}
 
 // One in-place pass over 2^lgnr rings (padded stride MP): sub-transform length 2^lgLs,
 // radix R, element stride S = Ls/R >= 16 (so the padded address is affine in k).
@@ -434,40 +335,6 @@ pxm_ring_fft_kernel(const PxmFftGroup* __restrict__ groups, int ngroups, cplx* _
 // stride is = 2 (mod 8) elements so that the 4 rings x 2 columns a quarter-warp touches in the
 // ring-coefficient gather/scatter phases fall into distinct banks.
 // =============================================================================================
-template <bool INV>
-__device__ __forceinline__ void dft32(cplx* x) {
-  cplx e[16], o[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    e[k] = x[2 * k];
-    o[k] = x[2 * k + 1];
-  }
-  dft16<INV>(e);
-  dft16<INV>(o);
-  constexpr double C32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                              0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
-                              0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
-                              -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
-                              -0.92387953251128675613, -0.98078528040323044913};
-  constexpr double S32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
-                              0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
-                              0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
-                              0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
-                              0.38268343236508977173, 0.19509032201612826785};
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    const cplx t = (k == 0) ? o[0] : twc<INV>(o[k], C32[k], S32[k]);
-    x[k] = cadd(e[k], t);
-    x[k + 16] = csub(e[k], t);
-  }
-}
-template <int R, bool INV>
-__device__ __forceinline__ void dftN(cplx* x) {
-  if (R == 32)
-    dft32<INV>(x);
-  else
-    dftR<R, INV>(x);
-}
 // x[k] *= w^k, k < R (two interleaved product chains: <= R/2 roundings deep)
 template <int R>
 __device__ __forceinline__ void twiddle_powers(cplx* x, cplx w1) {
@@ -761,63 +628,6 @@ constexpr int PXM_FFT3_MAX_MAPS = 8;
 struct Fft3Maps {
   CUtensorMap m[PXM_FFT3_MAX_MAPS];
 };
-
-// (cos, sin)(2 pi k / 32), k < 16; k is a compile-time constant at every use (unrolled loops)
-__device__ __forceinline__ void w32(int k, double* c, double* sn) {
-  constexpr double CW32[16] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708,
-                               0.70710678118654752440, 0.55557023301960222474, 0.38268343236508977173,
-                               0.19509032201612826785, 0.0, -0.19509032201612826785, -0.38268343236508977173,
-                               -0.55557023301960222474, -0.70710678118654752440, -0.83146961230254523708,
-                               -0.92387953251128675613, -0.98078528040323044913};
-  constexpr double SW32[16] = {0.0, 0.19509032201612826785, 0.38268343236508977173, 0.55557023301960222474,
-                               0.70710678118654752440, 0.83146961230254523708, 0.92387953251128675613,
-                               0.98078528040323044913, 1.0, 0.98078528040323044913, 0.92387953251128675613,
-                               0.83146961230254523708, 0.70710678118654752440, 0.55557023301960222474,
-                               0.38268343236508977173, 0.19509032201612826785};
-  *c = CW32[k];
-  *sn = SW32[k];
-}
-template <bool INV>
-__device__ __forceinline__ cplx tw32(cplx a, int k) {
-  double c, sn;
-  w32(k, &c, &sn);
-  return twc<INV>(a, c, sn);
-}
-// forward DFT of length R whose inputs x[R/2..R) are zero:  X[2q] = DFT_{R/2}(x)[q],
-// X[2q+1] = DFT_{R/2}(x_j W_R^j)[q]
-template <int R>
-__device__ __forceinline__ void dft_half_in(cplx* x) {
-  constexpr int H = R / 2, STEP = 32 / R;
-  cplx e[H], o[H];
-#pragma unroll
-  for (int j = 0; j < H; ++j) {
-    e[j] = x[j];
-    o[j] = (j == 0) ? x[0] : tw32<false>(x[j], j * STEP);
-  }
-  dftR<H, false>(e);
-  dftR<H, false>(o);
-#pragma unroll
-  for (int q = 0; q < H; ++q) {
-    x[2 * q] = e[q];
-    x[2 * q + 1] = o[q];
-  }
-}
-// inverse DFT of length R of which only the outputs z[0..R/2) are needed (left in x[0..R/2)):
-// z[j] = E[j] + W_R^{-j} O[j],  E / O = inverse DFT_{R/2} of the even / odd inputs
-template <int R>
-__device__ __forceinline__ void dft_half_out(cplx* x) {
-  constexpr int H = R / 2, STEP = 32 / R;
-  cplx e[H], o[H];
-#pragma unroll
-  for (int k = 0; k < H; ++k) {
-    e[k] = x[2 * k];
-    o[k] = x[2 * k + 1];
-  }
-  dftR<H, true>(e);
-  dftR<H, true>(o);
-#pragma unroll
-  for (int j = 0; j < H; ++j) x[j] = cadd(e[j], (j == 0) ? o[0] : tw32<true>(o[j], j * STEP));
-}
 
 // table loads of the persistent kernel run this many elements ahead of their use (pass 1 / middle pass)
 #ifndef PXM_PF1

@@ -364,3 +364,17 @@ def test_saving_roundtrip_uses_the_reference_dataset_names(tmp_path):
     assert int(attrs["nsamples"]) == 4 and int(attrs["L"]) == 10 and str(attrs["setting"]) == "synthesis"
     for k in prm.__dict__:
         assert k in attrs
+
+
+def test_dft_codelets_on_the_host(tmp_path):
+    """the register DFT codelets of the ring FFT (multiply-add butterflies, pruned half-input / half-output radix-16/32
+    transforms) compiled for the HOST by nvcc and compared with a direct long-double DFT: 2e-15 relative"""
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "dft_codelets")
+    subprocess.run([nvcc, "-Wno-deprecated-gpu-targets", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "pxmcmc_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "native", "dft_codelets.cu")], check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "worst" in r.stdout
