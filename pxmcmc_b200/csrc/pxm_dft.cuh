@@ -3,13 +3,16 @@
 // Replaces the FFTW codelets behind ssht's phi transforms (reference call sites:
 // /root/reference/pxmcmc/transforms.py:95-98, pxmcmc/measurements.py:223-239).
 //
-// The ring FFT is bound by the FP64 pipe, on which DADD, DMUL and DFMA cost the same issue slot, so the codelets
-// are written in multiply-add form (Linzer & Feig): a butterfly a +- w b with w = c (1 -+ i t), t = s / c, is
+// DADD, DMUL and DFMA cost the same FP64 issue slot, so the codelets are written in multiply-add form (Linzer &
+// Feig): a butterfly a +- w b with w = c (1 -+ i t), t = s / c, is
 //     u = b (1 -+ i t)        2 FMA        (|t| <= 1: the factor with the larger modulus is pulled out)
 //     a +- c u                4 FMA
 // = 6 instructions instead of 4 (complex product) + 4 (additions); a radix-4 butterfly whose inputs carry the
 // geometric twiddles (1, a, a^2, a^3) -- every twiddled radix-4 stage of a Cooley-Tukey split has this form --
-// costs 24 instead of 28, and 20 when a^2 = -+i.  PXM_HD: the same code runs on the host in
+// costs 24 instead of 28, and 20 when a^2 = -+i: 7.8 % fewer FP64 instructions in the persistent ring FFT.
+// Measured (B200, gpurun_out/r2l_lf.log): neutral on its own -- the kernel is bound by load latency at 8 warps per
+// SM, not by FP64 issue (ablations in DESIGN.md) -- and 5 % faster than the product-then-add form once the
+// inter-pass twiddles are computed (twiddle_tree) rather than loaded.  PXM_HD: the same code runs on the host in
 // tests/test_host_cpu.py (compiled by nvcc for the host) against a direct O(N^2) DFT.
 #pragma once
 #include <cuda_runtime.h>
@@ -94,20 +97,30 @@ PXM_HD void bfly_tw(cplx& a, cplx& b, double c, double s) {
     b = csub(t, r);
     return;
   }
+#ifdef PXM_DFT_PLAIN_TWIDDLES  // development switch: complex product, then the additions
+  const cplx p = twc<INV>(b, c, s), t0 = a;
+  a = cadd(t0, p);
+  b = csub(t0, p);
+#else
   double f;
   const cplx u = tw_unit<INV>(b, c, s, &f);
   const cplx t = a;
   a = make_double2(t.x + f * u.x, t.y + f * u.y);
   b = make_double2(t.x - f * u.x, t.y - f * u.y);
+#endif
 }
 // a + w b
 template <bool INV>
 PXM_HD cplx add_tw(cplx a, cplx b, double c, double s) {
   if (s == 0.0 && c == 1.0) return cadd(a, b);
   if (c == 0.0 && s == 1.0) return cadd(a, rot90<INV>(b));
+#ifdef PXM_DFT_PLAIN_TWIDDLES
+  return cadd(a, twc<INV>(b, c, s));
+#else
   double f;
   const cplx u = tw_unit<INV>(b, c, s, &f);
   return make_double2(a.x + f * u.x, a.y + f * u.y);
+#endif
 }
 
 // ---- small DFTs in registers: y_q = sum_r x_r exp(-+ 2 pi i r q / R), natural order in and out

@@ -351,6 +351,28 @@ __device__ __forceinline__ void twiddle_powers(cplx* x, cplx w1) {
   }
 }
 
+// x[k] *= w^k, k < R, for R = 16 / 32 with a radix-4 power tree: w^(4a+b) = (w^4)^a w^b, every power at most six
+// products deep (short dependency chains; the same 30 products as the linear chain at R = 32)
+template <int R, bool CONJ>
+__device__ __forceinline__ void twiddle_tree(cplx* x, cplx w1) {
+  if (CONJ) w1.y = -w1.y;
+  const cplx w2 = cmul(w1, w1), w3 = cmul(w2, w1), w4 = cmul(w2, w2);
+  x[1] = cmul(x[1], w1);
+  x[2] = cmul(x[2], w2);
+  x[3] = cmul(x[3], w3);
+  cplx b[R / 4];  // (w^4)^a
+  b[1] = w4;
+#pragma unroll
+  for (int a = 2; a < R / 4; ++a) b[a] = (a & 1) ? cmul(b[a - 1], w4) : cmul(b[a / 2], b[a / 2]);
+#pragma unroll
+  for (int a = 1; a < R / 4; ++a) {
+    x[4 * a] = cmul(x[4 * a], b[a]);
+    x[4 * a + 1] = cmul(x[4 * a + 1], cmul(b[a], w1));
+    x[4 * a + 2] = cmul(x[4 * a + 2], cmul(b[a], w2));
+    x[4 * a + 3] = cmul(x[4 * a + 3], cmul(b[a], w3));
+  }
+}
+
 // table loads (chirp, filter spectrum: L1/L2 hits) run PF elements ahead of their use, so their
 // latencies overlap instead of adding up along the in-order instruction stream
 template <int N, int PF, class Load, class Use>
@@ -659,12 +681,23 @@ __device__ __forceinline__ void fft3_find(const PxmFftGroupTable& tab, const Fft
   out->t0 = tab.g[out->gi].ring0 + ((int)blocks.blk[b] << tab.g[out->gi].pad);
 }
 
+template <int DIR>
+__device__ __forceinline__ void fft3_stage_one(const PxmFftGroup& gr, const Fft3Item& it, unsigned char* stage,
+                                               uint64_t* bar, const cplx* __restrict__ pix, size_t pix_chain_stride,
+                                               const CUtensorMap* map);
 // issue the TMA copies global -> shared of one item's inputs (one thread); they complete on `bar`
 template <int DIR>
 __device__ __forceinline__ void fft3_stage(const PxmFftGroup& gr, const Fft3Item& it, unsigned char* stage,
                                            uint64_t* bar, const cplx* __restrict__ pix, size_t pix_chain_stride,
                                            const CUtensorMap* map) {
   if (threadIdx.x != 0) return;
+  fft3_stage_one<DIR>(gr, it, stage, bar, pix, pix_chain_stride, map);
+}
+// the same, called by the one thread that issues the copies
+template <int DIR>
+__device__ __forceinline__ void fft3_stage_one(const PxmFftGroup& gr, const Fft3Item& it, unsigned char* stage,
+                                               uint64_t* bar, const cplx* __restrict__ pix, size_t pix_chain_stride,
+                                               const CUtensorMap* map) {
   const int nr = 1 << gr.pad;
   if (DIR == 0) {  // the rows of a block are contiguous: one 1-D copy
     const int rows = min(nr, gr.rings - it.t0);
@@ -730,8 +763,18 @@ __device__ __forceinline__ void ring_fft3_pass1(const PxmFftGroup& gr, const Fft
         x[j1] = v;
       }
     }
+#ifndef PXM_ABL_NODFT
     dft_half_in<R1>(x);
+#endif
+#ifdef PXM_ABL_NOTABLES
+    prefetched<R1 - 1, PXM_PF1>([&](int i) { return tw2[0]; }, [&](int i, cplx w) { x[i + 1] = cmul(x[i + 1], w); });
+#elif !defined(PXM_FFT3_TWTABLE)
+    // W_M^(k1 j2), k1 < R1, from W_M^(j2): one table load instead of R1 - 1 (the loads, not the FP64 pipe, bound
+    // the pass: 1.164 -> 1.132 ms per 64-chain step, gpurun_out/r2l_lf.log)
+    twiddle_tree<R1, false>(x, tw2[R2 + j2]);
+#else
     prefetched<R1 - 1, PXM_PF1>([&](int i) { return tw2[(i + 1) * R2 + j2]; }, [&](int i, cplx w) { x[i + 1] = cmul(x[i + 1], w); });
+#endif
     cplx* dst = s + r * RS + j2;
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
@@ -754,11 +797,25 @@ __device__ __forceinline__ void ring_fft3_middle(const PxmFftGroup& gr, cplx* __
     cplx x[R2];
 #pragma unroll
     for (int j2 = 0; j2 < R2; ++j2) x[j2] = row[j2];
+#ifndef PXM_ABL_NODFT
     dftN<R2, false>(x);
+#endif
+#if defined(PXM_ABL_NOTABLES) || defined(PXM_ABL_NOBHAT)
+    prefetched<R2, PXM_PF2>([&](int k2) { return bhat[0]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+#else
     prefetched<R2, PXM_PF2>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+#endif
+#ifndef PXM_ABL_NODFT
     dftN<R2, true>(x);
+#endif
+#ifdef PXM_ABL_NOTABLES
+    prefetched<R2 - 1, PXM_PF2>([&](int i) { return tw2t[0]; }, [&](int i, cplx w) { x[i + 1] = cmulc(x[i + 1], w); });
+#elif !defined(PXM_FFT3_TWTABLE)
+    twiddle_tree<R2, true>(x, tw2t[R1 + k1]);  // conj W_M^(j2 k1), j2 < R2, from W_M^(k1)
+#else
     prefetched<R2 - 1, PXM_PF2>([&](int i) { return tw2t[(i + 1) * R1 + k1]; },
                           [&](int i, cplx w) { x[i + 1] = cmulc(x[i + 1], w); });
+#endif
 #pragma unroll
     for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
   }
@@ -784,7 +841,9 @@ __device__ __forceinline__ void ring_fft3_pass3(const PxmFftGroup& gr, const Fft
     cplx x[R1];
 #pragma unroll
     for (int k1 = 0; k1 < R1; ++k1) x[k1] = src[k1 * (R2 + 1)];
+#ifndef PXM_ABL_NODFT
     dft_half_out<R1>(x);
+#endif
     if (DIR == 0) {
       double* frow = F + gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
       const size_t ss = gr.slot_stride;
@@ -913,6 +972,291 @@ pxm_ring_fft3_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_
   }
 }
 
+#ifdef PXM_FFT_PINGPONG
+// =============================================================================================
+// DEVELOPMENT VARIANT, compiled only with -DPXM_FFT_PINGPONG (measured SLOWER: 1.31 vs 1.17 ms per 64-chain step,
+// gpurun_out/r2k_tests.log / DESIGN.md 7c: with one warp per scheduler in the FP64 section the filter-spectrum loads are exposed).
+// Ping-pong variant of the persistent staged transform: ONE CTA of 256 threads per SM made of two
+// groups of 4 warps.  Each group is what a CTA of pxm_ring_fft3_kernel was -- its own work items,
+// staging buffer, work buffer, chirp copy, TMA barrier -- but the groups hand a token back and forth so
+// that the FP64 section of a pass (register DFTs, twiddles, filter) of one group runs while the other
+// group is in the shared-memory / global-memory section of its pass (stores of the previous pass, group
+// barrier, loads of the next one).  Two independent CTAs per SM ran those sections in lockstep: measured
+// time = memory time + FP64 time (ablations in DESIGN.md); with the hand-over it is close to the larger
+// of the two.  The token is a pair of named barriers used as producer / consumer barriers
+// (bar.sync by the group that waits, bar.arrive by the group that releases).
+// Inter-pass twiddles W_M^(k1 j2) are formed from one table entry per thread by a power tree
+// (twiddle_tree) instead of R - 1 table loads: the loads sat on the critical path of the FP64 section.
+// =============================================================================================
+constexpr int PXM_FFT4_GROUP = ((PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP + 1023) / 1024) * 1024;
+constexpr int PXM_FFT4_SMEM = 2 * PXM_FFT4_GROUP + 64;
+
+__device__ __forceinline__ void grp_sync(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void tok_acquire(int g) { asm volatile("bar.sync %0, 256;" ::"r"(3 + g) : "memory"); }
+__device__ __forceinline__ void tok_release_to(int g) { asm volatile("bar.arrive %0, 256;" ::"r"(3 + g) : "memory"); }
+
+struct Fft4Tok {
+  int g;        // this group
+  bool last;    // the very last release of the launch is skipped (nobody waits for it)
+  __device__ __forceinline__ void acquire() const { tok_acquire(g); }
+  __device__ __forceinline__ void release(bool final_pass) const {
+    if (!(last && final_pass)) tok_release_to(g ^ 1);
+  }
+};
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft4_pass1(const PxmFftGroup& gr, const Fft3Item& it, cplx* __restrict__ s,
+                                                const unsigned char* __restrict__ stage,
+                                                const cplx* __restrict__ chirp_s, const cplx* __restrict__ arena,
+                                                int tid, const Fft4Tok& tok, bool have) {
+  constexpr int H1 = R1 / 2;
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ tw2 = arena + gr.tw2_off;  // [k1][j2]
+  // nr * R2 is 128 (M = 1024) or 256 (M = 512): every thread runs the same one or two trips; a group without an
+  // item (have == false) transforms zeros into its own work buffer so that the token changes hands all the same
+  const int padded = nr * R2;
+  for (int idx = tid; idx < padded; idx += 128) {
+    const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+    const int r = rhi * 4 + (rem & 3), j2 = rem >> 2;
+    const int nj = (have && it.t0 + r < rings) ? n : 0;  // rows past the end of the grid are zeros
+    cplx x[R1];
+    // ---- memory section: staged inputs -> registers
+    {
+      if (DIR == 0) {
+        const cplx* row = reinterpret_cast<const cplx*>(stage) + r * n;
+#pragma unroll
+        for (int j1 = 0; j1 < H1; ++j1) {
+          const int j = j1 * R2 + j2;
+          x[j1] = (j < nj) ? row[j] : make_double2(0.0, 0.0);
+        }
+      } else {
+        const unsigned char* grp = stage + (size_t)(r >> 2) * ((ell * 128 + 1023) & ~1023);
+        const int rl = r & 3;
+#pragma unroll
+        for (int j1 = 0; j1 < H1; ++j1) {
+          const int j = j1 * R2 + j2;
+          cplx v = make_double2(0.0, 0.0);
+          if (j < nj) {
+            const bool minus = j >= ell;  // order m = j - n < 0: second half of the 128-byte row
+            const int am = minus ? n - j : j;
+            const int d = (minus ? 8 : 0) + rl;  // re at double d, im at d + 4 (two chunks further)
+            const unsigned char* row = grp + am * 128 + (d & 1) * 8;
+            const int sw = am & 7, ch = d >> 1;
+            const double re = *reinterpret_cast<const double*>(row + ((ch ^ sw) << 4));
+            const double im = *reinterpret_cast<const double*>(row + (((ch + 2) ^ sw) << 4));
+            const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+            // (-1)^m of the paired layout and the conjugation on load (x_p = conj(DFT(conj F))) are sign-bit flips
+            v = make_double2(flip_sign(re, neg), flip_sign(im, neg ^ (int)0x80000000));
+          }
+          x[j1] = v;
+        }
+      }
+    }
+    if (idx == tid) tok.acquire();
+    // ---- FP64 section
+    {
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        x[j1] = cmul(x[j1], chirp_s[j < n ? j : 0]);
+      }
+      dft_half_in<R1>(x);
+      twiddle_tree<R1, false>(x, tw2[R2 + j2]);  // W_M^(k1 j2), k1 < R1, from W_M^(j2)
+    }
+    if (idx + 128 >= padded) tok.release(false);
+    // ---- memory section: registers -> work buffer
+    {
+      cplx* dst = s + r * RS + j2;
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) dst[k1 * (R2 + 1)] = x[k1];
+    }
+  }
+}
+
+template <int R1, int R2>
+__device__ __forceinline__ void ring_fft4_middle(const PxmFftGroup& gr, cplx* __restrict__ s,
+                                                 const cplx* __restrict__ arena, int tid, const Fft4Tok& tok, bool have) {
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ bhat = arena + gr.bhat2_off;
+  const cplx* __restrict__ tw2t = arena + gr.tw2_off + R1 * R2;  // [j2][k1]
+  const int padded = nr * R1;  // 128 for both radix pairs
+  for (int idx = tid; idx < padded; idx += 128) {
+    const int rhi = idx / (4 * R1), rem = idx - rhi * 4 * R1;
+    const int r = rhi * 4 + (rem & 3), k1 = rem >> 2;
+    cplx* row = s + r * RS + k1 * (R2 + 1);
+    cplx x[R2];
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) x[j2] = row[j2];
+    if (idx == tid) tok.acquire();
+    {
+      dftN<R2, false>(x);
+      prefetched<R2, PXM_PF2>([&](int k2) { return bhat[k2 * R1 + k1]; }, [&](int k2, cplx b) { x[k2] = cmul(x[k2], b); });
+      dftN<R2, true>(x);
+      twiddle_tree<R2, true>(x, tw2t[R1 + k1]);  // conj W_M^(j2 k1), j2 < R2, from W_M^(k1)
+    }
+    if (idx + 128 >= padded) tok.release(false);
+#pragma unroll
+    for (int j2 = 0; j2 < R2; ++j2) row[j2] = x[j2];
+  }
+}
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft4_pass3(const PxmFftGroup& gr, const Fft3Item& it, const cplx* __restrict__ s,
+                                                const cplx* __restrict__ chirp_s, cplx* __restrict__ pix,
+                                                size_t pix_chain_stride, double* __restrict__ F, int nld, int tid,
+                                                const Fft4Tok& tok, bool have) {
+  constexpr int H1 = R1 / 2;
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const size_t col0 = (size_t)it.chain * 4;  // paired layout only (the launcher checks)
+  const int padded = nr * R2;
+  for (int idx = tid; idx < padded; idx += 128) {
+    const int rhi = idx / (4 * R2), rem = idx - rhi * 4 * R2;
+    const int r = rhi * 4 + (rem & 3), j2 = rem >> 2;
+    const int t = it.t0 + r;
+    const bool act = have && t < rings;
+    cplx x[R1];
+    {
+      const cplx* src = s + r * RS + j2;
+#pragma unroll
+      for (int k1 = 0; k1 < R1; ++k1) x[k1] = src[k1 * (R2 + 1)];
+    }
+    if (idx == tid) tok.acquire();
+    {
+      dft_half_out<R1>(x);
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        x[j1] = cmul(x[j1], chirp_s[j < n ? j : 0]);
+      }
+    }
+    if (idx + 128 >= padded) tok.release(true);
+    if (act) {
+      if (DIR == 0) {
+        double* frow = F + gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
+        const size_t ss = gr.slot_stride;
+#pragma unroll
+        for (int j1 = 0; j1 < H1; ++j1) {
+          const int j = j1 * R2 + j2;
+          if (j < n) {
+            const bool minus = j >= ell;
+            const int am = minus ? n - j : j;
+            double* dst = frow + (size_t)am * ss + (minus ? 8 : 0);
+            const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+            dst[0] = flip_sign(x[j1].x, neg);
+            dst[4] = flip_sign(x[j1].y, neg);  // next column of the k4-interleaved layout
+          }
+        }
+      } else {
+        cplx* row = pix + (size_t)it.chain * pix_chain_stride + gr.pix_off + (size_t)(t - gr.ring0) * n;
+#pragma unroll
+        for (int j1 = 0; j1 < H1; ++j1) {
+          const int j = j1 * R2 + j2;
+          if (j < n) row[j] = make_double2(x[j1].x, flip_sign(x[j1].y, (int)0x80000000));
+        }
+      }
+    }
+  }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256, 1)
+pxm_ring_fft4_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_constant__ Fft3Blocks blocks,
+                     const __grid_constant__ Fft3Maps maps, cplx* __restrict__ pix, size_t pix_chain_stride,
+                     double* __restrict__ F, int nld, const cplx* __restrict__ arena, int nchains, long long nitems) {
+  extern __shared__ __align__(1024) unsigned char fsm4[];
+  const int g = threadIdx.x >> 7, tid = threadIdx.x & 127;
+  unsigned char* base = fsm4 + g * PXM_FFT4_GROUP;
+  unsigned char* stage = base;  // 1024-byte aligned: the TMA swizzle phase is (row & 7)
+  cplx* s = reinterpret_cast<cplx*>(base + PXM_FFT3_STAGE);
+  cplx* chirp_s = reinterpret_cast<cplx*>(base + PXM_FFT3_STAGE + PXM_FFT3_WORK);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm4 + 2 * PXM_FFT4_GROUP) + g;
+  if (tid == 0) {
+    if (smem_u32(fsm4) & 1023) __trap();
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // both groups run the same number of rounds (the token must change hands a fixed number of times)
+  const long long stride = 2LL * gridDim.x;
+  const long long rounds = (nitems + stride - 1) / stride;
+  long long item = 2LL * blockIdx.x + g;
+  uint32_t phase = 0;
+  Fft3Item cur, nxt;
+  int ib = (int)(item / nchains), ic = (int)(item - (long long)ib * nchains);
+  const int db = (int)(stride / nchains), dc = (int)(stride - (long long)db * nchains);
+  bool have = item < nitems;
+  if (have) {
+    fft3_find(tab, blocks, ib, ic, &cur);
+    if (tid == 0) fft3_stage_one<DIR>(tab.g[cur.gi], cur, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[cur.gi]]);
+  } else {
+    // a group without work still takes its turns with the token: it transforms zeros of the launch's first
+    // (radix-32 class) group into its own work buffer and stores nothing
+    cur.gi = blocks.gi[0];
+    cur.t0 = 0;
+    cur.chain = 0;
+  }
+  nxt = cur;
+  if (g == 1) tok_release_to(0);  // group 0 computes first
+  int chirp_group = -1;
+  for (long long rd = 0; rd < rounds; ++rd, item += stride) {
+    const PxmFftGroup& gr = tab.g[cur.gi];
+    const bool big = gr.logM == 10;
+    Fft4Tok tok;
+    tok.g = g;
+    tok.last = (g == 1) && (rd + 1 == rounds);
+    if (have && cur.gi != chirp_group) {  // a few times per launch: the blocks of a group are consecutive items
+      grp_sync(g);                        // pass 3 of the previous item has finished with the old chirp
+      const cplx* __restrict__ chirp = arena + gr.chirp_off;
+      const double rs = sqrt(gr.scale / (double)gr.M);
+      for (int j = tid; j < gr.n; j += 128) {
+        const cplx c = chirp[j];
+        chirp_s[j] = make_double2(c.x * rs, c.y * rs);
+      }
+      chirp_group = cur.gi;
+    }
+    grp_sync(g);  // pass 3 of the previous item has left the work buffer; the chirp copy is complete
+    if (have) {
+      mbar_wait(bar, phase);  // the staged inputs have landed
+      phase ^= 1;
+    }
+    if (big)
+      ring_fft4_pass1<DIR, 32, 32>(gr, cur, s, stage, chirp_s, arena, tid, tok, have);
+    else
+      ring_fft4_pass1<DIR, 16, 32>(gr, cur, s, stage, chirp_s, arena, tid, tok, have);
+    grp_sync(g);
+    bool have_next = false;
+    if (item + stride < nitems) {
+      have_next = true;
+      ib += db;
+      ic += dc;
+      if (ic >= nchains) {
+        ic -= nchains;
+        ++ib;
+      }
+      fft3_find(tab, blocks, ib, ic, &nxt);
+      if (tid == 0) fft3_stage_one<DIR>(tab.g[nxt.gi], nxt, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[nxt.gi]]);
+    }
+    if (big)
+      ring_fft4_middle<32, 32>(gr, s, arena, tid, tok, have);
+    else
+      ring_fft4_middle<16, 32>(gr, s, arena, tid, tok, have);
+    grp_sync(g);
+    if (big)
+      ring_fft4_pass3<DIR, 32, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld, tid, tok, have);
+    else
+      ring_fft4_pass3<DIR, 16, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld, tid, tok, have);
+    cur = nxt;
+    have = have_next;
+  }
+}
+
+#endif  // PXM_FFT_PINGPONG
+
 constexpr int PXM_FFT2_SMEM = (16 * (16 * 17 + 2)) * 16 > (4 * (32 * 33 + 2)) * 16 ? (16 * (16 * 17 + 2)) * 16
                                                                                   : (4 * (32 * 33 + 2)) * 16;
 
@@ -973,6 +1317,7 @@ int pxm_fft_rings_per_cta_log(int M) {
 }
 
 static int g_fft_legacy = 0;
+static int g_fft_pingpong = 1;  // builds with -DPXM_FFT_PINGPONG: the ping-pong kernel (1) or the two-CTA kernel (0)
 constexpr int PXM_FFT_SMEM = (4096 + 256 + 32) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
 
 int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_groups, int ngroups, void* d_arena,
@@ -988,6 +1333,10 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
+#ifdef PXM_FFT_PINGPONG
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT4_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT4_SMEM));
+#endif
     configured = true;
   }
   if (ngroups <= 0) return PXM_OK;  // a rank of an m-sharded plan that owns no ring
@@ -1100,6 +1449,18 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
 #else
       const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);  // 2 CTAs per SM (shared memory, 252 registers)
 #endif
+#ifdef PXM_FFT_PINGPONG
+      if (g_fft_pingpong) {
+        // one 256-thread CTA per SM whose two 4-warp groups alternate between FP64 and memory sections
+        const int g4 = (int)std::min<long long>((nitems + 1) / 2, (long long)nsm);
+        if (dir == 0)
+          pxm_ring_fft4_kernel<0><<<g4, 256, PXM_FFT4_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                    nitems);
+        else
+          pxm_ring_fft4_kernel<1><<<g4, 256, PXM_FFT4_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                    nitems);
+      } else
+#endif
       if (dir == 0)
         pxm_ring_fft3_kernel<0><<<g3, 128, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
                                                                   nitems);
@@ -1131,7 +1492,11 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
 
 // 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies),
 // 3: two-pass, with the persistent staged kernel for the radix-32 class (what 0 picks for large grids)
-void pxm_fft_set_legacy(int on) { g_fft_legacy = on; }
+// 4: like 3 but with the two-CTA persistent kernel instead of the ping-pong one; any other value re-enables it
+void pxm_fft_set_legacy(int on) {
+  g_fft_pingpong = on != 4;
+  g_fft_legacy = on == 4 ? 3 : on;
+}
 
 #ifdef PXM_FFT3_TIMING
 namespace {

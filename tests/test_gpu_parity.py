@@ -514,19 +514,20 @@ def test_myula_graph_replay_matches_eager(px, iters_per_graph):
         px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, P0)
 
 
-@pytest.mark.parametrize("mode", [2, 3])
-def test_ring_fft_two_pass_against_multipass(px, mode):
-    """the two-pass ring FFT (mode 2: all Bluestein lengths <= 1024; mode 3: its persistent, TMA-staged
-    variant for lengths 512 / 1024) against the independent multi-pass kernel (the path lengths > 1024
-    take), through all four wavelet operators at the BASELINE bandlimit"""
+@pytest.mark.parametrize("mode,nb", [(2, 2), (3, 2), (3, 3), (3, 9), (4, 3)])
+def test_ring_fft_two_pass_against_multipass(px, mode, nb):
+    """the two-pass ring FFT (mode 2: all Bluestein lengths <= 1024; mode 3 / 4: its persistent, TMA-staged
+    variant for lengths 512 / 1024, even and odd item counts) against the
+    independent multi-pass kernel (the path lengths > 1024 take), through all four wavelet operators at the
+    BASELINE bandlimit"""
     from pxmcmc_b200 import _lib
     from pxmcmc_b200 import device as D
 
     L, B, J = 256, 1.5, 2
     rng = np.random.default_rng(13)
-    plan = D.WaveletPlan.get(L, B, J, 2)
-    coef = D.to_dev_c(rng.standard_normal((2, plan.ncoefs)) + 1j * rng.standard_normal((2, plan.ncoefs)))
-    pix = D.to_dev_c(rng.standard_normal((2, plan.npix)) + 1j * rng.standard_normal((2, plan.npix)))
+    plan = D.WaveletPlan.get(L, B, J, nb)
+    coef = D.to_dev_c(rng.standard_normal((nb, plan.ncoefs)) + 1j * rng.standard_normal((nb, plan.ncoefs)))
+    pix = D.to_dev_c(rng.standard_normal((nb, plan.npix)) + 1j * rng.standard_normal((nb, plan.npix)))
     for name, x in (("synthesis", coef), ("synthesis_adjoint", pix), ("analysis", pix), ("analysis_adjoint", coef)):
         try:
             _lib.check(_lib.lib.pxm_debug_set_fft_multipass(mode))
@@ -564,7 +565,7 @@ def test_iterate_host_pipeline_matches_device_iteration(px):
         assert m._step_counter == 1
 
 
-@pytest.mark.parametrize("mode", [2, 3])
+@pytest.mark.parametrize("mode", [2, 3, 4])
 def test_ring_fft_two_pass_all_radices_against_oracle(px, mode):
     """two-pass ring FFT forced on (mode 2; mode 3: persistent staged kernel for length 512, ragged
     item count) at L=70, B=2: Bluestein lengths 16...512, i.e. every radix pair below (32, 32), paired
