@@ -23,4 +23,20 @@ Parity status
   (``tests/test_transforms.py``, ``tests/test_measurements.py``,
   ``tests/test_utils.py:85-100``) and against closed-form spin-weighted
   spherical harmonics.
+
+  What is and is not pinned there (``tests/test_oracle_golden.py``):
+  - the spin-weighted harmonics themselves: scipy ``sph_harm_y`` and closed-form Wigner d (independent of ssht);
+  - the wavelet / scaling coefficients against their DEFINITION <f, R psi^j>, <f, R phi> by direct quadrature with
+    the ``wavelet_tiling`` arrays the reference consumes
+    (``test_wavelet_coefficients_are_the_defining_inner_products``): fixes the so3 (2 pi)^(-1/2), the tiling
+    normalisations sqrt((2l+1)/8 pi^2) and sqrt((2l+1)/4 pi), grid positions and coefficient ordering;
+  - exactly three numbers remain that only the wheels could confirm, each a single named symbol:
+      1. ``s2let_ref.tiling_axisym: n = 300`` -- the trapezoid resolution of s2let's kappa integral (another
+         quadrature changes kappa_j(l) at the 1e-6 level; partition of unity holds either way);
+      2. ``s2let_ref._SQ2PI`` -- whether s2let stores W^j as defined (checked against the definition above) or
+         rescaled by a constant (would rescale all wavelet coefficients, not the reconstruction);
+      3. ``healpix_ref.map2alm(iter=3)`` -- healpy's default number of Jacobi refinements.
+* ``greatcircle_ref`` -- restates ``greatcirclepaths==1.1.0`` (absent): points per radian, nearest-pixel binning and
+  "average" weighting from the package's documented behaviour; parity unpinned, pinned by geometry and the
+  path-average property the reference's test asserts.
 """

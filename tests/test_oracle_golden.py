@@ -356,3 +356,79 @@ def test_host_lm_hp2lm_matches_oracle():
         utils.lm_hp2lm(alm[:-1], L)
     with pytest.raises(ValueError):
         utils.map2alm(np.zeros(13), 3)
+
+
+@pytest.mark.parametrize("L,B,J_min", [(12, 2.0, 1), (14, 1.5, 2)])
+def test_wavelet_coefficients_are_the_defining_inner_products(L, B, J_min):
+    """Second, independently written derivation of the s2let / so3 normalisation (oracle/__init__.py "parity status"):
+    the coefficient maps of `analysis_px2wav` are compared with the DEFINITION of the scale-discretised transform,
+        W^j(w0) = <f, R_w0 psi^j> = int f(w) conj((R_w0 psi^j)(w)) dOmega ,   S(w0) = <f, R_w0 phi> ,
+    evaluated by direct quadrature of closed-form harmonics (scipy sph_harm_y) with the wavelets psi^j_lm / phi_l that
+    `wavelet_tiling` returns (the arrays the reference itself consumes in pxmcmc/prior.py:120-149).  This fixes, without
+    reference to the transform code: the (2 pi)^(-1/2) of the wavelet coefficients versus none for the scaling
+    coefficients, the sqrt((2l+1)/8 pi^2) / sqrt((2l+1)/4 pi) normalisations of the tiling, the sample positions of the
+    multiresolution grids and the [scaling, wavelets by increasing j] ordering."""
+    from scipy.special import sph_harm_y
+
+    rng = np.random.default_rng(L)
+    flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    f = ssht_ref.inverse(flm, L, 0).ravel()
+    f_wav, f_scal = s2let_ref.analysis_px2wav(f, B, L, J_min)
+    phi_l, psi_lm = s2let_ref.wavelet_tiling(B, L, 1, J_min, 0)
+    bls = s2let_ref.bandlimits(B, L, J_min)
+    # quadrature grid: the integrand f * conj(R psi) has bandlimit 2L - 1 -> exact MW quadrature at bandlimit 2L
+    Lq = 2 * L
+    fq = ssht_ref.inverse(np.concatenate([flm, np.zeros(Lq * Lq - L * L)]), Lq, 0).ravel()
+    wq = R.mw_map_weights(Lq)
+    thq, phq = ssht_ref.sample_positions(Lq)
+    TH, PH = np.meshgrid(thq, phq, indexing="ij")
+    TH, PH = TH.ravel(), PH.ravel()
+    Yq = {(el, m): sph_harm_y(el, m, TH, PH) for el in range(L) for m in range(-el, el + 1)}
+
+    def rotated_kernel(k_l0, th0, ph0):
+        """(R_w0 k)(w) for an axisymmetric kernel with harmonic coefficients k_{l0}: addition theorem"""
+        out = np.zeros(TH.size, dtype=complex)
+        for el in range(L):
+            if k_l0[el] == 0:
+                continue
+            c = k_l0[el] * np.sqrt(4 * np.pi / (2 * el + 1))
+            for m in range(-el, el + 1):
+                out += c * np.conj(sph_harm_y(el, m, th0, ph0)) * Yq[(el, m)]
+        return out
+
+    ls = np.arange(L)
+    kernels = [phi_l] + [psi_lm[ls * ls + ls, j] for j in range(psi_lm.shape[1])]
+    coef = np.concatenate([f_scal, f_wav])
+    off = 0
+    for Lj, k_l0 in zip(bls, kernels):
+        th, ph = ssht_ref.sample_positions(Lj)
+        for (t, p) in [(0, 0), (Lj // 2, Lj // 3), (Lj - 1, 2 * Lj - 2), (1, Lj)]:
+            direct = np.sum(wq * fq * np.conj(rotated_kernel(k_l0, th[t], ph[p])))
+            got = coef[off + t * (2 * Lj - 1) + p]
+            assert abs(got - direct) < 1e-11 * max(1.0, abs(direct)), (Lj, t, p, got, direct)
+        off += Lj * (2 * Lj - 1)
+    assert off == coef.size
+
+
+def test_wavelet_power_weights_closed_form():
+    """S2_Wavelets_L1_Power_Weights (pxmcmc/prior.py:120-149): the powers P = sum_l |psi_l0|^2 are
+    sum_l (2l+1)/(8 pi^2) kappa_j(l)^2 resp. sum_l (2l+1)/(4 pi) kappa_0(l)^2 -- evaluated here from the tiling alone and
+    compared with the weight vectors of the restated prior"""
+    L, B, J = 20, 2.0, 2
+    kappa, kappa0 = s2let_ref.tiling_axisym(B, L, J)
+    ls = np.arange(L)
+    prior = R.S2WaveletsL1PowerWeights("synthesis", None, None, 1.0, L, B, J, eta=1)
+    bls = s2let_ref.bandlimits(B, L, J)
+    off = 0
+    P0 = np.sum((2 * ls + 1) / (4 * np.pi) * kappa0 ** 2)
+    Le = int(np.nonzero(kappa0)[0].max()) + 1
+    th, _ = ssht_ref.sample_positions(Le)
+    assert np.allclose(prior.map_weights[: Le * (2 * Le - 1)].reshape(Le, -1)[:, 0], 2 * np.pi ** 2 / (P0 * Le * (2 * Le - 1)) * np.sin(th))
+    off = bls[0] * (2 * bls[0] - 1)
+    for j, Lj in zip(range(J, s2let_ref.j_max(L, B) + 1), bls[1:]):
+        Pj = np.sum((2 * ls + 1) / (8 * np.pi ** 2) * kappa[j] ** 2)
+        peak = int(np.argmax(kappa[j] * np.sqrt(2 * ls + 1)))
+        th, _ = ssht_ref.sample_positions(Lj)
+        w = prior.map_weights[off: off + Lj * (2 * Lj - 1)].reshape(Lj, -1)[:, 0]
+        assert np.allclose(w, 2 * np.pi ** 2 * peak / (Pj * Lj * (2 * Lj - 1)) * np.sin(th), rtol=1e-12), j
+        off += Lj * (2 * Lj - 1)
