@@ -566,7 +566,7 @@ def run_ours(args):
         if wl is not None:
             extras["config4_msharded"] = {k: wl[k] for k in ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "config",
                                                             "eager_ms_per_step", "stage_ms_per_step_max_over_ranks", "roofline",
-                                                            "finite", "peer_barrier_ok", "launch_mode")}
+                                                            "finite", "peer_barrier_ok", "launch_mode", "nvlink")}
     if ctx.rank == 0:
         if world == 1 and not args.no_extras:
             extras["per_chain_latency"] = measure_single_chain(ctx, args)
@@ -674,6 +674,27 @@ def wl_flops_per_iteration(L, B, J_min):
     return algorithmic_flops_per_chain_iteration(L, B, J_min) + 2 * 4.0 * L * L * L + 2 * 4.0 * L * (L * L - 4)
 
 
+def nvlink_counters(local):
+    """(tx, rx) bytes moved over all NVLink links of GPU `local` since boot, from NVML's throughput counters
+    (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, KiB, all links); None when NVML does not expose them"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        tx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138)
+        rx_id = getattr(pynvml, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(tx_id, 0xFFFFFFFF), (rx_id, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(float(v.value.ullVal) * 1024.0)
+        return tuple(out)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measure_msharded(ctx, args, e2e=True):
     """-> the JSON line of the m-sharded weak-lensing workload on rank 0 (None elsewhere)"""
     import ctypes as C
@@ -740,12 +761,16 @@ def measure_msharded(ctx, args, e2e=True):
         chain.step()
     ctx.barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nv0 = nvlink_counters(ctx.local)
     g0.record()
     for _ in range(steps):
         chain.step()
     g1.record()
     ctx.barrier()
+    nv1 = nvlink_counters(ctx.local)
     ms_total = g0.elapsed_time(g1)
+    nvl = [(nv1[0] - nv0[0]) / steps, (nv1[1] - nv0[1]) / steps] if (nv0 and nv1) else [-1.0, -1.0]
+    nvl = ctx.reduce(nvl, op="sum")  # bytes per iteration over all ranks (negative: counters unavailable)
     X, P = chain.state()
     ok = tr.plan.barrier_ok() and wl.s0.barrier_ok() and wl.s2.barrier_ok()
     lp, l2, pr = m._logpi_dev(X, P)
@@ -807,6 +832,15 @@ def measure_msharded(ctx, args, e2e=True):
             "traffic_source": tsrc,
             "clocks": sampler.summary(),
         }
+        # the theta <-> m transposition rides inside the Legendre kernels (peer stores / bulk pulls): NVML's link counters
+        # around the timed region are the evidence of what actually crossed NVLink (no separate collective exists to count)
+        npix_t, nscale_px = L * (2 * L - 1), int(tr.ncoefs_global)
+        line["nvlink"] = {"tx_bytes_per_iteration_all_gpus": nvl[0] if nvl[0] >= 0 else None,
+                          "rx_bytes_per_iteration_all_gpus": nvl[1] if nvl[1] >= 0 else None,
+                          "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links), difference around the timed graph replays, summed over ranks",
+                          "expected_bytes_per_iteration": (16.0 * (2 * npix_t + 2 * nscale_px) * (world - 1) / world) if world > 1 else 0.0,
+                          "expected_note": "ring-Fourier slabs of one iteration: 2 spin-2 SHTs at L (16 B x L(2L-1) each) and the two "
+                                           "multi-scale wavelet stages (16 B x ncoefs each), of which a share (N-1)/N changes rank"}
         if e2e_val is not None:
             line["e2e"] = {"value": e2e_val, "unit": "iterations/s", "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(nbytes),
                            "steps": e2e_steps, "api": "MYULA.iterate_host on every rank's local rows (pinned host buffers)"}
