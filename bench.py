@@ -228,7 +228,21 @@ class Ctx:
             # stdout carries ONE JSON line: NCCL's own log (version banner, NCCL_DEBUG=INFO topology / comm lines) goes to
             # stderr instead of being switched off
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"  # NCCL honours NCCL_DEBUG_FILE only above the VERSION level
+            # belt and braces: while the communicator comes up (NCCL prints its banner at the first collective) this
+            # process's stdout IS stderr
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
             self.dist = dist
 
     def barrier(self):
@@ -757,11 +771,12 @@ def measure_msharded(ctx, args, e2e=True):
     # ~36 launches + 12 peer barriers per iteration are launch-latency bound when issued one by one)
     eager_ms = ms_total
     chain = m.capture(X, P, iterations=1)
-    for _ in range(20):
+    nv0 = nvlink_counters(ctx.local)  # BEFORE the warm-up replays: nothing may idle the GPU between warm-up and timing
+    nwarm = 20
+    for _ in range(nwarm):
         chain.step()
     ctx.barrier()
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    nv0 = nvlink_counters(ctx.local)
     g0.record()
     for _ in range(steps):
         chain.step()
@@ -769,7 +784,7 @@ def measure_msharded(ctx, args, e2e=True):
     ctx.barrier()
     nv1 = nvlink_counters(ctx.local)
     ms_total = g0.elapsed_time(g1)
-    nvl = [(nv1[0] - nv0[0]) / steps, (nv1[1] - nv0[1]) / steps] if (nv0 and nv1) else [-1.0, -1.0]
+    nvl = [(nv1[0] - nv0[0]) / (steps + nwarm), (nv1[1] - nv0[1]) / (steps + nwarm)] if (nv0 and nv1) else [-1.0, -1.0]
     nvl = ctx.reduce(nvl, op="sum")  # bytes per iteration over all ranks (negative: counters unavailable)
     X, P = chain.state()
     ok = tr.plan.barrier_ok() and wl.s0.barrier_ok() and wl.s2.barrier_ok()
@@ -837,7 +852,9 @@ def measure_msharded(ctx, args, e2e=True):
         npix_t, nscale_px = L * (2 * L - 1), int(tr.ncoefs_global)
         line["nvlink"] = {"tx_bytes_per_iteration_all_gpus": nvl[0] if nvl[0] >= 0 else None,
                           "rx_bytes_per_iteration_all_gpus": nvl[1] if nvl[1] >= 0 else None,
-                          "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links), difference around the timed graph replays, summed over ranks",
+                          "source": "NVML NVLINK_THROUGHPUT_DATA_TX/RX (all links), difference around the graph replays, summed over ranks; null = NVML "
+                                    "answers NOT_SUPPORTED in this VM (nvidia-smi nvlink -gt d prints N/A: gpurun_out/nvlink_probe.log), and ncu may not "
+                                    "wrap a multi-rank command, so the expected figure below is the plan's own count",
                           "expected_bytes_per_iteration": (16.0 * (2 * npix_t + 2 * nscale_px) * (world - 1) / world) if world > 1 else 0.0,
                           "expected_note": "ring-Fourier slabs of one iteration: 2 spin-2 SHTs at L (16 B x L(2L-1) each) and the two "
                                            "multi-scale wavelet stages (16 B x ncoefs each), of which a share (N-1)/N changes rank"}

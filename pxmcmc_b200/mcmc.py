@@ -603,8 +603,17 @@ class GraphedChain:
         with torch.cuda.graph(self.graph):
             # the chain advances IN PLACE: the update kernel and the operator's last kernel write into X / P
             # (no copy-back, no ATen kernel inside the graph)
-            for _ in range(self.iterations):
-                sampler.iterate(self.X, self.P, out=(self.X, self.P))
+            import os
+
+            if os.environ.get("PXM_GRAPH_COPYBACK"):  # development A/B switch: the round-1 form (fresh buffers + copy-back)
+                x, p = self.X, self.P
+                for _ in range(self.iterations):
+                    x, p = sampler.iterate(x, p)
+                self.X.copy_(x)
+                self.P.copy_(p)
+            else:
+                for _ in range(self.iterations):
+                    sampler.iterate(self.X, self.P, out=(self.X, self.P))
 
     def step(self):
         """advance the chain by `iterations` iterations (asynchronous, like any kernel launch)"""
