@@ -167,12 +167,21 @@ def run_reference(args):
         "e2e": {"value": value_at_L, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def bind_to_gpu_numa_node(local):
     """pin this rank's threads to the CPUs next to its GPU BEFORE any pinned host buffer is allocated (first touch):
     the end-to-end path moves ~1 GB per step and GPU over PCIe, and host memory on the far socket halves that"""
@@ -661,7 +670,7 @@ def run_ours(args):
                 "sample": f"4 consecutive chain-iterations of the numpy oracle (port of the reference's Python layer over a numpy "
                           f"restatement of ssht / s2let; the real wheels are not installable here) at L={args.ref_L} ({t_it:.1f} s each on one core)"
                           + ("" if args.ref_L == L else f", scaled by the O(L^3) flop ratio {scale:.1f} to L={L}")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
 
 
@@ -871,7 +880,7 @@ def run_msharded(args):
     ctx = Ctx()
     line = measure_msharded(ctx, args)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     ctx.close()
 
 
@@ -897,6 +906,11 @@ def main():
                     help="chains: the BASELINE metric (independent chains, weak scaling); wl-msharded: config 4, one "
                          "weak-lensing chain m-sharded over the GPUs (strong scaling; defaults L=512 B=2)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything else this process prints (the samplers' "DONE", progress lines,
+    # library banners) goes to stderr; emit() writes the line to the real stdout
+    global _REAL_STDOUT
+    _REAL_STDOUT = sys.stdout
+    sys.stdout = sys.stderr
     if args.workload == "wl-msharded":
         if args.L == L_DEF and args.B == B_DEF:
             args.L, args.B = 512, 2.0
