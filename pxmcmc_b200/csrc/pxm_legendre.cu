@@ -37,6 +37,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+// the same copy with an L2 eviction-priority hint: table tiles are read once per launch and, at 0.2-4 GB per
+// transform, can never stay in the 126 MB L2 -- streamed evict-first they stop flushing the state vectors, the ring
+// arrays and the FFT tables out of it between the launches of an iteration
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   const uint32_t addr = smem_u32(bar);
@@ -59,6 +74,12 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+#ifdef PXM_LEG_NO_L2_HINT
+#define LEG_TABLE_COPY(dst, src, bytes, bar) bulk_g2s(dst, src, bytes, bar)
+#else
+#define LEG_TABLE_COPY(dst, src, bytes, bar) bulk_g2s_hint(dst, src, bytes, bar, pol)
+#endif
 
 constexpr int LEG_CONSUMER_WARPS = 8;
 constexpr int LEG_THREADS = (LEG_CONSUMER_WARPS + 1) * 32;  // + one TMA producer warp
@@ -117,6 +138,9 @@ pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmP
     // ===================== TMA producer warp (one elected lane) =====================
     if (lane == 0) {
       int it = 0;
+#ifndef PXM_LEG_NO_L2_HINT
+      const uint64_t pol = l2_evict_first_policy();
+#endif
       for (int s = 0; s < item.seg_count; ++s) {
         const PxmLegSeg sg = segs[item.seg_begin + s];
         const int nst = ORIENT == 0 ? sg.nk : 2 * sg.nk;
@@ -130,11 +154,11 @@ pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmP
           if (ORIENT == 0) {
             const double* srcA = tab + sg.a_off + (size_t)k * (size_t)sg.a_kstride;
             for (int j = 0; j < sg.nmt; ++j)
-              bulk_g2s(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
+              LEG_TABLE_COPY(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
           } else {
             const double* srcA = tab + sg.a_off + (size_t)(k >> 1) * (size_t)sg.a_kstride + (k & 1) * C::A_PIECE;
             for (int j = 0; j < sg.nmt; ++j)
-              bulk_g2s(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
+              LEG_TABLE_COPY(dstA + j * C::A_PIECE, srcA + (size_t)j * (size_t)sg.a_mstride, C::A_PIECE * 8, bar);
           }
           double* dstB = sB + slot * C::B_STAGE;
           // m-sharded plans: the ring block may live in a peer's workspace (pulled over NVLink)
