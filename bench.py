@@ -419,12 +419,31 @@ def measure_single_chain(ctx, args, iters=500):
         torch.cuda.synchronize()
         per.append(a.elapsed_time(b) / (iters // 5))
     ms_it = float(np.median(per))
-    tb = int(op.transform._plan(1).table_bytes)
+    import ctypes as C
+
+    from pxmcmc_b200 import _lib
+
+    fam = (C.c_longlong * 4)()
+    _lib.check(_lib.lib.pxm_wav_plan_table_bytes_by_family(op.transform._plan(1).h, fam))
+    # stage times of the same iteration launched eagerly (library events around every launch)
+    n = 200
+    _lib.check(_lib.lib.pxm_profile_begin(16 * n + 64))
+    x, p_ = chain.state()
+    x, p_ = x.clone(), p_.clone()
+    for _ in range(n):
+        x, p_ = m.iterate(x, p_)
+    msk, cnt = (C.c_double * 3)(), (C.c_longlong * 3)()
+    _lib.check(_lib.lib.pxm_profile_end(msk, cnt))
     chain.release()
     del chain, m, op
+    streamed = 2 * int(fam[0] + fam[1])  # Lambda_L and the kappa-weighted W_j, once for Psi and once for Psi^dagger
     return {"iterations_per_s": 1e3 / ms_it, "ms_per_iteration": ms_it, "iterations_timed": iters,
             "mode": "one chain, iteration replayed as one CUDA graph (in-place state), Philox noise; median of 5 blocks",
-            "table_bytes_streamed_per_iteration": 2 * tb}
+            "eager_stage_us": {"legendre": msk[0] / n * 1e3, "ring_fft": msk[1] / n * 1e3, "elementwise": msk[2] / n * 1e3},
+            "table_bytes_streamed_per_iteration": streamed,
+            "legendre_table_stream_GBps": streamed / (msk[0] / n / 1e3) / 1e9 if msk[0] > 0 else None,
+            "note": "10 launches of 18-36 us each: at one chain every kernel is a single short wave whose duration is its own "
+                    "load latency chain (ncu: long_scoreboard 59 % in the ring FFT), not a throughput limit"}
 
 
 def measure_configs(ctx, args):
