@@ -972,6 +972,321 @@ pxm_ring_fft3_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_
   }
 }
 
+#ifdef PXM_FFT_PAIRSPLIT
+// =============================================================================================
+// DEVELOPMENT VARIANT, compiled only with -DPXM_FFT_PAIRSPLIT (correct -- it passes the ring-FFT parity tests -- but measured
+// SLOWER: 1.57 vs 1.14 ms per 64-chain step; profiles/fft5_r2_metrics.txt: +49 % instructions from selects, shuffles, doubled
+// twiddle generation and index arithmetic; FP64 pipe 48 % at 16 warps per SM).
+// Pair-split variant of the persistent staged transform (pxm_ring_fft5_kernel): the same items, staging,
+// work-buffer layout and three passes as pxm_ring_fft3_kernel, but every 32-point column / row DFT is shared
+// by a PAIR of threads (adjacent lanes l and l ^ 4) that hold 16 points each and swap halves with warp
+// shuffles.  Half the registers per thread (<= 128) => 256-thread CTAs, 2 per SM = 16 warps per SM instead
+// of 8: the round-2 ablations showed the two-CTA kernel bound by exposed latency at 2 warps per scheduler,
+// not by FP64 issue or shared-memory bandwidth.
+//   pass 1  (pruned forward DFT over j1, inputs j1 >= R1/2 are zero):  thread h of a pair computes
+//           X[2q + h] = DFT_{R1/2}(x_j W_R1^{h j})[q]  -- the same code for both threads, the input twiddle
+//           selected by h; no exchange.
+//   middle  (row DFT over j2, x filter, inverse DFT):  thread h transforms the inputs j2 = 2i + h (radix-2
+//           decimation in time), the pair swaps 8 values and each finishes 8 of the 16 butterflies
+//           (k = i + 8h: the extra twiddle W_32^{8h} = (-i)^h is a predicated rotation); the inverse runs the
+//           mirror image (decimation in frequency, one swap) and leaves thread h with the outputs j2 = 2q + h.
+//   pass 3  (pruned inverse DFT over k1, only outputs j1 < R1/2 needed): thread h transforms the inputs
+//           k1 = 2q + h, one swap, thread h finishes the outputs j1 = i + (R1/4) h.
+// Lane layout: lane = 8 (column & 3) + 4 h + (ring & 3): the 4 rings of a row-group stay on adjacent lanes
+// (32-byte sectors of the k4-interleaved ring array), partners are 4 lanes apart, and every shared-memory
+// access of a quarter-warp (4 rings x 2 halves) falls on 32 distinct banks.
+// =============================================================================================
+__device__ __forceinline__ cplx shfl_pair(cplx v) {
+  return make_double2(__shfl_xor_sync(0xffffffffu, v.x, 4), __shfl_xor_sync(0xffffffffu, v.y, 4));
+}
+__device__ __forceinline__ cplx csel(bool p, cplx a, cplx b) { return make_double2(p ? a.x : b.x, p ? a.y : b.y); }
+
+// x[q] *= f * w^q, q < N, where f is a per-thread factor and w a per-thread base (radix-4 power tree)
+template <int N>
+__device__ __forceinline__ void twiddle_tree_f(cplx* x, cplx f, cplx w) {
+  const cplx w2 = cmul(w, w), w3 = cmul(w2, w), w4 = cmul(w2, w2);
+  cplx b = f;  // f (w^4)^a
+#pragma unroll
+  for (int a = 0; a < N / 4; ++a) {
+    x[4 * a] = cmul(x[4 * a], b);
+    x[4 * a + 1] = cmul(x[4 * a + 1], cmul(b, w));
+    x[4 * a + 2] = cmul(x[4 * a + 2], cmul(b, w2));
+    x[4 * a + 3] = cmul(x[4 * a + 3], cmul(b, w3));
+    if (a + 1 < N / 4) b = cmul(b, w4);
+  }
+}
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft5_pass1(const PxmFftGroup& gr, const Fft3Item& it, cplx* __restrict__ s,
+                                                const unsigned char* __restrict__ stage,
+                                                const cplx* __restrict__ chirp_s, const cplx* __restrict__ arena) {
+  constexpr int H1 = R1 / 2;       // nonzero inputs = outputs per thread
+  constexpr int STEP = 32 / R1;    // W_R1 = W_32^STEP
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ tw2 = arena + gr.tw2_off;  // [k1][j2]
+  for (int idx = threadIdx.x; idx < nr * R2 * 2; idx += blockDim.x) {
+    const int h = (idx >> 2) & 1, j2 = (idx >> 3) & (R2 - 1);
+    const int r = ((idx >> 8) << 2) | (idx & 3);
+    const int nj = (it.t0 + r < rings) ? n : 0;  // rows past the end of the grid are zeros
+    cplx x[H1];
+    if (DIR == 0) {
+      const cplx* row = reinterpret_cast<const cplx*>(stage) + r * n;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        x[j1] = (j < nj) ? cmul(row[j], chirp_s[j]) : make_double2(0.0, 0.0);
+      }
+    } else {
+      const unsigned char* grp = stage + (size_t)(r >> 2) * ((ell * 128 + 1023) & ~1023);
+      const int rl = r & 3;
+#pragma unroll
+      for (int j1 = 0; j1 < H1; ++j1) {
+        const int j = j1 * R2 + j2;
+        cplx v = make_double2(0.0, 0.0);
+        if (j < nj) {
+          const bool minus = j >= ell;  // order m = j - n < 0: second half of the 128-byte row
+          const int am = minus ? n - j : j;
+          const int d = (minus ? 8 : 0) + rl;  // re at double d, im at d + 4 (two chunks further)
+          const unsigned char* row = grp + am * 128 + (d & 1) * 8;
+          const int sw = am & 7, ch = d >> 1;
+          const double re = *reinterpret_cast<const double*>(row + ((ch ^ sw) << 4));
+          const double im = *reinterpret_cast<const double*>(row + (((ch + 2) ^ sw) << 4));
+          const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+          v = cmul(make_double2(flip_sign(re, neg), flip_sign(im, neg ^ (int)0x80000000)), chirp_s[j]);
+        }
+        x[j1] = v;
+      }
+    }
+    // input twiddle W_R1^{h j1}: identity for h = 0 (same instructions for both halves, constants by select)
+#pragma unroll
+    for (int j1 = 1; j1 < H1; ++j1) {
+      double c, sn;
+      w32(j1 * STEP, &c, &sn);
+      x[j1] = twc<false>(x[j1], h ? c : 1.0, h ? sn : 0.0);
+    }
+    dftR<H1, false>(x);  // x[q] = X[2q + h]
+    // inter-pass twiddle W_M^{(2q + h) j2} = (W^{j2})^h (W^{2 j2})^q
+    {
+      const cplx w1 = tw2[R2 + j2];
+      const cplx f = h ? w1 : make_double2(1.0, 0.0);
+      twiddle_tree_f<H1>(x, f, cmul(w1, w1));
+    }
+    cplx* dst = s + r * RS + j2 + h * (R2 + 1);
+#pragma unroll
+    for (int q = 0; q < H1; ++q) dst[2 * q * (R2 + 1)] = x[q];
+  }
+}
+
+// middle pass, R2 = 32: 16 points per thread
+template <int R1>
+__device__ __forceinline__ void ring_fft5_middle(const PxmFftGroup& gr, cplx* __restrict__ s,
+                                                 const cplx* __restrict__ arena) {
+  constexpr int R2 = 32;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const cplx* __restrict__ bhat = arena + gr.bhat2_off;
+  const cplx* __restrict__ tw2t = arena + gr.tw2_off + R1 * R2;  // [j2][k1]
+  for (int idx = threadIdx.x; idx < nr * R1 * 2; idx += blockDim.x) {
+    const bool h = (idx >> 2) & 1;
+    // columns k1: 3 + log2(R1) bits above the ring / half bits; R1 * 8 thread slots per group of 4 rings
+    const int k1 = (idx >> 3) & (R1 - 1);
+    const int r = ((idx / (8 * R1)) << 2) | (idx & 3);
+    cplx* row = s + r * RS + k1 * (R2 + 1) + (h ? 1 : 0);
+    cplx y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) y[i] = row[2 * i];
+    dft16<false>(y);  // h = 0: E[k], h = 1: O[k]
+    cplx p[8], q[8];
+    // swap: thread 0 keeps E[0..7] and receives O[0..7]; thread 1 keeps O[8..15] and receives E[8..15]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const cplx got = shfl_pair(csel(h, y[i], y[8 + i]));
+      p[i] = csel(h, got, y[i]);        // E[k], k = i + 8 h
+      q[i] = csel(h, y[8 + i], got);    // O[k]
+      if (h) q[i] = rot90<false>(q[i]); // W_32^{8} = -i
+    }
+    // X[k] = E[k] + W_32^k O[k], X[k + 16] = E[k] - W_32^k O[k]; times the filter spectrum
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double c, sn;
+      w32(i, &c, &sn);
+      bfly_tw<false>(p[i], q[i], c, sn);
+    }
+    {
+      const int k0 = h ? 8 : 0;
+      prefetched<8, PXM_PF2>([&](int i) { return bhat[(k0 + i) * R1 + k1]; }, [&](int i, cplx b) { p[i] = cmul(p[i], b); });
+      prefetched<8, PXM_PF2>([&](int i) { return bhat[(k0 + i + 16) * R1 + k1]; }, [&](int i, cplx b) { q[i] = cmul(q[i], b); });
+    }
+    // inverse, decimation in frequency: u[k] = X[k] + X[k+16], v[k] = (X[k] - X[k+16]) W_32^{-k}
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const cplx u = cadd(p[i], q[i]);
+      cplx d = csub(p[i], q[i]);
+      if (h) d = rot90<true>(d);  // W_32^{-8} = +i
+      double c, sn;
+      w32(i, &c, &sn);
+      p[i] = u;
+      q[i] = (i == 0) ? d : twc<true>(d, c, sn);
+    }
+    // swap: thread 0 collects u[0..15] (even outputs), thread 1 collects v[0..15] (odd outputs)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const cplx got = shfl_pair(csel(h, p[i], q[i]));  // thread 1 sends u[8 + i], thread 0 sends v[i]
+      y[i] = csel(h, got, p[i]);
+      y[8 + i] = csel(h, q[i], got);
+    }
+    dft16<true>(y);  // y[qq] = x[2 qq + h]
+    // inverse inter-pass twiddle conj(W_M^{(2qq + h) k1})
+    {
+      cplx w1 = tw2t[R1 + k1];
+      w1.y = -w1.y;
+      const cplx f = h ? w1 : make_double2(1.0, 0.0);
+      twiddle_tree_f<16>(y, f, cmul(w1, w1));
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) row[2 * i] = y[i];
+  }
+}
+
+template <int DIR, int R1, int R2>
+__device__ __forceinline__ void ring_fft5_pass3(const PxmFftGroup& gr, const Fft3Item& it, const cplx* __restrict__ s,
+                                                const cplx* __restrict__ chirp_s, cplx* __restrict__ pix,
+                                                size_t pix_chain_stride, double* __restrict__ F, int nld) {
+  constexpr int H1 = R1 / 2;     // inputs per thread
+  constexpr int Q1 = R1 / 4;     // outputs per thread
+  constexpr int STEP = 32 / R1;
+  const int n = gr.n, rings = gr.rings, ell = gr.ell;
+  const int nr = 1 << gr.pad;
+  const int RS = ring_stride2(R1, R2);
+  const size_t col0 = (size_t)it.chain * 4;  // paired layout only (the launcher checks)
+  for (int idx = threadIdx.x; idx < nr * R2 * 2; idx += blockDim.x) {
+    const bool h = (idx >> 2) & 1;
+    const int j2 = (idx >> 3) & (R2 - 1);
+    const int r = ((idx >> 8) << 2) | (idx & 3);
+    const int t = it.t0 + r;
+    const cplx* src = s + r * RS + j2 + (h ? (R2 + 1) : 0);
+    cplx x[H1];
+#pragma unroll
+    for (int q = 0; q < H1; ++q) x[q] = src[2 * q * (R2 + 1)];
+    dftR<H1, true>(x);  // h = 0: E[j], h = 1: O[j], j < R1/2
+    // z[j] = E[j] + W_R1^{-j} O[j], j < R1/2: thread h finishes j = i + (R1/4) h; W_R1^{-R1/4} = +i
+    cplx z[Q1];
+#pragma unroll
+    for (int i = 0; i < Q1; ++i) {
+      const cplx got = shfl_pair(csel(h, x[i], x[Q1 + i]));  // thread 1 sends O[i], thread 0 sends E[Q1 + i]
+      const cplx e = csel(h, got, x[i]);
+      cplx o = csel(h, x[Q1 + i], got);
+      if (h) o = rot90<true>(o);
+      double c, sn;
+      w32(i * STEP, &c, &sn);
+      z[i] = add_tw<true>(e, o, c, sn);
+    }
+    if (t >= rings) continue;
+    const int j1base = h ? Q1 : 0;
+    if (DIR == 0) {
+      double* frow = F + gr.f_off + ((size_t)(t >> 2) * (size_t)nld + col0) * 4 + (size_t)(t & 3);
+      const size_t ss = gr.slot_stride;
+#pragma unroll
+      for (int i = 0; i < Q1; ++i) {
+        const int j = (j1base + i) * R2 + j2;
+        if (j < n) {
+          const cplx v = cmul(z[i], chirp_s[j]);
+          const bool minus = j >= ell;
+          const int am = minus ? n - j : j;
+          double* dst = frow + (size_t)am * ss + (minus ? 8 : 0);
+          const int neg = (minus && (am & 1)) ? (int)0x80000000 : 0;
+          dst[0] = flip_sign(v.x, neg);
+          dst[4] = flip_sign(v.y, neg);  // next column of the k4-interleaved layout
+        }
+      }
+    } else {
+      cplx* row = pix + (size_t)it.chain * pix_chain_stride + gr.pix_off + (size_t)(t - gr.ring0) * n;
+#pragma unroll
+      for (int i = 0; i < Q1; ++i) {
+        const int j = (j1base + i) * R2 + j2;
+        if (j < n) {
+          const cplx v = cmul(z[i], chirp_s[j]);
+          row[j] = make_double2(v.x, flip_sign(v.y, (int)0x80000000));
+        }
+      }
+    }
+  }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256, 2)
+pxm_ring_fft5_kernel(const __grid_constant__ PxmFftGroupTable tab, const __grid_constant__ Fft3Blocks blocks,
+                     const __grid_constant__ Fft3Maps maps, cplx* __restrict__ pix, size_t pix_chain_stride,
+                     double* __restrict__ F, int nld, const cplx* __restrict__ arena, int nchains, long long nitems) {
+  extern __shared__ __align__(1024) unsigned char fsm5[];
+  unsigned char* stage = fsm5;  // 1024-byte aligned: the TMA swizzle phase is (row & 7)
+  cplx* s = reinterpret_cast<cplx*>(fsm5 + PXM_FFT3_STAGE);
+  cplx* chirp_s = reinterpret_cast<cplx*>(fsm5 + PXM_FFT3_STAGE + PXM_FFT3_WORK);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(fsm5 + PXM_FFT3_STAGE + PXM_FFT3_WORK + PXM_FFT3_CHIRP);
+  long long item = blockIdx.x;
+  if (item >= nitems) return;
+  if (threadIdx.x == 0) {
+    if (smem_u32(fsm5) & 1023) __trap();
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  Fft3Item cur, nxt;
+  int ib = (int)(item / nchains), ic = (int)(item - (long long)ib * nchains);
+  const int db = (int)gridDim.x / nchains, dc = (int)gridDim.x - db * nchains;
+  fft3_find(tab, blocks, ib, ic, &cur);
+  nxt = cur;
+  fft3_stage<DIR>(tab.g[cur.gi], cur, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[cur.gi]]);
+  int chirp_group = -1;
+  for (; item < nitems; item += gridDim.x) {
+    const PxmFftGroup& gr = tab.g[cur.gi];
+    const bool big = gr.logM == 10;
+    if (cur.gi != chirp_group) {  // a few times per launch: the blocks of a group are consecutive items
+      __syncthreads();            // pass 3 of the previous item has finished with the old chirp
+      const cplx* __restrict__ chirp = arena + gr.chirp_off;
+      const double rs = sqrt(gr.scale / (double)gr.M);
+      for (int j = threadIdx.x; j < gr.n; j += blockDim.x) {
+        const cplx c = chirp[j];
+        chirp_s[j] = make_double2(c.x * rs, c.y * rs);
+      }
+      chirp_group = cur.gi;
+    }
+    __syncthreads();        // pass 3 of the previous item has left the work buffer
+    mbar_wait(bar, phase);  // the staged inputs have landed
+    phase ^= 1;
+    if (big)
+      ring_fft5_pass1<DIR, 32, 32>(gr, cur, s, stage, chirp_s, arena);
+    else
+      ring_fft5_pass1<DIR, 16, 32>(gr, cur, s, stage, chirp_s, arena);
+    __syncthreads();
+    if (item + gridDim.x < nitems) {
+      ib += db;
+      ic += dc;
+      if (ic >= nchains) {
+        ic -= nchains;
+        ++ib;
+      }
+      fft3_find(tab, blocks, ib, ic, &nxt);
+      fft3_stage<DIR>(tab.g[nxt.gi], nxt, stage, bar, pix, pix_chain_stride, &maps.m[blocks.map_of_group[nxt.gi]]);
+    }
+    if (big)
+      ring_fft5_middle<32>(gr, s, arena);
+    else
+      ring_fft5_middle<16>(gr, s, arena);
+    __syncthreads();
+    if (big)
+      ring_fft5_pass3<DIR, 32, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld);
+    else
+      ring_fft5_pass3<DIR, 16, 32>(gr, cur, s, chirp_s, pix, pix_chain_stride, F, nld);
+    cur = nxt;
+  }
+}
+
+#endif  // PXM_FFT_PAIRSPLIT
+
 #ifdef PXM_FFT_PINGPONG
 // =============================================================================================
 // DEVELOPMENT VARIANT, compiled only with -DPXM_FFT_PINGPONG (measured SLOWER: 1.31 vs 1.17 ms per 64-chain step,
@@ -1317,6 +1632,7 @@ int pxm_fft_rings_per_cta_log(int M) {
 }
 
 static int g_fft_legacy = 0;
+static int g_fft_pair = 0;      // persistent class: the pair-split kernel (16 points per thread, 16 warps per SM)
 static int g_fft_pingpong = 1;  // builds with -DPXM_FFT_PINGPONG: the ping-pong kernel (1) or the two-CTA kernel (0)
 constexpr int PXM_FFT_SMEM = (4096 + 256 + 32) * 16;  // up to 4096 complex points (+1/16 padding) per CTA
 
@@ -1333,6 +1649,10 @@ int pxm_fft_setup_tables(const PxmFftGroup* d_groups, const PxmFftGroup* h_group
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT2_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
+#ifdef PXM_FFT_PAIRSPLIT
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft5_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
+    PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT3_SMEM));
+#endif
 #ifdef PXM_FFT_PINGPONG
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT4_SMEM));
     PXM_CUDA(cudaFuncSetAttribute(pxm_ring_fft4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PXM_FFT4_SMEM));
@@ -1449,6 +1769,17 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
 #else
       const int g3 = (int)std::min<long long>(nitems, 2LL * nsm);  // 2 CTAs per SM (shared memory, 252 registers)
 #endif
+#ifdef PXM_FFT_PAIRSPLIT
+      if (g_fft_pair) {
+        // pair-split kernel: 256-thread CTAs, 16 points per thread, 2 CTAs per SM = 16 warps per SM
+        if (dir == 0)
+          pxm_ring_fft5_kernel<0><<<g3, 256, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                    nitems);
+        else
+          pxm_ring_fft5_kernel<1><<<g3, 256, PXM_FFT3_SMEM, stream>>>(tab, blocks, maps, px, pix_chain_stride, F, nld, ar, nchains,
+                                                                    nitems);
+      } else
+#endif
 #ifdef PXM_FFT_PINGPONG
       if (g_fft_pingpong) {
         // one 256-thread CTA per SM whose two 4-warp groups alternate between FP64 and memory sections
@@ -1493,9 +1824,12 @@ int pxm_fft_launch(int dir, const PxmFftGroup* d_groups, const PxmFftGroup* h_gr
 // 0: choose by grid size, 1: always the multi-pass kernel, 2: always the two-pass kernel (where it applies),
 // 3: two-pass, with the persistent staged kernel for the radix-32 class (what 0 picks for large grids)
 // 4: like 3 but with the two-CTA persistent kernel instead of the ping-pong one; any other value re-enables it
+// 5: like 3 with the pair-split persistent kernel, 6: like 3 with the 32-points-per-thread persistent kernel
 void pxm_fft_set_legacy(int on) {
   g_fft_pingpong = on != 4;
-  g_fft_legacy = on == 4 ? 3 : on;
+  if (on == 5) g_fft_pair = 1;
+  if (on == 6) g_fft_pair = 0;
+  g_fft_legacy = (on >= 4) ? 3 : on;
 }
 
 #ifdef PXM_FFT3_TIMING
