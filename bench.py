@@ -208,6 +208,18 @@ def csrc_sha():
     return h.hexdigest()[:16]
 
 
+def fft_stage_traffic(traffic, ring_mode):
+    """mean DRAM bytes per executed ring-FFT stage: all four stages of the literal step, or only the two coefficient-side
+    stages (the large ones) when the predictions are carried as ring coefficients"""
+    ls = [d["bytes"] for d in traffic.get("ring_fft_launches", [])]
+    if not ls:
+        return traffic.get("ring_fft_bytes_per_stage")
+    if ring_mode:
+        big = [b for b in ls if b > 0.5 * max(ls)]
+        return sum(big) / len(big)
+    return sum(ls) / len(ls)
+
+
 def load_traffic():
     """DRAM traffic per launch of the dominant kernels from the tracked ncu summary profiles/traffic_r2.json
     (regenerated by scripts/refresh_traffic.py under ncu); `current` says whether the kernels have changed since"""
@@ -311,7 +323,12 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     ncoef, npix = op.nparams, L * (2 * L - 1)
     rng = np.random.default_rng(7 + ctx.rank)
     X = D.to_dev_c(rng.laplace(size=(nch, ncoef)))
-    P = D.to_dev_c(op.forward(X))
+    # the form MYULA.run carries the predictions in: ring-Fourier coefficients of the image when the operator allows it
+    # (Identity measurement, inverse covariance constant along rings: the pixel-side ring-FFT pair of consecutive
+    # iterations cancels), pixels otherwise (--no-ring-fusion)
+    op.fuse_ring = not args.no_ring_fusion
+    P = m._initial_preds(X)
+    ring_mode = m._ring_mode()
     for _ in range(max(args.warmup, 3)):
         X, P = m.iterate(X, P)
     # the GPU leaves its idle clocks only after some tens of ms of load: keep iterating (untimed)
@@ -338,7 +355,7 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     _lib.check(_lib.lib.pxm_profile_end(ms_kind, cnt_kind))
     launches = _lib.lib.pxm_launch_count() - l0
     ms, leg, fft, el = ctx.reduce([ms, ms_kind[0], ms_kind[1], ms_kind[2]])
-    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches),
+    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches), "ring_mode": ring_mode,
            "stage_ms": {"legendre": leg / steps, "ring_fft": fft / steps, "elementwise": el / steps},
            "counts": [int(c) for c in cnt_kind], "table_bytes": int(op.transform._plan(nch).table_bytes)}
     # sustained rate: `blocks` blocks of `block_iters` iterations, each timed on the device; median over blocks of the
@@ -365,7 +382,7 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
         Xh = torch.empty((nch, ncoef), dtype=torch.complex128).pin_memory()
         Ph = torch.empty((nch, npix), dtype=torch.complex128).pin_memory()
         Xh.copy_(X.cpu())
-        Ph.copy_(P.cpu())
+        Ph.copy_(m._pix(P).cpu())
         Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
         m.iterate_host(Xh, Ph, Xo, Po)  # warm-up
         ctx.barrier()
@@ -404,7 +421,8 @@ def measure_single_chain(ctx, args, iters=500):
     reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 1e-6, L=L, B=B, J_min=J_min)
     m = MYULA(op, reg, prm, noise="device", seed=99)
     X = D.to_dev_c(np.random.default_rng(0).laplace(size=(1, op.nparams)))
-    P = D.to_dev_c(op.forward(X))
+    op.fuse_ring = not args.no_ring_fusion
+    P = m._initial_preds(X)
     chain = m.capture(X, P, iterations=1)
     for _ in range(50):
         chain.step()
@@ -428,7 +446,7 @@ def measure_single_chain(ctx, args, iters=500):
     # stage times of the same iteration launched eagerly (library events around every launch)
     n = 200
     _lib.check(_lib.lib.pxm_profile_begin(16 * n + 64))
-    x, p_ = chain.state()
+    x, p_ = chain._state_raw()
     x, p_ = x.clone(), p_.clone()
     for _ in range(n):
         x, p_ = m.iterate(x, p_)
@@ -630,14 +648,18 @@ def run_ours(args):
         flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
         st = main["stage_ms"]
         leg_tf = flops_step / (st["legendre"] / 1e3) / 1e12 if st["legendre"] > 0 else None
-        fft_bytes_step = 2 * 32.0 * (ncoef + npix) * nch
+        # ring FFT stages executed per step: coefficient side in and out, plus -- unless the predictions are carried as
+        # ring coefficients -- pixel side in and out; every stage moves 16 B per sample on each of its two sides
+        fft_bytes_step = 2 * 32.0 * (ncoef + (0 if main["ring_mode"] else npix)) * nch
+        fft_stages = 2 if main["ring_mode"] else 4
         fft_gbs = fft_bytes_step / (st["ring_fft"] / 1e3) / 1e9 if st["ring_fft"] > 0 else None
-        roof_fft = {"bound": "hbm", "kernel": "pxm_ring_fft3_kernel (persistent TMA-staged two-pass Bluestein ring FFT; 4 stages = "
-                                              "4 launches + 2 of pxm_ring_fft2_kernel<.,0> for lengths <= 256 per step)",
+        roof_fft = {"bound": "hbm", "kernel": "pxm_ring_fft3_kernel (persistent TMA-staged two-pass Bluestein ring FFT) + pxm_ring_fft2_kernel<.,0> "
+                                              "for lengths <= 256: one launch of each per stage",
                     "achieved": fft_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": (fft_gbs / hbm_peak) if fft_gbs else None,
                     # dram__bytes_read + dram__bytes_write per stage (mean of the 4 stages of one step), from the tracked ncu summary
-                    "traffic": traffic.get("ring_fft_bytes_per_stage") if default_wl else None,
-                    "launches_timed": main["counts"][1], "algorithmic_bytes_per_stage": fft_bytes_step / 4,
+                    "traffic": (fft_stage_traffic(traffic, main["ring_mode"]) if default_wl else None),
+                    "launches_timed": main["counts"][1], "algorithmic_bytes_per_stage": fft_bytes_step / fft_stages,
+                    "stages_per_step": fft_stages,
                     "ms_per_step": st["ring_fft"], "peak_source": hbm_src,
                     "note": "HBM class per SURVEY 8(d): algorithmic bytes = pixels or coefficients in + ring coefficients out = "
                             "32 B x (ncoef + npix) per Psi per chain.  DRAM traffic = algorithmic bytes and HBM is ~20-25 % busy: the "
@@ -657,6 +679,8 @@ def run_ours(args):
             "config": {"workload": f"MYULA L={L} B={B} J_min={J_min} synthesis, Identity measurement, S2_Wavelets_L1, "
                                    f"{nch} independent chains per GPU (config 5 of BASELINE.json; per-chain it/s = value/(n_gpus*chains))",
                        "chains_per_gpu": nch, "ncoefs": ncoef, "npix": npix, "noise": "Philox4x32-10 in-kernel",
+                       "predictions": ("ring-Fourier coefficients of the image (the pixel-side ring-FFT pair of consecutive iterations cancels; "
+                                       "pixels on demand)" if main["ring_mode"] else "pixels"),
                        "l2_note": f"inputs larger than L2: per-step working set {(ncoef + npix) * nch * 16 * 3 / 2**20:.0f} MiB of state + "
                                   f"{main['table_bytes'] / 2**20:.0f} MiB of Legendre tables exceeds the 126 MB L2"},
             "per_chain_iterations_per_s": steps / (ms / 1e3),
@@ -917,6 +941,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=5, help="sustained-rate blocks after the K-step timed region (0: none)")
     ap.add_argument("--block-iters", type=int, default=100)
     ap.add_argument("--strong-total", type=int, default=64, help="chains in TOTAL of the strong-scaling split (config 5)")
+    ap.add_argument("--no-ring-fusion", action="store_true", help="carry the predictions as pixels (the reference's literal composition)")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no per-chain / config 1-4 / strong-split legs)")
     ap.add_argument("--ref-L", type=int, default=256, help="bandlimit of the bounded CPU sample")
     ap.add_argument("--ref-procs", type=int, default=64)

@@ -71,6 +71,22 @@ int pxm_wav_analysis_adjoint(pxm_wav_plan* plan, const void* d_coef, void* d_pix
  * A_fwd(L,0) (WeakLensing, pxmcmc/measurements.py:223,239) composes with them exactly (A_fwd o A_inv = I on f_lm). */
 int pxm_wav_synthesis_harmonic(pxm_wav_plan* plan, const void* d_coef, void* d_flm, int nbatch, void* stream);
 int pxm_wav_synthesis_adjoint_harmonic(pxm_wav_plan* plan, const void* d_flm, void* d_coef, int nbatch, void* stream);
+/* Ring-Fourier form of the predictions: ForwardOperator with an Identity measurement behind a wavelet synthesis
+ * (pxmcmc/forward.py:60-72, pxmcmc/measurements.py:43-56).  Psi ends with the ring FFT F_m(theta_t) -> pixels and the next
+ * gradient starts with the ring FFT pixels -> F_m(theta_t); the DFT of length n = 2L-1 is invertible, so for an inverse
+ * covariance that is constant along every ring the pair cancels:  FFT_in(ic (FFT_out(F) - data)) = ic_t (n F - FFT_in(data)).
+ * Ring array = the plan's layout [slot |m| < L][ring/4][col][ring%4] doubles, col = 4 chain + 2 (m<0) + (im);
+ * pxm_wav_ring_doubles: its size (all chains of the plan).  _to_ring: synthesis without its last stage; _from_ring:
+ * synthesis_adjoint without its first stage; ring_to_pix / pix_to_ring: those stages alone; ring_resid:
+ * out = ic[t] ((2L-1) pred - data), data = pix_to_ring(data) with nbatch = 1, d_ic = L complex values (one per ring).
+ * Not available on m-sharded plans. */
+long long pxm_wav_ring_doubles(const pxm_wav_plan* plan);
+int pxm_wav_synthesis_to_ring(pxm_wav_plan* plan, const void* d_coef, double* d_ring, int nbatch, void* stream);
+int pxm_wav_synthesis_adjoint_from_ring(pxm_wav_plan* plan, const double* d_ring, void* d_coef, int nbatch, void* stream);
+int pxm_wav_ring_to_pix(pxm_wav_plan* plan, const double* d_ring, void* d_pix, int nbatch, void* stream);
+int pxm_wav_pix_to_ring(pxm_wav_plan* plan, const void* d_pix, double* d_ring, int nbatch, void* stream);
+int pxm_wav_ring_resid(pxm_wav_plan* plan, const double* d_ring_pred, const double* d_ring_data, const void* d_ic,
+                       double* d_ring_out, int nbatch, void* stream);
 /* host-only: kappa0[L], kappa[(J-J_min+1)][L] of pys2let.wavelet_tiling
  * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);

@@ -235,6 +235,34 @@ __global__ void k_resid(const cplx* __restrict__ preds, const cplx* __restrict__
   }
 }
 
+// Residual in ring-Fourier space (see pxm_wav_ring_resid): out = ic[t] * (scale * pred - data) on k4-interleaved ring
+// arrays [slot][ring/4][col][ring%4], col = 4 chain + 2 (m < 0) + (im); the data array holds chain 0 only.
+__global__ void k_ring_resid(const double* __restrict__ pred, const double* __restrict__ data, const cplx* __restrict__ ic,
+                             double* __restrict__ out, int rings, int nld, int ncols, double scale,
+                             unsigned long long slot_stride, unsigned long long total) {
+  // one thread per (slot, row-group, column pair, ring%4); ring%4 fastest, then the column pair
+  const unsigned int halfc = (unsigned int)ncols >> 1;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned int r4 = (unsigned int)(i & 3);
+    unsigned long long q = i >> 2;
+    const unsigned int c2 = (unsigned int)(q % halfc);
+    q /= halfc;
+    const unsigned int rgs = (unsigned int)((rings + 3) >> 2);
+    const unsigned int rg = (unsigned int)(q % rgs);
+    const unsigned long long slot = q / rgs;
+    const unsigned int t = rg * 4 + r4;
+    if ((int)t >= rings) continue;
+    const unsigned long long base = slot * slot_stride + ((unsigned long long)rg * nld) * 4 + r4;
+    const unsigned long long ire = base + (unsigned long long)(2 * c2) * 4, iim = ire + 4;
+    const unsigned long long dre = base + (unsigned long long)(2 * (c2 & 1)) * 4, dim_ = dre + 4;  // chain 0, same sign
+    const double vx = scale * pred[ire] - data[dre], vy = scale * pred[iim] - data[dim_];
+    const cplx c = ic[t];
+    out[ire] = c.x * vx - c.y * vy;
+    out[iim] = c.x * vy + c.y * vx;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // per-chain reductions (deterministic two-stage)
 //  kind 0: sum |w_i x_i|                         (prior.py:28-35, :83-84)   -> (re, 0)
@@ -751,6 +779,15 @@ int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* 
   return PXM_OK;
 }
 
+int pxm_launch_ring_resid(const double* pred, const double* data, const void* ic, double* out, int nslots, int rings,
+                          int nld, int ncols, double scale, unsigned long long slot_stride, cudaStream_t st) {
+  const unsigned long long total = (unsigned long long)nslots * ((rings + 3) / 4) * (ncols / 2) * 4;
+  if (!total) return PXM_OK;
+  k_ring_resid<<<grid_for((size_t)total), 256, 0, st>>>(pred, data, (const cplx*)ic, out, rings, nld, ncols, scale, slot_stride, total);
+  PXM_LAUNCHED();
+  return PXM_OK;
+}
+
 constexpr int PXM_REDUCE_PARTS = 148;
 
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
@@ -819,6 +856,7 @@ int pxm_elem_preload() {
   PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update_pair));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_resid));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_ring_resid));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage1));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage2));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_gradlogpi));

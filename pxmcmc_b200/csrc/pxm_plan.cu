@@ -990,6 +990,90 @@ int pxm_wav_synthesis_adjoint_harmonic(pxm_wav_plan* p, const void* d_flm, void*
   return PXM_OK;
 }
 
+// Ring-Fourier form of the predictions (Identity measurement behind a wavelet synthesis).  Psi ends with the ring FFT
+// F_m(theta_t) -> pixels and the next gradient evaluation starts with the ring FFT pixels -> F_m(theta_t)
+// (pxmcmc/forward.py:60-72 with an Identity measurement); the DFT of length n = 2L - 1 is invertible, so for an inverse
+// covariance that is constant along every ring the pair cancels:
+//     FFT_in( ic (FFT_out(F) - data) ) = ic_t ( n F - FFT_in(data) ).
+// The ring array is the plan's own layout [slot |m| < L][ring/4][col][ring%4] (doubles), col = 4 chain + 2 (m < 0) + (im),
+// `nld` columns, rings padded to a multiple of 32; pxm_wav_ring_doubles gives its size for all chains of the plan.
+// Not available on m-sharded plans.
+static int ring_check(const pxm_wav_plan* p, int nb) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(nb >= 1 && nb <= p->nb, "nbatch exceeds the plan's max_batch");
+  PXM_REQUIRE(p->ps.sh.world == 1, "ring-space predictions are not available on m-sharded plans");
+  return PXM_OK;
+}
+long long pxm_wav_ring_doubles(const pxm_wav_plan* p) { return p ? (long long)p->Rfull.doubles() : 0; }
+
+int pxm_wav_synthesis_to_ring(pxm_wav_plan* p, const void* d_coef, double* d_ring, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  PxmPeers out = pe;
+  out.p[0] = d_ring - p->Rfull.off;  // the last contraction stores its tiles straight into the caller's ring array
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, D.fft_scales_in.groups.data(), (int)D.fft_scales_in.groups.size(),
+                         D.fft_scales_in.ctas, const_cast<void*>(d_coef), (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_in.class_mask, st)); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, pe, D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                              (int)D.a_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, out, D.s_full.d_items.d, D.s_full.d_segs.d,
+                              (int)D.s_full.items.size(), p->nld, st, pxm_debug_naive())); }
+  return PXM_OK;
+}
+
+int pxm_wav_synthesis_adjoint_from_ring(pxm_wav_plan* p, const double* d_ring, void* d_coef, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  PxmPeers in = pe;
+  in.p[0] = const_cast<double*>(d_ring) - p->Rfull.off;  // the first contraction pulls its ring blocks from the caller's array
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, in, pe, D.a_full.d_items.d, D.a_full.d_segs.d,
+                              (int)D.a_full.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, pe, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+                              (int)D.s_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, D.fft_scales_out.groups.data(), (int)D.fft_scales_out.groups.size(),
+                         D.fft_scales_out.ctas, d_coef, (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_out.class_mask, st)); }
+  return PXM_OK;
+}
+
+int pxm_wav_ring_to_pix(pxm_wav_plan* p, const double* d_ring, void* d_pix, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  ProfScope _ps(1, st);
+  return pxm_fft_launch(1, D.fft_full_out.d_groups.d, D.fft_full_out.groups.data(), (int)D.fft_full_out.groups.size(), D.fft_full_out.ctas,
+                        d_pix, (size_t)p->npix_local, const_cast<double*>(d_ring) - p->Rfull.off, p->nld, p->ffttab.d_arena, nb,
+                        D.fft_full_out.class_mask, st);
+}
+
+int pxm_wav_pix_to_ring(pxm_wav_plan* p, const void* d_pix, double* d_ring, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  ProfScope _ps(1, st);
+  return pxm_fft_launch(0, D.fft_full_in.d_groups.d, D.fft_full_in.groups.data(), (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas,
+                        const_cast<void*>(d_pix), (size_t)p->npix_local, d_ring - p->Rfull.off, p->nld, p->ffttab.d_arena, nb,
+                        D.fft_full_in.class_mask, st);
+}
+
+// d_ring_out = ic[t] * ((2L - 1) d_ring_pred - d_ring_data); d_ring_data = pxm_wav_pix_to_ring of the data (chain 0 of a ring
+// array); d_ic: L complex values, the inverse covariance of every ring.  d_ring_out may be d_ring_pred.
+int pxm_wav_ring_resid(pxm_wav_plan* p, const double* d_ring_pred, const double* d_ring_data, const void* d_ic, double* d_ring_out,
+                       int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  ProfScope _ps(2, (cudaStream_t)stream);
+  return pxm_launch_ring_resid(d_ring_pred, d_ring_data, d_ic, d_ring_out, p->Rfull.nslots, p->Rfull.rows, p->nld, 4 * nb,
+                               (double)(2 * p->L - 1), p->Rfull.slot_stride, (cudaStream_t)stream);
+}
+
 // =========================================================================
 //        HEALPix plan (healpy.alm2map / map2alm: data preparation, once per run)
 // =========================================================================

@@ -114,6 +114,8 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
 int pxm_launch_counter_add(unsigned long long* ctr, unsigned long long inc, cudaStream_t st);
 int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* out, size_t n, size_t nchains,
                      cudaStream_t st);
+int pxm_launch_ring_resid(const double* pred, const double* data, const void* ic, double* out, int nslots, int rings,
+                          int nld, int ncols, double scale, unsigned long long slot_stride, cudaStream_t st);
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
                       double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st,
                       const double* d_par = nullptr);

@@ -176,6 +176,49 @@ class WaveletPlan:
         return self._run(lib.pxm_wav_synthesis_adjoint_harmonic, flm, self.L * self.L, self.ncoefs, True)
 
 
+    # ---- ring-Fourier form of the pixel side (pxm_wav_*_ring*): float64 tensors [ring_doubles] in the plan's layout
+    @property
+    def ring_doubles(self):
+        return int(lib.pxm_wav_ring_doubles(self.h))
+
+    def new_ring(self, device, like=None):
+        if like is not None:
+            return like
+        return torch.empty(self.ring_doubles, dtype=FDT, device=device)
+
+    def synthesis_to_ring(self, coef, out=None):
+        c2, _ = batch2d(coef)
+        if c2.shape[1] != self.ncoefs or c2.shape[0] > self.nbatch:
+            raise ValueError("coefficient batch does not fit the plan")
+        ring = self.new_ring(c2.device, out)
+        check(lib.pxm_wav_synthesis_to_ring(self.h, ptr(c2), ptr(ring), c2.shape[0], stream_ptr()))
+        return ring
+
+    def synthesis_adjoint_from_ring(self, ring, nb):
+        out = torch.empty((nb, self.ncoefs), dtype=CDT, device=ring.device)
+        check(lib.pxm_wav_synthesis_adjoint_from_ring(self.h, ptr(ring), ptr(out), nb, stream_ptr()))
+        return out
+
+    def ring_to_pix(self, ring, nb):
+        out = torch.empty((nb, self.npix), dtype=CDT, device=ring.device)
+        check(lib.pxm_wav_ring_to_pix(self.h, ptr(ring), ptr(out), nb, stream_ptr()))
+        return out
+
+    def pix_to_ring(self, pix, out=None):
+        p2, _ = batch2d(pix)
+        if p2.shape[1] != self.npix or p2.shape[0] > self.nbatch:
+            raise ValueError("pixel batch does not fit the plan")
+        ring = out if out is not None else torch.zeros(self.ring_doubles, dtype=FDT, device=p2.device)
+        check(lib.pxm_wav_pix_to_ring(self.h, ptr(p2), ptr(ring), p2.shape[0], stream_ptr()))
+        return ring
+
+    def ring_resid(self, pred, data_ring, ic_rings, nb, out=None):
+        """ic[t] * ((2L-1) pred - data) on ring arrays; ic_rings: complex128 [L]"""
+        ring = self.new_ring(pred.device, out)
+        check(lib.pxm_wav_ring_resid(self.h, ptr(pred), ptr(data_ring), ptr(ic_rings), ptr(ring), nb, stream_ptr()))
+        return ring
+
+
 class ShtPlan:
     """pxm_sht_plan: the four pyssht-level transforms for one (L, spin, nbatch)."""
 

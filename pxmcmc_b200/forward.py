@@ -8,6 +8,27 @@ from .transforms import SphericalWaveletTransform
 from .utils import mw_size
 
 
+class RingPreds:
+    """Predictions of an Identity-measurement synthesis operator kept as ring-Fourier coefficients F_m(theta_t) of the
+    image (the plan's ring array, float64 [ring_doubles]) instead of pixels: what `ForwardOperator.forward_ring`
+    returns and `gradg_from_ring` consumes.  `.pixels()` gives the ordinary [nchains, npix] predictions."""
+
+    __slots__ = ("t", "op", "nb")
+
+    def __init__(self, t, op, nb):
+        self.t, self.op, self.nb = t, op, int(nb)
+
+    def pixels(self):
+        return self.op.ring_to_pixels(self)
+
+    def clone(self):
+        return RingPreds(self.t.clone(), self.op, self.nb)
+
+    def scaled_(self, c):
+        self.t.mul_(c)
+        return self
+
+
 class ForwardOperator:
     """Transform + measurement + Gaussian data fidelity (pxmcmc/forward.py:9-88).
 
@@ -71,6 +92,70 @@ class ForwardOperator:
         return (self.fuse_harmonic and self.setting == "synthesis" and getattr(m, "_pxm_harmonic_input", False)
                 and (type(m).forward, type(m).adjoint) == getattr(type(m), "_pxm_fused_methods", None)  # not overridden
                 and hasattr(t, "_inverse_harmonic") and getattr(t, "spin", 0) == 0 and getattr(t, "L", None) == getattr(m, "L", -1))
+
+    # Identity measurement behind a wavelet synthesis: Psi ends with the ring FFT F -> pixels and the gradient of the next
+    # iteration starts with the ring FFT pixels -> F.  The DFT of length 2L-1 is invertible, so when the inverse
+    # covariance is constant along every ring (a scalar sigma, or the reference's per-ring noise sqrt(sigma^2 / area),
+    # experiments/earthtopography/main.py:92-94) the pair cancels: FFT_in(ic (FFT_out(F) - d)) = ic_t ((2L-1) F - FFT_in(d)).
+    # The samplers then carry the predictions as ring coefficients (`RingPreds`) and convert them to pixels only where
+    # pixels are needed (tracked samples, checkpoints, the host-buffer path).  Same results to round-off;
+    # `fuse_ring = False` restores the literal composition.
+    fuse_ring = True
+
+    def _ring_fusable(self):
+        t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
+        if not (self.fuse_ring and self.setting == "synthesis" and self._diag is not None):
+            return False
+        if type(m) is not Identity or m.ndata != m.npix:
+            return False
+        if (type(t).inverse is not SphericalWaveletTransform.inverse
+                or type(t).inverse_adjoint is not SphericalWaveletTransform.inverse_adjoint or not hasattr(t, "_plan")):
+            return False
+        if len(self._diag) != t.L * (2 * t.L - 1):
+            return False
+        return self._ic_rings() is not None
+
+    def _ic_rings(self):
+        """inverse covariance of every ring as a complex device vector [L], or None when it varies along a ring"""
+        c = getattr(self, "_ic_rings_cache", None)
+        if c is None or c[0] is not self._diag:
+            L = self.transform.L
+            d = np.asarray(self._diag).reshape(L, 2 * L - 1)
+            ok = bool(np.all(d == d[:, :1]))
+            self._ic_rings_cache = c = (self._diag, D.to_dev_c(np.ascontiguousarray(d[:, 0])) if ok else None)
+        return c[1]
+
+    def _ring_data(self, nb):
+        c = getattr(self, "_ring_data_cache", None)
+        if c is None:
+            c = self._ring_data_cache = {}
+        if nb not in c:
+            data_d, _ = self._upload()
+            c[nb] = self.transform._plan(nb).pix_to_ring(data_d.reshape(1, -1))
+        return c[nb]
+
+    def forward_ring(self, X, out=None):
+        """predictions of the state(s) as ring coefficients (synthesis without its last ring FFT)"""
+        x = D.to_dev_c(X)
+        x = x.unsqueeze(0) if x.dim() == 1 else x
+        nb = x.shape[0]
+        t = self.transform._plan(nb).synthesis_to_ring(x, out=None if out is None else out.t)
+        return out if out is not None else RingPreds(t, self, nb)
+
+    def gradg_from_ring(self, R):
+        """gradient of the data fidelity from ring-space predictions: Psi^dagger without its first ring FFT"""
+        plan = self.transform._plan(R.nb)
+        resid = plan.ring_resid(R.t, self._ring_data(R.nb), self._ic_rings(), R.nb)
+        return plan.synthesis_adjoint_from_ring(resid, R.nb)
+
+    def ring_to_pixels(self, R):
+        return self.transform._plan(R.nb).ring_to_pix(R.t, R.nb)
+
+    def pixels_to_ring(self, P):
+        p = D.to_dev_c(P)
+        p = p.unsqueeze(0) if p.dim() == 1 else p
+        plan = self.transform._plan(p.shape[0])
+        return RingPreds(plan.pix_to_ring(p), self, p.shape[0]).scaled_(1.0 / (2 * self.transform.L - 1))
 
     def _forward_synthesis(self, X):
         if self._fused():

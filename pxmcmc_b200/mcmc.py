@@ -17,6 +17,7 @@ import torch
 from scipy.stats import laplace
 
 from . import device as D
+from .forward import RingPreds
 from .prior import L1, is_library_l1
 from .utils import cheb1der, chebyshev1
 
@@ -92,6 +93,23 @@ class PxMCMC:
             return self.prior._T_args()
         return None
 
+    def _ring_mode(self):
+        """True when the predictions can be carried as ring-Fourier coefficients (ForwardOperator._ring_fusable): the
+        pixel-side ring FFT pair of consecutive iterations cancels"""
+        f = getattr(self.forward, "_ring_fusable", None)
+        return bool(f is not None and getattr(self.forward, "_pxm_native", False) and f())
+
+    def _initial_preds(self, Xd):
+        """predictions of the state(s) in the form the run loops carry them: `RingPreds` in ring mode, else pixels"""
+        if self._ring_mode():
+            return self.forward.forward_ring(Xd)
+        return D.to_dev_c(self._forward_dev(Xd))
+
+    @staticmethod
+    def _pix(P):
+        """pixel-space predictions [nchains, ndata] whatever form they are carried in"""
+        return P.pixels() if isinstance(P, RingPreds) else P
+
     def _state(self, X):
         """[nchains, nparams] complex device tensor from a numpy vector / tensor"""
         x = D.to_dev_c(X)
@@ -164,9 +182,12 @@ class PxMCMC:
         return lp[0], l2[0], pr[0]
 
     def _gradlogpi_dev(self, Xd, Pd=None):
-        if Pd is None:
-            Pd = self._forward_dev(Xd)
-        gradg = D.to_dev_c(self._gradg_dev(Pd))
+        if Pd is None and self._ring_mode():
+            gradg = self.forward.gradg_from_ring(self.forward.forward_ring(Xd))
+        else:
+            if Pd is None:
+                Pd = self._forward_dev(Xd)
+            gradg = D.to_dev_c(self._gradg_dev(self._pix(Pd)))
         fused = self._fused_prox()
         if fused is not None:
             return D.gradlogpi_dev(Xd, None, fused[0], fused[1], gradg, self.lmda)
@@ -261,6 +282,7 @@ class PxMCMC:
         here waits for the device: the reductions stay device tensors, state and predictions are snapshotted on the
         compute stream and leave through `_Spill`; the host arrays are filled when the slot is reused, on `flush`, or
         before anything reads them (progress lines, checkpoints, the end of `run`)."""
+        curr_preds = self._pix(curr_preds)
         terms = self._logpi_terms_dev(X_curr, curr_preds) if self.async_spill else None
         if terms is None:
             logPi, L2, prior = self._logpi_dev(X_curr, curr_preds)
@@ -317,7 +339,7 @@ class PxMCMC:
     def save_checkpoint(self, path, i, j, X_curr, curr_preds):
         """Everything `run(resume=path)` needs to continue the chain exactly where it stands after iteration
         i - 1: state and predictions, loop counters, and the common fields of `_save_ckpt`."""
-        self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(curr_preds))
+        self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(self._pix(curr_preds)))
 
     def load_checkpoint(self, path):
         """-> (i, j, X, preds) as device tensors"""
@@ -441,6 +463,8 @@ class MYULA(PxMCMC):
             i, j, X_curr, curr_preds = self.load_checkpoint(resume)
         else:
             X_curr, curr_preds = self._initial_sample(start_point)
+        if self._ring_mode():  # predictions carried as ring coefficients: the pixel-side FFT pair of every iteration cancels
+            curr_preds = self.forward.pixels_to_ring(curr_preds) if resume is not None else self.forward.forward_ring(X_curr)
         # Philox noise and a native operator: the iteration is replayed as one CUDA graph (small bandlimits are
         # launch-latency bound: 85 -> 63 us per iteration at L = 32); the noise stream is the eager one
         graphed = None
@@ -449,7 +473,7 @@ class MYULA(PxMCMC):
         while j < self.nsamples:
             if graphed is not None:
                 graphed.step()
-                X_curr, curr_preds = graphed.state()
+                X_curr, curr_preds = graphed._state_raw()
             else:
                 X_curr, curr_preds = self.iterate(X_curr, curr_preds)
             if i >= self.nburn:
@@ -469,6 +493,7 @@ class MYULA(PxMCMC):
         if checkpoint is not None:
             self.save_checkpoint(checkpoint, i, j, X_curr, curr_preds)
         self._track_flush()
+        curr_preds = self._pix(curr_preds)
         if graphed is not None:
             X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
             graphed.release()
@@ -480,6 +505,12 @@ class MYULA(PxMCMC):
         [nchains, .]: gradg -> prox -> proposal -> new predictions.  `out = (X_buf, P_buf)`: where the new state and
         predictions are written; the input buffers themselves are allowed (the update is elementwise and the old
         predictions are consumed before the new ones are produced), which is how captured graphs advance in place."""
+        if isinstance(curr_preds, RingPreds):
+            # ring mode: the gradient starts from, and the new predictions stop at, the ring coefficients of the image
+            gradg = self.forward.gradg_from_ring(curr_preds)
+            proxf = None if self._fused_prox() is not None else self._proxf_dev(X_curr)
+            X_new = self._propose_dev(X_curr, proxf, gradg, out=None if out is None else out[0])
+            return X_new, self.forward.forward_ring(X_new, out=None if out is None else out[1])
         gradg = D.to_dev_c(self._gradg_dev(curr_preds))
         proxf = None if self._fused_prox() is not None else self._proxf_dev(X_curr)
         if out is None:
@@ -587,7 +618,12 @@ class GraphedChain:
     def __init__(self, sampler, X, P, iterations=1):
         self.sampler, self.iterations = sampler, int(iterations)
         self.X = sampler._state(X).clone()
-        self.P = sampler._state(P).clone()
+        if isinstance(P, RingPreds):
+            self.P = P.clone()
+        elif sampler._ring_mode():
+            self.P = sampler.forward.pixels_to_ring(sampler._state(P))
+        else:
+            self.P = sampler._state(P).clone()
         sampler._dstep = torch.full((1,), sampler._step_counter + 1, dtype=torch.int64, device=self.X.device)
         # warm-up on a side stream (tables, kernel attributes, allocator pools), as CUDA graphs require
         side = torch.cuda.Stream()
@@ -621,6 +657,10 @@ class GraphedChain:
         self.sampler._step_counter += self.iterations
 
     def state(self):
+        """(X, predictions) as [nchains, .] tensors (ring-carried predictions are converted to pixels)"""
+        return self.X, PxMCMC._pix(self.P)
+
+    def _state_raw(self):
         return self.X, self.P
 
     def release(self):

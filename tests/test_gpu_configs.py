@@ -245,6 +245,17 @@ def test_config5_myula_L256_chain_batch(px, pool):
         assert rel_l2(Pn[c], Po) < TOL, f"predictions chain {c}: {rel_l2(Pn[c], Po):.2e}"
         assert np.isclose(lp[c], lpo, rtol=1e-10) and np.isclose(l2[c], l2o, rtol=1e-10) and np.isclose(pr[c], pro, rtol=1e-12)
     assert 0 < np.count_nonzero(proxd[2] == 0) < op.nparams  # the support test is not vacuous
+    # the form MYULA.run and bench.py carry the predictions in (ring coefficients of the image: the pixel-side ring-FFT pair
+    # of consecutive iterations cancels) against the same oracle iterations
+    from pxmcmc_b200.forward import RingPreds
+
+    Pr = m._initial_preds(Xd)
+    assert isinstance(Pr, RingPreds)
+    np.random.seed(77)
+    Xr, Pr = m.iterate(Xd, Pr)
+    Xr, Prp = Xr.cpu().numpy(), Pr.pixels().cpu().numpy()
+    for c in range(nch):
+        assert rel_l2(Xr[c], Xn[c]) < 1e-12 and rel_l2(Prp[c], Pn[c]) < 1e-12, f"ring-carried predictions, chain {c}"
 
 
 # ------------------------------------------------------------------ config 2

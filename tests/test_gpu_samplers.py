@@ -146,14 +146,15 @@ def test_graphed_chains_advance_in_place(px):
     eager = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
     graphed = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
     chain = graphed.capture(X0, P0, iterations=2)
-    ptrs = (chain.X.data_ptr(), chain.P.data_ptr())
-    x, p = X0, P0
+    ptr_of = lambda P: (P.t if hasattr(P, "t") else P).data_ptr()  # noqa: E731  (ring-carried predictions wrap their tensor)
+    ptrs = (chain.X.data_ptr(), ptr_of(chain.P))
+    x, p = X0, eager._initial_preds(X0)  # the form run() carries the predictions in (ring coefficients here)
     for _ in range(3):
         for _ in range(2):
             x, p = eager.iterate(x, p)
         chain.step()
-        assert torch.equal(chain.state()[0], x) and torch.equal(chain.state()[1], p)
-    assert (chain.X.data_ptr(), chain.P.data_ptr()) == ptrs
+        assert torch.equal(chain.state()[0], x) and torch.equal(chain.state()[1], eager._pix(p))
+    assert (chain.X.data_ptr(), ptr_of(chain.P)) == ptrs
     # kernels of one replay: only libpxmcmc_b200 kernels (no ATen copy / fill kernels)
     try:
         from torch.profiler import ProfilerActivity, profile
@@ -326,3 +327,99 @@ def test_async_spill_and_memmapped_chain_equal_the_synchronous_tracking(px, nois
 
     path = save_mcmc(mm, px.mcmc.PxMCMCParams(nsamples=7), str(tmp_path), "out")
     assert np.array_equal(load_mcmc(path)[0]["chain"], sync.chain)
+
+
+def _ring_case(px, sig, nchains, L=24, B=1.5, J=2, complex_data=True, **kw):
+    rng = np.random.default_rng(14)
+    data = rng.standard_normal(L * (2 * L - 1)) + (1j * rng.standard_normal(L * (2 * L - 1)) if complex_data else 0j)
+    op = px.forward.SphericalWaveletTransformOperator(data, sig, "synthesis", L, B, J, nchains=nchains)
+    prm = px.mcmc.PxMCMCParams(delta=1e-5, lmda=2e-5, mu=1.0, verbosity=0, nsamples=4, nburn=2, ngap=3,
+                               track=["logposterior", "L2", "prior", "chain", "predictions"])
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 2e-5, L=L, B=B, J_min=J)
+    return op, reg, prm
+
+
+@pytest.mark.parametrize("sig_kind,nchains", [("scalar", 1), ("scalar", 3), ("per_ring", 2)])
+def test_ring_carried_predictions_equal_the_pixel_composition(px, sig_kind, nchains):
+    """Identity measurement behind a wavelet synthesis: the ring FFT that ends Psi and the one that starts the next
+    gradient cancel when the inverse covariance is constant along rings; the samplers then carry the predictions as ring
+    coefficients.  Same iterations (1e-12), same tracked arrays of run(), same CUDA-graph chain as the pixel composition."""
+    import torch
+
+    from pxmcmc_b200 import device as D
+    from pxmcmc_b200.forward import RingPreds
+
+    L = 24
+    if sig_kind == "scalar":
+        sig = 0.3
+    else:  # the reference's per-ring noise level sqrt(sigma^2 / pixel area) (experiments/earthtopography/main.py:92-94)
+        sig = np.sqrt(0.05 / px.utils.calc_pixel_areas(L)).flatten()
+    op, reg, prm = _ring_case(px, sig, nchains)
+    assert op._ring_fusable()
+    rng = np.random.default_rng(3)
+    X0 = D.to_dev_c(rng.laplace(size=(nchains, op.nparams)))
+    ring = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
+    lit = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
+    Pr = ring._initial_preds(X0)
+    assert isinstance(Pr, RingPreds) and ring._ring_mode()
+    Pl = D.to_dev_c(op.forward(X0))
+    assert rel_l2(Pr.pixels().cpu().numpy(), Pl.cpu().numpy()) < 1e-12
+    back = op.pixels_to_ring(Pl)                                   # the conversion resume / capture use
+    assert rel_l2(back.pixels().cpu().numpy(), Pl.cpu().numpy()) < 1e-12
+    Xr, Xl = X0, X0
+    for _ in range(4):
+        Xr, Pr = ring.iterate(Xr, Pr)
+        Xl, Pl = lit.iterate(Xl, Pl)
+        assert isinstance(Pr, RingPreds)
+        assert rel_l2(Xr.cpu().numpy(), Xl.cpu().numpy()) < 1e-12
+        assert rel_l2(Pr.pixels().cpu().numpy(), Pl.cpu().numpy()) < 1e-12
+    assert rel_l2(op.gradg_from_ring(Pr).cpu().numpy(), op.calc_gradg(Pl).cpu().numpy()) < 1e-12
+    # run(): graphed, ring-carried vs the literal composition
+    start = rng.laplace(size=op.nparams)
+    a = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=9)
+    a.run(start)
+    op.fuse_ring = False
+    try:
+        assert not op._ring_fusable()
+        b = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=9)
+        b.run(start)
+    finally:
+        op.fuse_ring = True
+    for name in ("chain", "preds", "logPi", "L2s", "priors"):
+        assert rel_l2(getattr(a, name), getattr(b, name)) < 1e-10, name
+    assert rel_l2(a._final_state[1].cpu().numpy(), b._final_state[1].cpu().numpy()) < 1e-10
+    # a captured chain started from pixel predictions converts them and advances in place
+    g = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
+    chain = g.capture(X0, D.to_dev_c(op.forward(X0)), iterations=2)
+    chain.step()
+    chain.step()
+    assert isinstance(chain.P, RingPreds)
+    assert rel_l2(chain.state()[0].cpu().numpy(), Xl.cpu().numpy()) < 1e-12
+    assert rel_l2(chain.state()[1].cpu().numpy(), Pl.cpu().numpy()) < 1e-12
+    assert torch.isfinite(torch.view_as_real(chain.state()[1])).all()
+
+
+def test_ring_mode_is_refused_when_it_does_not_apply(px):
+    """an inverse covariance that varies along a ring, an analysis setting, a path-integral measurement, a user subclass
+    of the transform: the predictions stay pixels"""
+    from scipy import sparse as sp
+
+    L = 12
+    rng = np.random.default_rng(2)
+    sig = 0.1 + rng.random(L * (2 * L - 1))
+    op, reg, prm = _ring_case(px, sig, 1, L=L)
+    assert not op._ring_fusable() and not px.mcmc.MYULA(op, reg, prm)._ring_mode()
+    data = rng.standard_normal(L * (2 * L - 1))
+    assert not px.forward.SphericalWaveletTransformOperator(data, 0.1, "analysis", L, 2.0, 2)._ring_fusable()
+    A = sp.random(20, L * (2 * L - 1), density=0.1, random_state=1, format="csr")
+    assert not px.forward.PathIntegralOperator(A, rng.standard_normal(20), 0.1, "synthesis", L, 2.0, 2)._ring_fusable()
+
+    class Mine(px.transforms.SphericalWaveletTransform):
+        def inverse(self, X):
+            return 2 * super().inverse(X)
+
+    op2 = px.forward.ForwardOperator(data, 0.1, "synthesis", transform=Mine(L, 2.0, 2),
+                                     measurement=px.measurements.Identity(data.size, data.size), nparams=Mine(L, 2.0, 2).ncoefs)
+    assert not op2._ring_fusable()
+    op3, _, _ = _ring_case(px, 0.1, 1, L=L)
+    assert op3._ring_fusable()
