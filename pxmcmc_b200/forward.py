@@ -121,7 +121,9 @@ class ForwardOperator:
         if c is None or c[0] is not self._diag:
             L = self.transform.L
             d = np.asarray(self._diag).reshape(L, 2 * L - 1)
-            ok = bool(np.all(d == d[:, :1]))
+            # constant along every ring up to rounding: the reference's own per-ring noise levels come out of
+            # calc_pixel_areas with last-bit differences along phi (pxmcmc/utils.py:227-246)
+            ok = bool(np.all(np.abs(d - d[:, :1]) <= 1e-13 * np.abs(d[:, :1])))
             self._ic_rings_cache = c = (self._diag, D.to_dev_c(np.ascontiguousarray(d[:, 0])) if ok else None)
         return c[1]
 

@@ -339,12 +339,20 @@ class PxMCMC:
     def save_checkpoint(self, path, i, j, X_curr, curr_preds):
         """Everything `run(resume=path)` needs to continue the chain exactly where it stands after iteration
         i - 1: state and predictions, loop counters, and the common fields of `_save_ckpt`."""
-        self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(self._pix(curr_preds)))
+        extra = {}
+        if isinstance(curr_preds, RingPreds):  # the ring coefficients themselves: a resumed chain continues bit for bit
+            extra["P_ring"] = D.to_host(curr_preds.t)
+        self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(self._pix(curr_preds)), **extra)
 
     def load_checkpoint(self, path):
         """-> (i, j, X, preds) as device tensors"""
         f = self._load_ckpt(path)
-        return int(f["i"]), int(f["j"]), self._state(f["X"]), self._state(f["P"])
+        X = self._state(f["X"])
+        if "P_ring" in f and self._ring_mode():
+            P = RingPreds(torch.from_numpy(np.ascontiguousarray(f["P_ring"])).to(X.device), self.forward, X.shape[0])
+        else:
+            P = self._state(f["P"])
+        return int(f["i"]), int(f["j"]), X, P
 
     def _on_grid(self, i):
         return i >= self.nburn and (self.ngap == 0 or (i - self.nburn) % self.ngap == 0)
@@ -463,7 +471,8 @@ class MYULA(PxMCMC):
             i, j, X_curr, curr_preds = self.load_checkpoint(resume)
         else:
             X_curr, curr_preds = self._initial_sample(start_point)
-        if self._ring_mode():  # predictions carried as ring coefficients: the pixel-side FFT pair of every iteration cancels
+        if self._ring_mode() and not isinstance(curr_preds, RingPreds):
+            # predictions carried as ring coefficients: the pixel-side FFT pair of every iteration cancels
             curr_preds = self.forward.pixels_to_ring(curr_preds) if resume is not None else self.forward.forward_ring(X_curr)
         # Philox noise and a native operator: the iteration is replayed as one CUDA graph (small bandlimits are
         # launch-latency bound: 85 -> 63 us per iteration at L = 32); the noise stream is the eager one

@@ -498,7 +498,7 @@ def test_myula_graph_replay_matches_eager(px, iters_per_graph):
 
     op, eager = make()
     X0 = D.to_dev_c(rng.laplace(size=(1, op.nparams)))
-    P0 = D.to_dev_c(op.forward(X0))
+    P0 = eager._initial_preds(X0)  # the form run() carries the predictions in (ring coefficients for this operator)
     X, P = X0, P0
     for _ in range(6):
         X, P = eager.iterate(X, P)
@@ -508,10 +508,10 @@ def test_myula_graph_replay_matches_eager(px, iters_per_graph):
         chain.step()
     torch.cuda.synchronize()
     Xg, Pg = chain.state()
-    assert torch.equal(Xg, X) and torch.equal(Pg, P)  # bit-identical
+    assert torch.equal(Xg, X) and torch.equal(Pg, eager._pix(P))  # bit-identical
     assert graphed._step_counter == eager._step_counter == 6
     with pytest.raises(ValueError):
-        px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, P0)
+        px.mcmc.MYULA(op, eager.prior, prm, noise="host").capture(X0, eager._pix(P0))
 
 
 @pytest.mark.parametrize("mode,nb", [(2, 2), (3, 2), (3, 3), (3, 9)])

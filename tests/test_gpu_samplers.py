@@ -145,7 +145,7 @@ def test_graphed_chains_advance_in_place(px):
     P0 = D.to_dev_c(op.forward(X0))
     eager = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
     graphed = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nch, seed=3)
-    chain = graphed.capture(X0, P0, iterations=2)
+    chain = graphed.capture(X0, graphed._initial_preds(X0), iterations=2)
     ptr_of = lambda P: (P.t if hasattr(P, "t") else P).data_ptr()  # noqa: E731  (ring-carried predictions wrap their tensor)
     ptrs = (chain.X.data_ptr(), ptr_of(chain.P))
     x, p = X0, eager._initial_preds(X0)  # the form run() carries the predictions in (ring coefficients here)
@@ -407,7 +407,7 @@ def test_ring_mode_is_refused_when_it_does_not_apply(px):
     L = 12
     rng = np.random.default_rng(2)
     sig = 0.1 + rng.random(L * (2 * L - 1))
-    op, reg, prm = _ring_case(px, sig, 1, L=L)
+    op, reg, prm = _ring_case(px, sig, 1, L=L, B=2.0)
     assert not op._ring_fusable() and not px.mcmc.MYULA(op, reg, prm)._ring_mode()
     data = rng.standard_normal(L * (2 * L - 1))
     assert not px.forward.SphericalWaveletTransformOperator(data, 0.1, "analysis", L, 2.0, 2)._ring_fusable()
@@ -421,5 +421,5 @@ def test_ring_mode_is_refused_when_it_does_not_apply(px):
     op2 = px.forward.ForwardOperator(data, 0.1, "synthesis", transform=Mine(L, 2.0, 2),
                                      measurement=px.measurements.Identity(data.size, data.size), nparams=Mine(L, 2.0, 2).ncoefs)
     assert not op2._ring_fusable()
-    op3, _, _ = _ring_case(px, 0.1, 1, L=L)
+    op3, _, _ = _ring_case(px, 0.1, 1, L=L, B=2.0)
     assert op3._ring_fusable()
