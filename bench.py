@@ -39,6 +39,12 @@ def bandlimits(L, B, J_min):
     return out
 
 
+def workload_name(L, B, J_min):
+    """the same string in both arms (ours and --impl reference): the driver compares the configurations"""
+    return (f"MYULA L={L} B={B} J_min={J_min} synthesis, Identity measurement, S2_Wavelets_L1 "
+            "(config 5 of BASELINE.json: independent chains, chain-iterations/s)")
+
+
 def algorithmic_flops_per_chain_iteration(L, B, J_min):
     """F_it = 2 F_Psi = 8 (L^3 + sum_scales L_j^3) FP64 flops (FFT flops excluded)."""
     return 8.0 * (L ** 3 + sum(b ** 3 for b in bandlimits(L, B, J_min)))
@@ -162,7 +168,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value_at_L, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * mean_it * scale, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"MYULA L={args.L} B={args.B} J_min={args.J_min} synthesis, Identity measurement, S2_Wavelets_L1 (CPU: numpy port of the reference Python layer over a restatement of ssht/s2let)"},
+        "config": {"workload": workload_name(args.L, args.B, args.J_min),
+                   "implementation": "CPU: numpy port of the reference's Python layer over a restatement of ssht / s2let, one chain per process"},
         "cpu_baseline": {"value": value_at_L, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": value_at_L, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
@@ -329,6 +336,7 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     op.fuse_ring = not args.no_ring_fusion
     P = m._initial_preds(X)
     ring_mode = m._ring_mode()
+    pred_kind = op._ring_kind() if ring_mode else None
     for _ in range(max(args.warmup, 3)):
         X, P = m.iterate(X, P)
     # the GPU leaves its idle clocks only after some tens of ms of load: keep iterating (untimed)
@@ -355,7 +363,7 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     _lib.check(_lib.lib.pxm_profile_end(ms_kind, cnt_kind))
     launches = _lib.lib.pxm_launch_count() - l0
     ms, leg, fft, el = ctx.reduce([ms, ms_kind[0], ms_kind[1], ms_kind[2]])
-    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches), "ring_mode": ring_mode,
+    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches), "ring_mode": ring_mode, "pred_kind": pred_kind,
            "stage_ms": {"legendre": leg / steps, "ring_fft": fft / steps, "elementwise": el / steps},
            "counts": [int(c) for c in cnt_kind], "table_bytes": int(op.transform._plan(nch).table_bytes)}
     # sustained rate: `blocks` blocks of `block_iters` iterations, each timed on the device; median over blocks of the
@@ -645,9 +653,15 @@ def run_ours(args):
         default_wl = (L, B, J_min, nch) == (256, 1.5, 2, 64)
         ncoef, npix, steps = main["ncoef"], main["npix"], main["steps"]
         ms = main["ms"]
-        flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch
+        flops_step = algorithmic_flops_per_chain_iteration(L, B, J_min) * nch  # what the iteration is credited with
+        # flops of the contractions actually executed: in the harmonic (Gram) form the two full-L contractions
+        # (8 L^3 per chain) are replaced by one with G^m: 4 flops x sum_m (L-|m|)^2 entries
+        exec_flops_step = flops_step
+        if main.get("pred_kind") == "harm":
+            gram_entries = L * L + 2 * sum((L - m) ** 2 for m in range(1, L))
+            exec_flops_step = flops_step - nch * 8.0 * L ** 3 + nch * 4.0 * gram_entries
         st = main["stage_ms"]
-        leg_tf = flops_step / (st["legendre"] / 1e3) / 1e12 if st["legendre"] > 0 else None
+        leg_tf = exec_flops_step / (st["legendre"] / 1e3) / 1e12 if st["legendre"] > 0 else None
         # ring FFT stages executed per step: coefficient side in and out, plus -- unless the predictions are carried as
         # ring coefficients -- pixel side in and out; every stage moves 16 B per sample on each of its two sides
         fft_bytes_step = 2 * 32.0 * (ncoef + (0 if main["ring_mode"] else npix)) * nch
@@ -667,8 +681,14 @@ def run_ours(args):
                             ">= 2n), which DFMA shares with DMMA on this part (profiles/ubench_fp64_r1g.txt)"}
         roof_leg = {"bound": "tensor", "achieved": leg_tf, "peak": peak, "unit": "TFLOP/s", "frac": (leg_tf / peak) if leg_tf else None,
                     "traffic": traffic.get("legendre_bytes_per_launch") if default_wl else None,
-                    "kernel": "pxm_legendre_kernel (FP64 DMMA, 4 launches per step)", "launches_timed": main["counts"][0],
-                    "algorithmic_flops_per_launch": flops_step / 4, "ms_per_step": st["legendre"],
+                    "kernel": "pxm_legendre_kernel (FP64 DMMA)", "launches_timed": main["counts"][0],
+                    "launches_per_step": main["counts"][0] / steps,
+                    "executed_algorithmic_flops_per_step": exec_flops_step, "credited_flops_per_step_survey_8d": flops_step,
+                    "ms_per_step": st["legendre"],
+                    "note": "achieved = flops of the contractions executed / device time; with the Gram form of the pixel side "
+                            "(one contraction with G^m = (2L-1) Lambda^T Lambda instead of the two full-L contractions) fewer flops are "
+                            "executed than SURVEY 8(d) credits: against the credited figure the stage runs at "
+                            f"{flops_step / (st['legendre'] / 1e3) / 1e12 if st['legendre'] > 0 else 0:.1f} TFLOP/s",
                     "peak_source": "cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)"}
         # `roofline` = the dominant kernel BY TIME of this run
         fft_dominant = st["ring_fft"] >= st["legendre"]
@@ -676,11 +696,14 @@ def run_ours(args):
             "metric": METRIC, "value": world * nch * steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"MYULA L={L} B={B} J_min={J_min} synthesis, Identity measurement, S2_Wavelets_L1, "
-                                   f"{nch} independent chains per GPU (config 5 of BASELINE.json; per-chain it/s = value/(n_gpus*chains))",
+            "config": {"workload": workload_name(L, B, J_min),
+                       "implementation": f"{nch} independent chains per GPU as one batch (per-chain it/s = value/(n_gpus*chains))",
                        "chains_per_gpu": nch, "ncoefs": ncoef, "npix": npix, "noise": "Philox4x32-10 in-kernel",
-                       "predictions": ("ring-Fourier coefficients of the image (the pixel-side ring-FFT pair of consecutive iterations cancels; "
-                                       "pixels on demand)" if main["ring_mode"] else "pixels"),
+                       "predictions": ({"harm": "harmonic coefficients f_lm of the image: the pixel-side ring-FFT pair of consecutive iterations "
+                                                "cancels and, the inverse covariance being one constant, the two full-L Legendre contractions "
+                                                "collapse into one with the Gram matrix; pixels on demand (tracked samples)",
+                                        "ring": "ring-Fourier coefficients of the image (the pixel-side ring-FFT pair of consecutive iterations "
+                                                "cancels); pixels on demand"}.get(main.get("pred_kind"), "pixels")),
                        "l2_note": f"inputs larger than L2: per-step working set {(ncoef + npix) * nch * 16 * 3 / 2**20:.0f} MiB of state + "
                                   f"{main['table_bytes'] / 2**20:.0f} MiB of Legendre tables exceeds the 126 MB L2"},
             "per_chain_iterations_per_s": steps / (ms / 1e3),

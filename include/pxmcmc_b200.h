@@ -87,6 +87,20 @@ int pxm_wav_ring_to_pix(pxm_wav_plan* plan, const double* d_ring, void* d_pix, i
 int pxm_wav_pix_to_ring(pxm_wav_plan* plan, const void* d_pix, double* d_ring, int nbatch, void* stream);
 int pxm_wav_ring_resid(pxm_wav_plan* plan, const double* d_ring_pred, const double* d_ring_data, const void* d_ic,
                        double* d_ring_out, int nbatch, void* stream);
+/* Harmonic form of the same predictions, for an inverse covariance that is ONE (complex) constant over the sphere: per order m
+ * the ring-space composition is g = ic Lambda^T ((2L-1) Lambda f - D) = ic (G f - b) with the Gram matrix
+ * G^m = (2L-1) Lambda^T Lambda ((L-|m|)^2 entries, generated once per plan) and b = A_inv^dagger(data): one contraction
+ * with a third fewer entries replaces the two full-L contractions of pxm_wav_synthesis_to_ring + _from_ring, and the
+ * predictions are carried as f_lm.  Harmonic arrays: the plan's layout, concatenated slots |m| < L of [rows/4][col][rows%4]
+ * doubles, rows = l - |m| padded to 64, col = 4 chain + 2 (m<0) + (im); pxm_wav_harm_doubles = its size.
+ * _to_harm: synthesis stopped at f_lm; gram_gradient: coefficients of Psi^dagger ic (Psi X - data) from f = _to_harm(X) and
+ * d_b = pxm_wav_pix_to_harm_adjoint(data, nbatch = 1); harm_to_pix: the pixels of f.  Not on m-sharded plans. */
+long long pxm_wav_harm_doubles(const pxm_wav_plan* plan);
+int pxm_wav_synthesis_to_harm(pxm_wav_plan* plan, const void* d_coef, double* d_harm, int nbatch, void* stream);
+int pxm_wav_gram_gradient(pxm_wav_plan* plan, const double* d_harm, const double* d_b, double ic_re, double ic_im, void* d_coef,
+                          int nbatch, void* stream);
+int pxm_wav_harm_to_pix(pxm_wav_plan* plan, const double* d_harm, void* d_pix, int nbatch, void* stream);
+int pxm_wav_pix_to_harm_adjoint(pxm_wav_plan* plan, const void* d_pix, double* d_harm, int nbatch, void* stream);
 /* host-only: kappa0[L], kappa[(J-J_min+1)][L] of pys2let.wavelet_tiling
  * (pxmcmc/utils.py:117, pxmcmc/prior.py:121,132) */
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out);

@@ -45,6 +45,11 @@ SIGNATURES = {
     "pxm_wav_ring_to_pix": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_pix_to_ring": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_ring_resid": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "pxm_wav_harm_doubles": (_ll, [_vp]),
+    "pxm_wav_synthesis_to_harm": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pxm_wav_gram_gradient": (_i, [_vp, _vp, _vp, _d, _d, _vp, _i, _vp]),
+    "pxm_wav_harm_to_pix": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "pxm_wav_pix_to_harm_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wavelet_tiling": (_i, [_i, _d, _i, _vp, _vp, C.POINTER(_i)]),
     "pxm_hpx_plan_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "pxm_hpx_plan_destroy": (_i, [_vp]),

@@ -249,6 +249,37 @@ void build_s_items(Stage& S, const TableRef& tr, const HarmBuf& H, const RingBuf
   }
 }
 
+// Gram contraction:  harmonic buffer (same layout)  <-  G^m x harmonic buffer   (rows and columns of G relative to |m|)
+void build_g_items(Stage& S, const PxmTableLayout& T, const HarmBuf& H, int nld) {
+  S.orient = 0;
+  for (int s = 0; s < T.nslots; ++s) {
+    if (T.nlb[s] == 0) continue;
+    const int m = T.slot_m[s];
+    const int hs = H.slot_of(m);
+    const int nrow = H.L - std::abs(m);
+    for (int i = 0; 64 * i < nrow; ++i) {
+      PxmLegSeg sg = {};
+      sg.a_off = T.tile_off[s] + (ull)(2 * i) * T.nlb[s] * PXM_TILE_DOUBLES;
+      sg.a_kstride = PXM_TILE_DOUBLES;
+      sg.a_mstride = T.nlb[s] * PXM_TILE_DOUBLES;
+      sg.mt0 = 0;
+      sg.nmt = std::min(2, pxm_ceil_div(nrow - 64 * i, PXM_TILE_T));
+      sg.nk = T.nlb[s];
+      sg.b_off = H.slot_off[hs];
+      sg.src = 0;
+      PxmLegItem it = {};
+      it.c_off = H.slot_off[hs] + (ull)(64 * i) * nld;
+      it.seg_begin = (int)S.segs.size();
+      it.seg_count = 1;
+      it.nmt_out = sg.nmt;
+      it.cost = sg.nk * sg.nmt;
+      it.dst = 0;
+      S.segs.push_back(sg);
+      S.items.push_back(it);
+    }
+  }
+}
+
 struct ASource {
   const TableRef* tr;
   const RingBuf* R;
@@ -689,6 +720,27 @@ struct pxm_wav_plan {
   PxmDevVec<unsigned char> d_own;  // per harmonic slot: 1 when this rank owns the azimuthal order
   FftTables ffttab;
   WavDirection syn, ana;  // syn: synthesis + synthesis_adjoint ; ana: analysis + analysis_adjoint
+  // Gram form of the pixel side (pxm_wav_gram_gradient): G^m = (2L-1) Lambda_L^T Lambda_L, a second harmonic buffer
+  PxmTableLayout gramT;
+  Stage g_full;
+  double* d_gram = nullptr;
+  double* d_h2 = nullptr;
+  bool gram_built = false;
+
+  int ensure_gram() {
+    if (gram_built) return PXM_OK;
+    PXM_TRY(ensure(syn));
+    pxm_make_table_layout(gramT, L, L, L, 0, 0, L, 0, 0, 1);
+    PXM_CUDA(cudaMalloc(&d_gram, std::max<size_t>(gramT.doubles, 1) * 8));
+    PXM_CUDA(cudaMemset(d_gram, 0, std::max<size_t>(gramT.doubles, 1) * 8));
+    PXM_TRY(pxm_generate_gram(syn.full.T, d_tab, gramT, d_gram, (double)(2 * L - 1), 0));
+    PXM_CUDA(cudaMalloc(&d_h2, std::max<ull>(H.total, 1) * 8));
+    PXM_CUDA(cudaMemset(d_h2, 0, std::max<ull>(H.total, 1) * 8));
+    build_g_items(g_full, gramT, H, nld);
+    PXM_TRY(g_full.upload());
+    gram_built = true;
+    return PXM_OK;
+  }
 
   int ensure(WavDirection& D) {
     if (D.built) return PXM_OK;
@@ -849,6 +901,9 @@ int pxm_wav_plan_destroy(pxm_wav_plan* p) {
   p->ffttab.release();
   p->H.d_slot_off.release();
   p->d_own.release();
+  p->g_full.release();
+  if (p->d_gram) cudaFree(p->d_gram);
+  if (p->d_h2) cudaFree(p->d_h2);
   if (p->d_tab) cudaFree(p->d_tab);
   if (p->d_ws) cudaFree(p->d_ws);
   delete p;
@@ -1072,6 +1127,81 @@ int pxm_wav_ring_resid(pxm_wav_plan* p, const double* d_ring_pred, const double*
   ProfScope _ps(2, (cudaStream_t)stream);
   return pxm_launch_ring_resid(d_ring_pred, d_ring_data, d_ic, d_ring_out, p->Rfull.nslots, p->Rfull.rows, p->nld, 4 * nb,
                                (double)(2 * p->L - 1), p->Rfull.slot_stride, (cudaStream_t)stream);
+}
+
+// Harmonic form of the predictions, for an inverse covariance that is one (complex) constant over the sphere: the ring-space
+// composition above is  g = ic Lambda^T ((2L-1) Lambda f - D)  per order m, i.e.  g = ic (G f - b)  with the Gram matrix
+// G^m = (2L-1) Lambda^T Lambda ((L-|m|)^2 entries per order, generated once per plan from the Lambda_L tiles) and
+// b = Lambda^T D = A_inv^dagger(data): ONE contraction with a third fewer entries replaces the two full-L contractions, and
+// the predictions are carried as f_lm.  Harmonic arrays use the plan's layout: concatenated slots |m| < L of
+// [rows/4][col][rows%4] doubles, rows = l - |m| padded to 64, col = 4 chain + 2 (m<0) + (im); pxm_wav_harm_doubles = size.
+long long pxm_wav_harm_doubles(const pxm_wav_plan* p) { return p ? (long long)p->H.total : 0; }
+
+static PxmPeers harm_peers(const pxm_wav_plan* p, const double* harm) {
+  PxmPeers q = p->ps.peers;
+  q.p[0] = const_cast<double*>(harm) - p->H.slot_off[0];
+  return q;
+}
+
+int pxm_wav_synthesis_to_harm(pxm_wav_plan* p, const void* d_coef, double* d_harm, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_scales_in.d_groups.d, D.fft_scales_in.groups.data(), (int)D.fft_scales_in.groups.size(),
+                         D.fft_scales_in.ctas, const_cast<void*>(d_coef), (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_in.class_mask, st)); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, harm_peers(p, d_harm), D.a_multi.d_items.d, D.a_multi.d_segs.d,
+                              (int)D.a_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  return PXM_OK;
+}
+
+// coefficients of  Psi^dagger ic (Psi X - data)  from f = pxm_wav_synthesis_to_harm(X): d_b = pxm_wav_pix_to_harm_adjoint(data)
+int pxm_wav_gram_gradient(pxm_wav_plan* p, const double* d_harm, const double* d_b, double ic_re, double ic_im, void* d_coef, int nb,
+                          void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure_gram());
+  const PxmPeers& pe = p->ps.peers;
+  const PxmPeers h2 = harm_peers(p, p->d_h2);
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_gram, harm_peers(p, d_harm), h2, p->g_full.d_items.d, p->g_full.d_segs.d,
+                              (int)p->g_full.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(2, st); PXM_TRY(pxm_launch_harm_affine(p->d_h2, d_b, ic_re, ic_im, p->nld, 4 * nb, p->H.total / ((ull)p->nld * 4), st)); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, h2, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
+                              (int)D.s_multi.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, D.fft_scales_out.groups.data(), (int)D.fft_scales_out.groups.size(),
+                         D.fft_scales_out.ctas, d_coef, (size_t)p->ncoefs_local, p->d_ws, p->nld, p->ffttab.d_arena, nb,
+                         D.fft_scales_out.class_mask, st)); }
+  return PXM_OK;
+}
+
+int pxm_wav_harm_to_pix(pxm_wav_plan* p, const double* d_harm, void* d_pix, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, harm_peers(p, d_harm), pe, D.s_full.d_items.d, D.s_full.d_segs.d,
+                              (int)D.s_full.items.size(), p->nld, st, pxm_debug_naive())); }
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_full_out.d_groups.d, D.fft_full_out.groups.data(), (int)D.fft_full_out.groups.size(),
+                         D.fft_full_out.ctas, d_pix, (size_t)p->npix_local, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_full_out.class_mask, st)); }
+  return PXM_OK;
+}
+
+// A_inv^dagger of a pixel map into a harmonic array (the constant b of pxm_wav_gram_gradient: pass the data, nbatch = 1)
+int pxm_wav_pix_to_harm_adjoint(pxm_wav_plan* p, const void* d_pix, double* d_harm, int nb, void* stream) {
+  PXM_TRY(ring_check(p, nb));
+  cudaStream_t st = (cudaStream_t)stream;
+  WavDirection& D = p->syn;
+  PXM_TRY(p->ensure(D));
+  const PxmPeers& pe = p->ps.peers;
+  { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(0, D.fft_full_in.d_groups.d, D.fft_full_in.groups.data(), (int)D.fft_full_in.groups.size(), D.fft_full_in.ctas,
+                         const_cast<void*>(d_pix), (size_t)p->npix_local, p->d_ws, p->nld, p->ffttab.d_arena, nb, D.fft_full_in.class_mask, st)); }
+  { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(1, p->d_tab, pe, harm_peers(p, d_harm), D.a_full.d_items.d, D.a_full.d_segs.d,
+                              (int)D.a_full.items.size(), p->nld, st, pxm_debug_naive())); }
+  return PXM_OK;
 }
 
 // =========================================================================

@@ -82,6 +82,8 @@ void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, i
                            unsigned long long base_off, int rank = 0, int world = 1);
 int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
 int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
+int pxm_generate_gram(const PxmTableLayout& Tl, const double* d_lam_tab, const PxmTableLayout& Tg, double* d_g_tab, double scale,
+                      cudaStream_t st);
 
 // kernels' launchers -------------------------------------------------------------
 int pxm_legendre_pad_columns(int ncols);
@@ -116,6 +118,8 @@ int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* 
                      cudaStream_t st);
 int pxm_launch_ring_resid(const double* pred, const double* data, const void* ic, double* out, int nslots, int rings,
                           int nld, int ncols, double scale, unsigned long long slot_stride, cudaStream_t st);
+int pxm_launch_harm_affine(double* h, const double* b, double cre, double cim, int nld, int ncols, unsigned long long rowgroups,
+                           cudaStream_t st);
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
                       double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st,
                       const double* d_par = nullptr);

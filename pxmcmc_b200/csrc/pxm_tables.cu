@@ -129,6 +129,31 @@ __global__ void k_c_to_tiles(const double* __restrict__ C, const unsigned long l
   }
 }
 
+// Gram tiles of the inverse transform: G^m[lam', lam] = scale * sum_t Lambda^m[t, m + lam'] Lambda^m[t, m + lam]
+// (rows and columns relative to |m|; one CTA per 32 x 16 output tile, one thread per entry)
+__global__ void k_gram_tiles(const double* __restrict__ lam_tab, double* __restrict__ g_tab, const PxmWigSlot* __restrict__ lslots,
+                             const PxmWigSlot* __restrict__ gslots, int rings, int lmax, int ntb_g, double scale) {
+  const int si = blockIdx.z;
+  const PxmWigSlot ls = lslots[si], gs = gslots[si];
+  const int tb = blockIdx.y, lb = blockIdx.x;
+  if (gs.nlb == 0 || lb >= gs.nlb || tb >= ntb_g) return;
+  const int am = ls.m < 0 ? -ls.m : ls.m;
+  const int nrow = lmax - am;
+  const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+  const int lp = 32 * tb + r, l = 16 * lb + c;  // relative degrees
+  double acc = 0.0;
+  if (lp < nrow && l < nrow) {
+    const int lbp = lp >> 4, cp = lp & 15;
+    for (int t = 0; t < rings; ++t) {
+      const double* tile_row = lam_tab + ls.tile_off + (size_t)(t >> 5) * (size_t)ls.nlb * PXM_TILE_DOUBLES;
+      const double a = tile_row[(size_t)(lbp - ls.lb0) * PXM_TILE_DOUBLES + pxm_tile_word(t & 31, cp)];
+      const double b = tile_row[(size_t)(lb - ls.lb0) * PXM_TILE_DOUBLES + pxm_tile_word(t & 31, c)];
+      acc += a * b;
+    }
+  }
+  g_tab[gs.tile_off + ((size_t)tb * gs.nlb + lb) * PXM_TILE_DOUBLES + pxm_tile_word(r, c)] = scale * acc;
+}
+
 }  // namespace
 
 void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, int spin, int l_lo, int l_hi,
@@ -332,5 +357,28 @@ extern "C" int pxm_debug_wigner_row_host(int grid_L, int ring, int m, int spin, 
     out[l] = ssign * sqrt((2.0 * l + 1.0) * 0.07957747154594767) * pxm_wigner_value(w);
     if (l + 1 < lmax) pxm_wigner_step(w);
   }
+  return PXM_OK;
+}
+
+// G^m = scale * Lambda^T Lambda from the (already generated, unweighted, full-support) Lambda table `Tl` in `d_lam_tab`
+// into the layout `Tg` (same slots; rows = relative degrees) in `d_g_tab`
+int pxm_generate_gram(const PxmTableLayout& Tl, const double* d_lam_tab, const PxmTableLayout& Tg, double* d_g_tab, double scale,
+                      cudaStream_t st) {
+  if (Tl.nslots != Tg.nslots || Tl.l_lo != 0 || Tg.l_lo != 0) {
+    pxm_set_error("gram tables need full-support Lambda tables with the same slots");
+    return PXM_ERR_ARG;
+  }
+  std::vector<PxmWigSlot> hl = wig_slots(Tl, 0, Tl.nslots), hg = wig_slots(Tg, 0, Tg.nslots);
+  PxmDevVec<PxmWigSlot> dl, dg;
+  PXM_TRY(dl.upload(hl));
+  PXM_TRY(dg.upload(hg));
+  int maxnlb = 0;
+  for (int v : Tg.nlb) maxnlb = std::max(maxnlb, v);
+  dim3 grid(std::max(maxnlb, 1), Tg.ntb, Tg.nslots);
+  k_gram_tiles<<<grid, 512, 0, st>>>(d_lam_tab, d_g_tab, dl.d, dg.d, Tl.rings, Tl.lmax, Tg.ntb, scale);
+  PXM_LAUNCHED();
+  PXM_CUDA(cudaStreamSynchronize(st));
+  dl.release();
+  dg.release();
   return PXM_OK;
 }

@@ -219,6 +219,37 @@ class WaveletPlan:
         return ring
 
 
+    # ---- harmonic (Gram) form of the pixel side (pxm_wav_*harm*, pxm_wav_gram_gradient): float64 tensors [harm_doubles]
+    @property
+    def harm_doubles(self):
+        return int(lib.pxm_wav_harm_doubles(self.h))
+
+    def synthesis_to_harm(self, coef, out=None):
+        c2, _ = batch2d(coef)
+        if c2.shape[1] != self.ncoefs or c2.shape[0] > self.nbatch:
+            raise ValueError("coefficient batch does not fit the plan")
+        # zero-initialised: the contraction does not touch the padding rows of the slots
+        harm = out if out is not None else torch.zeros(self.harm_doubles, dtype=FDT, device=c2.device)
+        check(lib.pxm_wav_synthesis_to_harm(self.h, ptr(c2), ptr(harm), c2.shape[0], stream_ptr()))
+        return harm
+
+    def gram_gradient(self, harm, b_harm, ic, nb):
+        out = torch.empty((nb, self.ncoefs), dtype=CDT, device=harm.device)
+        check(lib.pxm_wav_gram_gradient(self.h, ptr(harm), ptr(b_harm), float(ic.real), float(ic.imag), ptr(out), nb, stream_ptr()))
+        return out
+
+    def harm_to_pix(self, harm, nb):
+        out = torch.empty((nb, self.npix), dtype=CDT, device=harm.device)
+        check(lib.pxm_wav_harm_to_pix(self.h, ptr(harm), ptr(out), nb, stream_ptr()))
+        return out
+
+    def pix_to_harm_adjoint(self, pix):
+        p2, _ = batch2d(pix)
+        harm = torch.zeros(self.harm_doubles, dtype=FDT, device=p2.device)
+        check(lib.pxm_wav_pix_to_harm_adjoint(self.h, ptr(p2), ptr(harm), p2.shape[0], stream_ptr()))
+        return harm
+
+
 class ShtPlan:
     """pxm_sht_plan: the four pyssht-level transforms for one (L, spin, nbatch)."""
 

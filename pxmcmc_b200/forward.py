@@ -9,20 +9,21 @@ from .utils import mw_size
 
 
 class RingPreds:
-    """Predictions of an Identity-measurement synthesis operator kept as ring-Fourier coefficients F_m(theta_t) of the
-    image (the plan's ring array, float64 [ring_doubles]) instead of pixels: what `ForwardOperator.forward_ring`
+    """Predictions of an Identity-measurement synthesis operator kept in the transform's own intermediate space instead
+    of pixels: `kind == "ring"`: ring-Fourier coefficients F_m(theta_t) of the image (the plan's ring array);
+    `kind == "harm"`: its harmonic coefficients f_lm (the plan's harmonic array).  What `ForwardOperator.forward_ring`
     returns and `gradg_from_ring` consumes.  `.pixels()` gives the ordinary [nchains, npix] predictions."""
 
-    __slots__ = ("t", "op", "nb")
+    __slots__ = ("t", "op", "nb", "kind")
 
-    def __init__(self, t, op, nb):
-        self.t, self.op, self.nb = t, op, int(nb)
+    def __init__(self, t, op, nb, kind="ring"):
+        self.t, self.op, self.nb, self.kind = t, op, int(nb), kind
 
     def pixels(self):
         return self.op.ring_to_pixels(self)
 
     def clone(self):
-        return RingPreds(self.t.clone(), self.op, self.nb)
+        return RingPreds(self.t.clone(), self.op, self.nb, self.kind)
 
     def scaled_(self, c):
         self.t.mul_(c)
@@ -100,7 +101,20 @@ class ForwardOperator:
     # The samplers then carry the predictions as ring coefficients (`RingPreds`) and convert them to pixels only where
     # pixels are needed (tracked samples, checkpoints, the host-buffer path).  Same results to round-off;
     # `fuse_ring = False` restores the literal composition.
+    # When the inverse covariance is ONE constant over the whole sphere (a scalar sigma) the same composition collapses
+    # further, per order m, to g = ic (G f - b) with the Gram matrix G^m = (2L-1) Lambda^T Lambda and b = A_inv^dagger(data)
+    # (pxm_wav_gram_gradient): one contraction instead of the two full-L ones; the predictions are then carried as f_lm.
     fuse_ring = True
+    fuse_gram = True
+
+    def _ring_kind(self):
+        """'harm' (Gram form), 'ring', or None"""
+        if not self._ring_fusable():
+            return None
+        d = np.asarray(self._diag)
+        if self.fuse_gram and bool(np.all(d == d[0])):
+            return "harm"
+        return "ring"
 
     def _ring_fusable(self):
         t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
@@ -141,23 +155,42 @@ class ForwardOperator:
         x = D.to_dev_c(X)
         x = x.unsqueeze(0) if x.dim() == 1 else x
         nb = x.shape[0]
-        t = self.transform._plan(nb).synthesis_to_ring(x, out=None if out is None else out.t)
-        return out if out is not None else RingPreds(t, self, nb)
+        kind = out.kind if out is not None else self._ring_kind()
+        plan = self.transform._plan(nb)
+        if kind == "harm":
+            t = plan.synthesis_to_harm(x, out=None if out is None else out.t)
+        else:
+            t = plan.synthesis_to_ring(x, out=None if out is None else out.t)
+        return out if out is not None else RingPreds(t, self, nb, kind)
+
+    def _harm_b(self, nb):
+        c = getattr(self, "_harm_b_cache", None)
+        if c is None:
+            c = self._harm_b_cache = {}
+        if nb not in c:
+            data_d, _ = self._upload()
+            c[nb] = self.transform._plan(nb).pix_to_harm_adjoint(data_d.reshape(1, -1))
+        return c[nb]
 
     def gradg_from_ring(self, R):
-        """gradient of the data fidelity from ring-space predictions: Psi^dagger without its first ring FFT"""
+        """gradient of the data fidelity from ring- / harmonic-space predictions"""
         plan = self.transform._plan(R.nb)
+        if R.kind == "harm":
+            return plan.gram_gradient(R.t, self._harm_b(R.nb), complex(np.asarray(self._diag)[0]), R.nb)
         resid = plan.ring_resid(R.t, self._ring_data(R.nb), self._ic_rings(), R.nb)
         return plan.synthesis_adjoint_from_ring(resid, R.nb)
 
     def ring_to_pixels(self, R):
-        return self.transform._plan(R.nb).ring_to_pix(R.t, R.nb)
+        plan = self.transform._plan(R.nb)
+        return plan.harm_to_pix(R.t, R.nb) if R.kind == "harm" else plan.ring_to_pix(R.t, R.nb)
 
     def pixels_to_ring(self, P):
+        """ring form of pixel predictions (the harmonic form cannot be recovered from pixels without the analysis
+        tables: callers recompute it from the state with `forward_ring`)"""
         p = D.to_dev_c(P)
         p = p.unsqueeze(0) if p.dim() == 1 else p
         plan = self.transform._plan(p.shape[0])
-        return RingPreds(plan.pix_to_ring(p), self, p.shape[0]).scaled_(1.0 / (2 * self.transform.L - 1))
+        return RingPreds(plan.pix_to_ring(p), self, p.shape[0], "ring").scaled_(1.0 / (2 * self.transform.L - 1))
 
     def _forward_synthesis(self, X):
         if self._fused():

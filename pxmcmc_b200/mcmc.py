@@ -342,14 +342,16 @@ class PxMCMC:
         extra = {}
         if isinstance(curr_preds, RingPreds):  # the ring coefficients themselves: a resumed chain continues bit for bit
             extra["P_ring"] = D.to_host(curr_preds.t)
+            extra["P_kind"] = curr_preds.kind
         self._save_ckpt(path, i=i, j=j, X=D.to_host(X_curr), P=D.to_host(self._pix(curr_preds)), **extra)
 
     def load_checkpoint(self, path):
         """-> (i, j, X, preds) as device tensors"""
         f = self._load_ckpt(path)
         X = self._state(f["X"])
-        if "P_ring" in f and self._ring_mode():
-            P = RingPreds(torch.from_numpy(np.ascontiguousarray(f["P_ring"])).to(X.device), self.forward, X.shape[0])
+        if "P_ring" in f and self._ring_mode() and str(f["P_kind"]) == self.forward._ring_kind():
+            P = RingPreds(torch.from_numpy(np.ascontiguousarray(f["P_ring"])).to(X.device), self.forward, X.shape[0],
+                          str(f["P_kind"]))
         else:
             P = self._state(f["P"])
         return int(f["i"]), int(f["j"]), X, P
@@ -473,7 +475,7 @@ class MYULA(PxMCMC):
             X_curr, curr_preds = self._initial_sample(start_point)
         if self._ring_mode() and not isinstance(curr_preds, RingPreds):
             # predictions carried as ring coefficients: the pixel-side FFT pair of every iteration cancels
-            curr_preds = self.forward.pixels_to_ring(curr_preds) if resume is not None else self.forward.forward_ring(X_curr)
+            curr_preds = self.forward.forward_ring(X_curr)
         # Philox noise and a native operator: the iteration is replayed as one CUDA graph (small bandlimits are
         # launch-latency bound: 85 -> 63 us per iteration at L = 32); the noise stream is the eager one
         graphed = None
@@ -630,7 +632,7 @@ class GraphedChain:
         if isinstance(P, RingPreds):
             self.P = P.clone()
         elif sampler._ring_mode():
-            self.P = sampler.forward.pixels_to_ring(sampler._state(P))
+            self.P = sampler.forward.forward_ring(self.X)  # recomputed from the state in the form the iteration carries
         else:
             self.P = sampler._state(P).clone()
         sampler._dstep = torch.full((1,), sampler._step_counter + 1, dtype=torch.int64, device=self.X.device)

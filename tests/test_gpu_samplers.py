@@ -339,7 +339,7 @@ def _ring_case(px, sig, nchains, L=24, B=1.5, J=2, complex_data=True, **kw):
     return op, reg, prm
 
 
-@pytest.mark.parametrize("sig_kind,nchains", [("scalar", 1), ("scalar", 3), ("per_ring", 2)])
+@pytest.mark.parametrize("sig_kind,nchains", [("scalar", 1), ("scalar", 3), ("scalar_ring", 2), ("per_ring", 2)])
 def test_ring_carried_predictions_equal_the_pixel_composition(px, sig_kind, nchains):
     """Identity measurement behind a wavelet synthesis: the ring FFT that ends Psi and the one that starts the next
     gradient cancel when the inverse covariance is constant along rings; the samplers then carry the predictions as ring
@@ -350,18 +350,21 @@ def test_ring_carried_predictions_equal_the_pixel_composition(px, sig_kind, ncha
     from pxmcmc_b200.forward import RingPreds
 
     L = 24
-    if sig_kind == "scalar":
+    if sig_kind.startswith("scalar"):
         sig = 0.3
     else:  # the reference's per-ring noise level sqrt(sigma^2 / pixel area) (experiments/earthtopography/main.py:92-94)
         sig = np.sqrt(0.05 / px.utils.calc_pixel_areas(L)).flatten()
     op, reg, prm = _ring_case(px, sig, nchains)
+    op.fuse_gram = sig_kind != "scalar_ring"
     assert op._ring_fusable()
+    # one constant inverse covariance: harmonic (Gram) form, predictions carried as f_lm; per-ring constants: ring form
+    assert op._ring_kind() == {"scalar": "harm", "scalar_ring": "ring", "per_ring": "ring"}[sig_kind]
     rng = np.random.default_rng(3)
     X0 = D.to_dev_c(rng.laplace(size=(nchains, op.nparams)))
     ring = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
     lit = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
     Pr = ring._initial_preds(X0)
-    assert isinstance(Pr, RingPreds) and ring._ring_mode()
+    assert isinstance(Pr, RingPreds) and ring._ring_mode() and Pr.kind == op._ring_kind()
     Pl = D.to_dev_c(op.forward(X0))
     assert rel_l2(Pr.pixels().cpu().numpy(), Pl.cpu().numpy()) < 1e-12
     back = op.pixels_to_ring(Pl)                                   # the conversion resume / capture use
