@@ -468,8 +468,8 @@ def measure_single_chain(ctx, args, iters=500):
             "eager_stage_us": {"legendre": msk[0] / n * 1e3, "ring_fft": msk[1] / n * 1e3, "elementwise": msk[2] / n * 1e3},
             "table_bytes_streamed_per_iteration": streamed,
             "legendre_table_stream_GBps": streamed / (msk[0] / n / 1e3) / 1e9 if msk[0] > 0 else None,
-            "note": "10 launches of 18-36 us each: at one chain every kernel is a single short wave whose duration is its own "
-                    "load latency chain (ncu: long_scoreboard 59 % in the ring FFT), not a throughput limit"}
+            "note": f"{int(sum(cnt)) // n} launches per iteration: at one chain every kernel is a single short wave whose duration is its "
+                    "own load-latency chain (ncu: long_scoreboard 59 % in the one-chain ring FFT), not a throughput limit"}
 
 
 def measure_configs(ctx, args):

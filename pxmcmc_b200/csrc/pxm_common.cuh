@@ -101,7 +101,7 @@ struct PxmLegItem {
   int nmt_out;  // number of M-direction tiles to store
   int cost;     // k-stages x tiles, for ordering
   int dst;      // rank whose workspace receives the output tile (0 when not sharded)
-  int pad;
+  int pad;      // 1: also store (zero) rows beyond nmt_out up to the 64-row tile (outputs in harmonic buffers)
 };
 
 // Workspaces of the ranks of an m-sharded plan (peer-mapped device memory, NVLink):

@@ -235,7 +235,9 @@ pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmP
 #pragma unroll
   for (int mi = 0; mi < C::MI; ++mi) {
     const int row = wm * C::WM + mi * 8 + g;
-    if (row / C::TILE_ROWS >= item.nmt_out) continue;
+    // rows past the last tile: skipped, or -- harmonic buffers, whose slots are padded to whole 64-row tiles -- written as the
+    // zeros the accumulators still hold, so that a caller-provided output array needs no initialisation
+    if (row / C::TILE_ROWS >= item.nmt_out && !item.pad) continue;
 #pragma unroll
     for (int ni = 0; ni < C::NI; ++ni) {
       const int col = n0 + wn * C::WN + ni * 8 + 2 * q;

@@ -272,6 +272,7 @@ void build_g_items(Stage& S, const PxmTableLayout& T, const HarmBuf& H, int nld)
       it.seg_begin = (int)S.segs.size();
       it.seg_count = 1;
       it.nmt_out = sg.nmt;
+      it.pad = 1;
       it.cost = sg.nk * sg.nmt;
       it.dst = 0;
       S.segs.push_back(sg);
@@ -329,6 +330,7 @@ void build_a_items(Stage& S, const std::vector<ASource>& srcs, const HarmBuf& H,
       it.dst = sh.rank;  // harmonic coefficients of an owned order stay local
       it.c_off = H.slot_off[hs] + (ull)(64 * lt) * nld;
       it.nmt_out = std::min(4, nlbH - 4 * lt);
+      it.pad = 1;  // harmonic slots hold whole 64-row tiles: the padding rows are written (as zeros)
       S.items.push_back(it);
     }
   }

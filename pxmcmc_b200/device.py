@@ -228,8 +228,8 @@ class WaveletPlan:
         c2, _ = batch2d(coef)
         if c2.shape[1] != self.ncoefs or c2.shape[0] > self.nbatch:
             raise ValueError("coefficient batch does not fit the plan")
-        # zero-initialised: the contraction does not touch the padding rows of the slots
-        harm = out if out is not None else torch.zeros(self.harm_doubles, dtype=FDT, device=c2.device)
+        # (the contraction writes every row of every slot, padding included: no initialisation needed)
+        harm = out if out is not None else torch.empty(self.harm_doubles, dtype=FDT, device=c2.device)
         check(lib.pxm_wav_synthesis_to_harm(self.h, ptr(c2), ptr(harm), c2.shape[0], stream_ptr()))
         return harm
 

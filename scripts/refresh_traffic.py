@@ -43,9 +43,11 @@ def main():
     logs = []
     # one full MYULA step = 4 ring-FFT launches of the persistent kernel and 4 Legendre launches; skip the plan set-up and
     # the first steps (the Legendre kernel also builds the quadrature tables at plan creation: skip generously)
-    fft, log = ncu(chains, "pxm_ring_fft3_kernel", 16, 4)
+    # (the bench carries the predictions in harmonic form: 2 persistent ring-FFT launches and 3 Legendre launches per step;
+    # two consecutive steps are captured)
+    fft, log = ncu(chains, "pxm_ring_fft3_kernel", 12, 4)
     logs.append(log)
-    leg, log = ncu(chains, "pxm_legendre_kernel", 60, 4)
+    leg, log = ncu(chains, "pxm_legendre_kernel", 60, 6)
     logs.append(log)
     wleg, log = ncu(wl, "pxm_legendre_kernel", 400, 4)
     logs.append(log)
