@@ -462,9 +462,16 @@ def measure_single_chain(ctx, args, iters=500):
     _lib.check(_lib.lib.pxm_profile_end(msk, cnt))
     chain.release()
     del chain, m, op
-    streamed = 2 * int(fam[0] + fam[1])  # Lambda_L and the kappa-weighted W_j, once for Psi and once for Psi^dagger
+    gram = C.c_longlong(0)
+    _lib.check(_lib.lib.pxm_wav_plan_gram_bytes(op.transform._plan(1).h, C.byref(gram)))
+    kind = P.kind if hasattr(P, "kind") else "pixels"
+    if kind == "harm":  # the kappa-weighted W_j in both directions and the Gram table in between
+        streamed = 2 * int(fam[1]) + int(gram.value)
+    else:  # Lambda_L and the kappa-weighted W_j, once for Psi and once for Psi^dagger
+        streamed = 2 * int(fam[0] + fam[1])
     return {"iterations_per_s": 1e3 / ms_it, "ms_per_iteration": ms_it, "iterations_timed": iters,
             "mode": "one chain, iteration replayed as one CUDA graph (in-place state), Philox noise; median of 5 blocks",
+            "predictions": kind,
             "eager_stage_us": {"legendre": msk[0] / n * 1e3, "ring_fft": msk[1] / n * 1e3, "elementwise": msk[2] / n * 1e3},
             "table_bytes_streamed_per_iteration": streamed,
             "legendre_table_stream_GBps": streamed / (msk[0] / n / 1e3) / 1e9 if msk[0] > 0 else None,
@@ -676,9 +683,10 @@ def run_ours(args):
                     "stages_per_step": fft_stages,
                     "ms_per_step": st["ring_fft"], "peak_source": hbm_src,
                     "note": "HBM class per SURVEY 8(d): algorithmic bytes = pixels or coefficients in + ring coefficients out = "
-                            "32 B x (ncoef + npix) per Psi per chain.  DRAM traffic = algorithmic bytes and HBM is ~20-25 % busy: the "
-                            "kernel is bound by the FP64 pipe (Bluestein: an odd ring length 2l-1 costs two power-of-two FFTs of length "
-                            ">= 2n), which DFMA shares with DMMA on this part (profiles/ubench_fp64_r1g.txt)"}
+                            "32 B x coefficients (and pixels, when the pixel side is not carried in ring / harmonic form) per stage per "
+                            "chain.  DRAM traffic = algorithmic bytes and HBM is ~20-25 % busy: Bluestein (odd ring length 2l-1 = two "
+                            "power-of-two FFTs of length >= 2n) needs 255 registers per thread, so an SM holds 8 warps and the kernel "
+                            "is bound by exposed latency, not by HBM nor by FP64 issue (ablation builds, DESIGN.md section 3)"}
         roof_leg = {"bound": "tensor", "achieved": leg_tf, "peak": peak, "unit": "TFLOP/s", "frac": (leg_tf / peak) if leg_tf else None,
                     "traffic": traffic.get("legendre_bytes_per_launch") if default_wl else None,
                     "kernel": "pxm_legendre_kernel (FP64 DMMA)", "launches_timed": main["counts"][0],

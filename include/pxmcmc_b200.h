@@ -62,6 +62,8 @@ int pxm_wav_plan_info(const pxm_wav_plan* plan, int* nscales_total, long long* n
 int pxm_wav_plan_bandlimits(const pxm_wav_plan* plan, int* out, int cap);
 /* bytes of this rank's Legendre tables by family: synthesis {Lambda_L, W_j kappa_j}, analysis {W_L, Lambda_j kappa_j} */
 int pxm_wav_plan_table_bytes_by_family(const pxm_wav_plan* plan, long long* out4);
+/* bytes of the Gram table G^m = (2L-1) Lambda^T Lambda behind pxm_wav_gram_gradient (0 until its first call builds it) */
+int pxm_wav_plan_gram_bytes(const pxm_wav_plan* plan, long long* out);
 int pxm_wav_synthesis(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int nbatch, void* stream);
 int pxm_wav_synthesis_adjoint(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
 int pxm_wav_analysis(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);

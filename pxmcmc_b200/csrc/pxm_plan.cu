@@ -942,6 +942,12 @@ int pxm_wav_plan_table_bytes_by_family(const pxm_wav_plan* p, long long* out4) {
   return PXM_OK;
 }
 
+int pxm_wav_plan_gram_bytes(const pxm_wav_plan* p, long long* out) {
+  PXM_REQUIRE(p != nullptr && out != nullptr, "null argument");
+  *out = p->gram_built ? (long long)p->gramT.doubles * 8 : 0;
+  return PXM_OK;
+}
+
 // host-only: harmonic kernels kappa0 / kappa_j (what pys2let.wavelet_tiling exposes)
 int pxm_wavelet_tiling(int L, double B, int J_min, double* kappa0, double* kappa, int* J_out) {
   PXM_REQUIRE(L >= 1 && B > 1.0 && J_min >= 0, "tiling arguments");
