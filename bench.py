@@ -460,11 +460,11 @@ def measure_single_chain(ctx, args, iters=500):
         x, p_ = m.iterate(x, p_)
     msk, cnt = (C.c_double * 3)(), (C.c_longlong * 3)()
     _lib.check(_lib.lib.pxm_profile_end(msk, cnt))
-    chain.release()
-    del chain, m, op
     gram = C.c_longlong(0)
     _lib.check(_lib.lib.pxm_wav_plan_gram_bytes(op.transform._plan(1).h, C.byref(gram)))
     kind = P.kind if hasattr(P, "kind") else "pixels"
+    chain.release()
+    del chain, m, op
     if kind == "harm":  # the kappa-weighted W_j in both directions and the Gram table in between
         streamed = 2 * int(fam[1]) + int(gram.value)
     else:  # Lambda_L and the kappa-weighted W_j, once for Psi and once for Psi^dagger
