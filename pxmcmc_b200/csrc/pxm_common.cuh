@@ -104,6 +104,14 @@ struct PxmLegItem {
   int pad;      // 1: also store (zero) rows beyond nmt_out up to the 64-row tile (outputs in harmonic buffers)
 };
 
+// optional epilogue of a contraction whose output is a harmonic array: out <- c (acc - b) on the complex numbers formed by
+// adjacent (re, im) columns, b = chain 0 of an array in the output's own layout (b == nullptr: plain store).  The Gram
+// form of the data-fidelity gradient, g = ic (G f - A^dagger d), in one launch (pxm_wav_gram_gradient)
+struct PxmLegAffine {
+  const double* b;  // same base convention as the output pointer (item.c_off applies)
+  double re, im;
+};
+
 // Workspaces of the ranks of an m-sharded plan (peer-mapped device memory, NVLink):
 // the contraction over l PUSHES its output tile into the ring buffer of the rank that
 // owns those rings, the contraction over rings PULLS ring blocks from their owners with

@@ -263,26 +263,6 @@ __global__ void k_ring_resid(const double* __restrict__ pred, const double* __re
   }
 }
 
-// h <- c * (h - b) on harmonic arrays in the k4-interleaved layout (concatenated slots of [rows/4][col][rows%4] doubles,
-// col = 4 chain + 2 (m < 0) + (im)); b holds chain 0 only (see pxm_wav_gram_gradient)
-__global__ void k_harm_affine(double* __restrict__ h, const double* __restrict__ b, double cre, double cim, int nld, int ncols,
-                              unsigned long long total) {
-  const unsigned int halfc = (unsigned int)ncols >> 1;
-  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const unsigned int r4 = (unsigned int)(i & 3);
-    const unsigned long long q = i >> 2;
-    const unsigned int c2 = (unsigned int)(q % halfc);
-    const unsigned long long rg = q / halfc;
-    const unsigned long long base = rg * (unsigned long long)nld * 4 + r4;
-    const unsigned long long ire = base + (unsigned long long)(2 * c2) * 4, iim = ire + 4;
-    const unsigned long long bre = base + (unsigned long long)(2 * (c2 & 1)) * 4, bim = bre + 4;
-    const double vx = h[ire] - b[bre], vy = h[iim] - b[bim];
-    h[ire] = cre * vx - cim * vy;
-    h[iim] = cre * vy + cim * vx;
-  }
-}
-
 // ---------------------------------------------------------------------------
 // per-chain reductions (deterministic two-stage)
 //  kind 0: sum |w_i x_i|                         (prior.py:28-35, :83-84)   -> (re, 0)
@@ -808,15 +788,6 @@ int pxm_launch_ring_resid(const double* pred, const double* data, const void* ic
   return PXM_OK;
 }
 
-int pxm_launch_harm_affine(double* h, const double* b, double cre, double cim, int nld, int ncols, unsigned long long rowgroups,
-                           cudaStream_t st) {
-  const unsigned long long total = rowgroups * (unsigned long long)(ncols / 2) * 4;
-  if (!total) return PXM_OK;
-  k_harm_affine<<<grid_for((size_t)total), 256, 0, st>>>(h, b, cre, cim, nld, ncols, total);
-  PXM_LAUNCHED();
-  return PXM_OK;
-}
-
 constexpr int PXM_REDUCE_PARTS = 148;
 
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
@@ -886,7 +857,6 @@ int pxm_elem_preload() {
   PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update_pair));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_resid));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_ring_resid));
-  PXM_CUDA(cudaFuncGetAttributes(&a, k_harm_affine));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage1));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage2));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_gradlogpi));

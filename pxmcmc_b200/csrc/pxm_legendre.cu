@@ -110,7 +110,7 @@ template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
 __global__ void __launch_bounds__(LEG_THREADS, 2)
 pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmPeers bpeers,
                     const __grid_constant__ PxmPeers cpeers, const PxmLegItem* __restrict__ items,
-                    const PxmLegSeg* __restrict__ segs, int nld) {
+                    const PxmLegSeg* __restrict__ segs, int nld, const PxmLegAffine aff) {
   using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -240,9 +240,16 @@ pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmP
     if (row / C::TILE_ROWS >= item.nmt_out && !item.pad) continue;
 #pragma unroll
     for (int ni = 0; ni < C::NI; ++ni) {
-      const int col = n0 + wn * C::WN + ni * 8 + 2 * q;
-      cmat[item.c_off + pxm_il_index(row, col, nld)] = acc[mi][ni][0];
-      cmat[item.c_off + pxm_il_index(row, col + 1, nld)] = acc[mi][ni][1];
+      const int col = n0 + wn * C::WN + ni * 8 + 2 * q;  // even: the thread holds (re, im) of one complex number
+      double vr = acc[mi][ni][0], vi = acc[mi][ni][1];
+      if (aff.b != nullptr) {
+        const double xr = vr - aff.b[item.c_off + pxm_il_index(row, col & 2, nld)];
+        const double xi = vi - aff.b[item.c_off + pxm_il_index(row, (col & 2) + 1, nld)];
+        vr = __dsub_rn(__dmul_rn(aff.re, xr), __dmul_rn(aff.im, xi));  // products rounded as in the elementwise kernels
+        vi = __dadd_rn(__dmul_rn(aff.re, xi), __dmul_rn(aff.im, xr));
+      }
+      cmat[item.c_off + pxm_il_index(row, col, nld)] = vr;
+      cmat[item.c_off + pxm_il_index(row, col + 1, nld)] = vi;
     }
   }
 }
@@ -253,7 +260,7 @@ pxm_legendre_kernel(const double* __restrict__ tab, const __grid_constant__ PxmP
 template <int ORIENT>
 __global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const PxmPeers bpeers, const PxmPeers cpeers,
                                           const PxmLegItem* __restrict__ items, const PxmLegSeg* __restrict__ segs,
-                                          int nld) {
+                                          int nld, const PxmLegAffine aff) {
   constexpr int BK = ORIENT == 0 ? 16 : 32;
   constexpr int TILE_ROWS = ORIENT == 0 ? 32 : 16;
   const PxmLegItem item = items[blockIdx.x];
@@ -279,13 +286,32 @@ __global__ void pxm_legendre_naive_kernel(const double* __restrict__ tab, const 
         }
       }
     }
+    if (aff.b != nullptr) {  // the partner (re or im) of this column is recomputed: keep the debugging kernel simple
+      double oth = 0.0;
+      const int pc = col ^ 1;
+      for (int s = 0; s < item.seg_count; ++s) {
+        const PxmLegSeg sg = segs[item.seg_begin + s];
+        const double* bmat = bpeers.p[sg.src];
+        if (tl < sg.mt0 || tl >= sg.mt0 + sg.nmt) continue;
+        for (int k = 0; k < sg.nk; ++k) {
+          const double* tile = tab + sg.a_off + (size_t)k * sg.a_kstride + (size_t)(tl - sg.mt0) * sg.a_mstride;
+          for (int kk = 0; kk < BK; ++kk)
+            oth += (ORIENT == 0 ? tile[pxm_tile_word(row & 31, kk)] : tile[pxm_tile_word(kk, row & 15)]) *
+                   bmat[sg.b_off + pxm_il_index(k * BK + kk, pc, nld)];
+        }
+      }
+      const double x0 = acc - aff.b[item.c_off + pxm_il_index(row, col & 3, nld)];
+      const double x1 = oth - aff.b[item.c_off + pxm_il_index(row, pc & 3, nld)];
+      acc = (col & 1) ? __dadd_rn(__dmul_rn(aff.re, x0), __dmul_rn(aff.im, x1))    // im: re * xi + im * xr
+                      : __dsub_rn(__dmul_rn(aff.re, x0), __dmul_rn(aff.im, x1));   // re: re * xr - im * xi
+    }
     cmat[item.c_off + pxm_il_index(row, col, nld)] = acc;
   }
 }
 
 template <int ORIENT, int BN, int WARPS_M, int WARPS_N, int STAGES>
 int launch_cfg(const double* tab, const PxmPeers& b, const PxmPeers& c, const PxmLegItem* items, const PxmLegSeg* segs,
-               int nitems, int nld, cudaStream_t stream) {
+               int nitems, int nld, cudaStream_t stream, const PxmLegAffine& aff) {
   using C = LegCfg<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
   static bool configured = false;
   auto kern = pxm_legendre_kernel<ORIENT, BN, WARPS_M, WARPS_N, STAGES>;
@@ -295,7 +321,7 @@ int launch_cfg(const double* tab, const PxmPeers& b, const PxmPeers& c, const Px
   }
   if (nitems == 0) return PXM_OK;  // preload only (pxm_legendre_preload)
   dim3 grid(nitems, nld / BN);
-  kern<<<grid, LEG_THREADS, C::SMEM, stream>>>(tab, b, c, items, segs, nld);
+  kern<<<grid, LEG_THREADS, C::SMEM, stream>>>(tab, b, c, items, segs, nld, aff);
   PXM_LAUNCHED();
   return PXM_OK;
 }
@@ -305,22 +331,22 @@ int launch_cfg(const double* tab, const PxmPeers& b, const PxmPeers& c, const Px
 // part of the tile (wavelet scales) keep all eight warps equally busy
 template <int ORIENT>
 int launch_orient(const double* tab, const PxmPeers& b, const PxmPeers& c, const PxmLegItem* items,
-                  const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream) {
+                  const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, const PxmLegAffine& aff) {
   // pipeline depth: few right-hand sides (single chain) make the kernel a pure table stream, so the
   // narrow variants keep 8 stages (~10 KB each) in flight per CTA; the wide ones are DMMA-bound
   constexpr int ST = 4, STN = 8;
   if (ORIENT == 0) {
-    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 64) return launch_cfg<ORIENT, 64, 2, 4, ST>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
   } else {
-    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 64) return launch_cfg<ORIENT, 64, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 32) return launch_cfg<ORIENT, 32, 2, 4, STN>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream);
-    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream);
+    if (nld % 128 == 0) return launch_cfg<ORIENT, 128, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 64) return launch_cfg<ORIENT, 64, 1, 8, ST>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 32) return launch_cfg<ORIENT, 32, 2, 4, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 16) return launch_cfg<ORIENT, 16, 4, 2, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
+    if (nld == 8) return launch_cfg<ORIENT, 8, 8, 1, STN>(tab, b, c, items, segs, nitems, nld, stream, aff);
   }
   pxm_set_error("legendre: unsupported column count " + std::to_string(nld));
   return PXM_ERR_ARG;
@@ -339,22 +365,23 @@ int pxm_legendre_pad_columns(int ncols) {
 
 int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
                               const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
-                              cudaStream_t stream, int naive);
+                              cudaStream_t stream, int naive, const PxmLegAffine* affine);
 
 int pxm_legendre_launch(int orient, const double* tab, const double* b, double* c, const PxmLegItem* items,
                         const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive) {
   PxmPeers bp = {}, cp = {};
   bp.p[0] = const_cast<double*>(b);
   cp.p[0] = c;
-  return pxm_legendre_launch_peers(orient, tab, bp, cp, items, segs, nitems, nld, stream, naive);
+  return pxm_legendre_launch_peers(orient, tab, bp, cp, items, segs, nitems, nld, stream, naive, nullptr);
 }
 
 // Load and configure the kernels a plan with `nld` columns will launch (CUDA loads kernels
 // lazily, and a first-use load may synchronise the device -- fatal while a peer barrier spins).
 int pxm_legendre_preload(int nld) {
   PxmPeers z = {};
-  PXM_TRY(launch_orient<0>(nullptr, z, z, nullptr, nullptr, 0, nld, 0));
-  PXM_TRY(launch_orient<1>(nullptr, z, z, nullptr, nullptr, 0, nld, 0));
+  const PxmLegAffine none = {nullptr, 0.0, 0.0};
+  PXM_TRY(launch_orient<0>(nullptr, z, z, nullptr, nullptr, 0, nld, 0, none));
+  PXM_TRY(launch_orient<1>(nullptr, z, z, nullptr, nullptr, 0, nld, 0, none));
   cudaFuncAttributes a;
   PXM_CUDA(cudaFuncGetAttributes(&a, pxm_legendre_naive_kernel<0>));
   PXM_CUDA(cudaFuncGetAttributes(&a, pxm_legendre_naive_kernel<1>));
@@ -363,17 +390,18 @@ int pxm_legendre_preload(int nld) {
 
 int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
                               const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
-                              cudaStream_t stream, int naive) {
+                              cudaStream_t stream, int naive, const PxmLegAffine* affine) {
   if (nitems <= 0) return PXM_OK;
+  const PxmLegAffine aff = affine ? *affine : PxmLegAffine{nullptr, 0.0, 0.0};
   if (naive) {
     dim3 grid(nitems, 4);
     if (orient == 0)
-      pxm_legendre_naive_kernel<0><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
+      pxm_legendre_naive_kernel<0><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld, aff);
     else
-      pxm_legendre_naive_kernel<1><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld);
+      pxm_legendre_naive_kernel<1><<<grid, 256, 0, stream>>>(tab, b, c, items, segs, nld, aff);
     PXM_LAUNCHED();
     return PXM_OK;
   }
-  if (orient == 0) return launch_orient<0>(tab, b, c, items, segs, nitems, nld, stream);
-  return launch_orient<1>(tab, b, c, items, segs, nitems, nld, stream);
+  if (orient == 0) return launch_orient<0>(tab, b, c, items, segs, nitems, nld, stream, aff);
+  return launch_orient<1>(tab, b, c, items, segs, nitems, nld, stream, aff);
 }

@@ -1174,9 +1174,10 @@ int pxm_wav_gram_gradient(pxm_wav_plan* p, const double* d_harm, const double* d
   PXM_TRY(p->ensure_gram());
   const PxmPeers& pe = p->ps.peers;
   const PxmPeers h2 = harm_peers(p, p->d_h2);
+  // g = ic (G f - b): the affine part rides on the epilogue of the Gram contraction
+  const PxmLegAffine aff = {d_b - p->H.slot_off[0], ic_re, ic_im};
   { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_gram, harm_peers(p, d_harm), h2, p->g_full.d_items.d, p->g_full.d_segs.d,
-                              (int)p->g_full.items.size(), p->nld, st, pxm_debug_naive())); }
-  { ProfScope _ps(2, st); PXM_TRY(pxm_launch_harm_affine(p->d_h2, d_b, ic_re, ic_im, p->nld, 4 * nb, p->H.total / ((ull)p->nld * 4), st)); }
+                              (int)p->g_full.items.size(), p->nld, st, pxm_debug_naive(), &aff)); }
   { ProfScope _ps(0, st); PXM_TRY(pxm_legendre_launch_peers(0, p->d_tab, h2, pe, D.s_multi.d_items.d, D.s_multi.d_segs.d,
                               (int)D.s_multi.items.size(), p->nld, st, pxm_debug_naive())); }
   { ProfScope _ps(1, st); PXM_TRY(pxm_fft_launch(1, D.fft_scales_out.d_groups.d, D.fft_scales_out.groups.data(), (int)D.fft_scales_out.groups.size(),

@@ -91,7 +91,7 @@ int pxm_legendre_launch(int orient, const double* tab, const double* b, double* 
                         const PxmLegSeg* segs, int nitems, int nld, cudaStream_t stream, int naive);
 int pxm_legendre_launch_peers(int orient, const double* tab, const PxmPeers& b, const PxmPeers& c,
                               const PxmLegItem* items, const PxmLegSeg* segs, int nitems, int nld,
-                              cudaStream_t stream, int naive);
+                              cudaStream_t stream, int naive, const PxmLegAffine* affine = nullptr);
 int pxm_legendre_preload(int nld);
 int pxm_elem_preload();
 int pxm_hpx_ring_dft_launch(int dir, int nside, int L, const void* map, double* F, unsigned long long f_off,
@@ -118,8 +118,6 @@ int pxm_launch_resid(const void* preds, const void* data, const void* ic, void* 
                      cudaStream_t st);
 int pxm_launch_ring_resid(const double* pred, const double* data, const void* ic, double* out, int nslots, int rings,
                           int nld, int ncols, double scale, unsigned long long slot_stride, cudaStream_t st);
-int pxm_launch_harm_affine(double* h, const double* b, double cre, double cim, int nld, int ncols, unsigned long long rowgroups,
-                           cudaStream_t st);
 int pxm_launch_reduce(int kind, const void* a, const void* b, const void* c, const void* d, const double* w,
                       double delta, double lmda, size_t n, size_t nchains, void* partial, void* out, cudaStream_t st,
                       const double* d_par = nullptr);
