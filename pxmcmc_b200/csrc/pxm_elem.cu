@@ -6,6 +6,8 @@
 // covariance and weights are shared by all chains and indexed by i.
 #include <math_constants.h>
 
+#include <algorithm>
+
 #include "pxm_common.cuh"
 
 namespace {
@@ -24,19 +26,20 @@ __device__ __forceinline__ double np_cabs(double re, double im) {
   re = fabs(re);
   im = fabs(im);
   const double larger = fmax(re, im), smaller = fmin(im, re);
-  if (larger == 0.0 || isinf(larger)) return larger;
+  // (selects instead of early returns: the same values, no divergent regions around the division and the root)
   const double ratio = smaller / larger;
-  return sqrt(fma(ratio, ratio, 1.0)) * larger;
+  const double h = sqrt(fma(ratio, ratio, 1.0)) * larger;
+  return (larger == 0.0 || isinf(larger)) ? larger : h;
 }
 
 __device__ __forceinline__ cplx soft_c(cplx z, double T) {
   const double a = np_cabs(z.x, z.y);
-  if (a <= T) return make_double2(0.0, 0.0);
   const double r = a - T;
   // numpy evaluates z/|z| through its complex division loop, i.e. as a product
   // with the reciprocal 1/|z| (loops.c.src, *_divide); replicate it bit for bit
   const double scl = 1.0 / a;
-  return make_double2((z.x * scl) * r, (z.y * scl) * r);
+  const bool zero = a <= T;
+  return make_double2(zero ? 0.0 : (z.x * scl) * r, zero ? 0.0 : (z.y * scl) * r);
 }
 __device__ __forceinline__ double soft_r(double x, double T) {
   const double a = fabs(x);
@@ -180,13 +183,15 @@ __global__ void k_myula_update(MyulaArgs p) {
 // Philox real-noise variant: one Box-Muller pair serves two consecutive coefficients, so a
 // thread updates elements (2p, 2p+1) of one chain (halves the transcendental work; the noise
 // stream is identical to the per-element kernel: element e uses normal (e&1) of pair e>>1)
-__global__ void k_myula_update_pair(MyulaArgs p) {
+// grid = (blocks per chain, chains in this launch); `chain0` = first chain of the launch (more than 65 535 chains are
+// launched in slices): no 64-bit division per pair (ncu: 552 instructions per pair, issue slots 75 % busy, with it)
+__global__ void k_myula_update_pair(MyulaArgs p, size_t chain0) {
   const size_t npairs = (p.n + 1) >> 1;
-  const size_t nchains = p.total / p.n;
-  const size_t tot = npairs * nchains;
   myula_device_params(p);
-  for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < tot; q += (size_t)gridDim.x * blockDim.x) {
-    const size_t chain = q / npairs, pr = q - chain * npairs;
+  const size_t chain = chain0 + blockIdx.y;
+  double ca, cb, cd, cs;
+  myula_chain_params(p, chain, &ca, &cb, &cd, &cs);
+  for (size_t pr = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
     const size_t e0 = 2 * pr, i0 = chain * p.n + e0;
     const bool two = e0 + 1 < p.n;
     // every input of the pair is requested before any arithmetic: one exposed DRAM latency per iteration, not three
@@ -205,8 +210,6 @@ __global__ void k_myula_update_pair(MyulaArgs p) {
     }
     double z[2];
     philox_normal2(p.seed, p.stream0 + (unsigned int)chain, p.step, pr, &z[0], &z[1]);
-    double ca, cb, cd, cs;
-    myula_chain_params(p, chain, &ca, &cb, &cd, &cs);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       if (h == 1 && !two) break;
@@ -756,9 +759,14 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
   p.step = step;
   p.stream0 = stream0;
   if (!p.total) return PXM_OK;
-  if (noise_mode == 2)
-    k_myula_update_pair<<<grid_for((p.total + 1) / 2), 256, 0, st>>>(p);
-  else
+  if (noise_mode == 2) {
+    const size_t npairs = (n + 1) / 2;
+    for (size_t c0 = 0; c0 < nchains; c0 += 65535) {
+      const size_t nc = std::min<size_t>(nchains - c0, 65535);
+      const int per_chain = std::max(1, std::min(grid_for(npairs), (int)((148 * 16 + nc - 1) / nc)));
+      k_myula_update_pair<<<dim3(per_chain, (unsigned)nc), 256, 0, st>>>(p, c0);
+    }
+  } else
     k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
   PXM_LAUNCHED();
   return PXM_OK;
