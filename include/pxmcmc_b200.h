@@ -164,7 +164,11 @@ int pxm_soft(int is_complex, const void* d_x, const double* d_T, double T_scalar
              long long nchains, void* stream);
 /* pxm_myula_update: MYULA.chain_step (pxmcmc/mcmc.py:185-201) fused with the
  * synthesis prox (pxmcmc/prior.py:49-50) when d_prox == NULL.
- * noise_mode 0: none; 1: injected d_w_re (+ d_w_im); 2/3: Philox4x32-10 real/complex. */
+ * noise_mode 0: none; 1: injected d_w_re (+ d_w_im); 2/3: Philox4x32-10 real/complex.
+ * Real chain pairs (two real-valued chains packed as the real and imaginary part of one complex chain; every linear
+ * operator of the path is complex-linear and maps real fields to real fields, so the parts never mix; the threshold
+ * acts on each part): 4: Philox, packed chain c draws streams stream0 + 2c (real part) and stream0 + 2c + 1; 5: injected
+ * d_w_re / d_w_im = the two chains' noise. */
 int pxm_myula_update(const void* d_X, const void* d_prox, const void* d_gradg, const double* d_T, double T_scalar,
                      const double* d_w_re, const double* d_w_im, void* d_Xout, void* d_prox_out, long long n,
                      long long nchains, double delta, double lmda, int noise_mode, unsigned long long seed,

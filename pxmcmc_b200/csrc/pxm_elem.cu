@@ -41,6 +41,13 @@ __device__ __forceinline__ cplx soft_c(cplx z, double T) {
   const bool zero = a <= T;
   return make_double2(zero ? 0.0 : (z.x * scl) * r, zero ? 0.0 : (z.y * scl) * r);
 }
+// two REAL chains packed as the real and imaginary part of one complex chain (MYULA real_pairs): the threshold acts on
+// each part, sign(x) (|x| - T) evaluated exactly
+__device__ __forceinline__ double soft_part(double x, double T) {
+  const double a = fabs(x);
+  return a <= T ? 0.0 : copysign(a - T, x);
+}
+__device__ __forceinline__ cplx soft_parts(cplx z, double T) { return make_double2(soft_part(z.x, T), soft_part(z.y, T)); }
 __device__ __forceinline__ double soft_r(double x, double T) {
   const double a = fabs(x);
   if (a <= T) return 0.0;
@@ -112,7 +119,8 @@ struct MyulaArgs {
   cplx* prox_out;  // may be null
   size_t n, total;
   double a, b, delta, sq2d;
-  int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex)
+  int noise_mode;  // 0 none, 1 injected, 2 philox (real), 3 philox (complex); real chain pairs (chain 2c in the real,
+                   // 2c+1 in the imaginary part, threshold per part): 4 philox (streams stream0 + 2c, + 2c + 1), 5 injected
   unsigned long long seed, step;
   const unsigned long long* step_ptr;  // may be null; otherwise the step is read from the device (CUDA-graph replays)
   const double* dpar;  // may be null; otherwise chain c reads {delta, 1 - delta/lmda, delta/lmda, sqrt(2 delta)} from
@@ -150,14 +158,22 @@ __global__ void k_myula_update(MyulaArgs p) {
     if (p.prox) {
       px = p.prox[i];
     } else {
-      px = soft_c(x, p.Tv ? p.Tv[i % p.n] : p.Ts);
+      const double T = p.Tv ? p.Tv[i % p.n] : p.Ts;
+      px = p.noise_mode >= 4 ? soft_parts(x, T) : soft_c(x, T);
     }
     if (p.prox_out) p.prox_out[i] = px;
     const cplx g = p.gradg[i];
     double wr = 0.0, wi = 0.0;
-    if (p.noise_mode == 1) {
+    if (p.noise_mode == 1 || p.noise_mode == 5) {
       wr = p.w_re[i];
       if (p.w_im) wi = p.w_im[i];
+    } else if (p.noise_mode == 4) {
+      const size_t chain = i / p.n, e = i % p.n;
+      double z0, z1;
+      philox_normal2(p.seed, p.stream0 + 2u * (unsigned int)chain, p.step, e >> 1, &z0, &z1);
+      wr = (e & 1) ? z1 : z0;
+      philox_normal2(p.seed, p.stream0 + 2u * (unsigned int)chain + 1u, p.step, e >> 1, &z0, &z1);
+      wi = (e & 1) ? z1 : z0;
     } else if (p.noise_mode >= 2) {
       const size_t chain = i / p.n, e = i % p.n;
       double z0, z1;
@@ -219,6 +235,49 @@ __global__ void k_myula_update_pair(MyulaArgs p, size_t chain0) {
       cplx o;
       o.x = ((ca * x[h].x + cb * px[h].x) - cd * g[h].x) + cs * z[h];
       o.y = ((ca * x[h].y + cb * px[h].y) - cd * g[h].y) + cs * 0.0;
+      p.Xout[i] = o;
+    }
+  }
+}
+
+// Real chain pairs with Philox noise (noise_mode 4): packed chain c holds real chain 2c in its real and 2c+1 in its
+// imaginary part; each part is thresholded on its own and draws the normals the unpacked chain would draw (element e of
+// real chain r: normal (e & 1) of pair e >> 1 of stream stream0 + r), so packing does not change the noise.
+__global__ void k_myula_update_realpair(MyulaArgs p, size_t chain0) {
+  const size_t npairs = (p.n + 1) >> 1;
+  myula_device_params(p);
+  const size_t chain = chain0 + blockIdx.y;
+  double ca, cb, cd, cs;
+  myula_chain_params(p, chain, &ca, &cb, &cd, &cs);
+  const unsigned int sa = p.stream0 + 2u * (unsigned int)chain;
+  for (size_t pr = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pr < npairs; pr += (size_t)gridDim.x * blockDim.x) {
+    const size_t e0 = 2 * pr, i0 = chain * p.n + e0;
+    const bool two = e0 + 1 < p.n;
+    cplx x[2], g[2], px[2];
+    double T[2];
+    x[0] = p.X[i0];
+    g[0] = p.gradg[i0];
+    x[1] = two ? p.X[i0 + 1] : make_double2(0.0, 0.0);
+    g[1] = two ? p.gradg[i0 + 1] : make_double2(0.0, 0.0);
+    if (p.prox) {
+      px[0] = p.prox[i0];
+      px[1] = two ? p.prox[i0 + 1] : make_double2(0.0, 0.0);
+    } else {
+      T[0] = p.Tv ? p.Tv[e0] : p.Ts;
+      T[1] = (p.Tv && two) ? p.Tv[e0 + 1] : p.Ts;
+    }
+    double za[2], zb[2];
+    philox_normal2(p.seed, sa, p.step, pr, &za[0], &za[1]);
+    philox_normal2(p.seed, sa + 1u, p.step, pr, &zb[0], &zb[1]);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const size_t i = i0 + h;
+      if (!p.prox) px[h] = soft_parts(x[h], T[h]);
+      if (p.prox_out) p.prox_out[i] = px[h];
+      cplx o;
+      o.x = ((ca * x[h].x + cb * px[h].x) - cd * g[h].x) + cs * za[h];
+      o.y = ((ca * x[h].y + cb * px[h].y) - cd * g[h].y) + cs * zb[h];
       p.Xout[i] = o;
     }
   }
@@ -759,12 +818,15 @@ int pxm_launch_myula(const void* X, const void* prox, const void* gradg, const d
   p.step = step;
   p.stream0 = stream0;
   if (!p.total) return PXM_OK;
-  if (noise_mode == 2) {
+  if (noise_mode == 2 || noise_mode == 4) {
     const size_t npairs = (n + 1) / 2;
     for (size_t c0 = 0; c0 < nchains; c0 += 65535) {
       const size_t nc = std::min<size_t>(nchains - c0, 65535);
       const int per_chain = std::max(1, std::min(grid_for(npairs), (int)((148 * 16 + nc - 1) / nc)));
-      k_myula_update_pair<<<dim3(per_chain, (unsigned)nc), 256, 0, st>>>(p, c0);
+      if (noise_mode == 2)
+        k_myula_update_pair<<<dim3(per_chain, (unsigned)nc), 256, 0, st>>>(p, c0);
+      else
+        k_myula_update_realpair<<<dim3(per_chain, (unsigned)nc), 256, 0, st>>>(p, c0);
     }
   } else
     k_myula_update<<<grid_for(p.total), 256, 0, st>>>(p);
@@ -863,6 +925,7 @@ int pxm_elem_preload() {
   PXM_CUDA(cudaFuncGetAttributes(&a, k_soft_r));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update_pair));
+  PXM_CUDA(cudaFuncGetAttributes(&a, k_myula_update_realpair));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_resid));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_ring_resid));
   PXM_CUDA(cudaFuncGetAttributes(&a, k_reduce_stage1));

@@ -1429,7 +1429,8 @@ int pxm_myula_update_dstep(const void* d_X, const void* d_prox, const void* d_gr
                            int noise_mode, unsigned long long seed, const unsigned long long* d_step,
                            unsigned int stream0, void* stream) {
   ProfScope _ps(2, (cudaStream_t)stream);
-  PXM_REQUIRE(d_step != nullptr && (noise_mode == 2 || noise_mode == 3), "dstep update needs a device counter and Philox noise");
+  PXM_REQUIRE(d_step != nullptr && (noise_mode == 2 || noise_mode == 3 || noise_mode == 4),
+              "dstep update needs a device counter and Philox noise");
   return pxm_launch_myula(d_X, d_prox, d_gradg, d_T, T_scalar, nullptr, nullptr, d_Xout, d_prox_out, (size_t)n,
                           (size_t)nchains, delta, lmda, noise_mode, seed, 0, d_step, stream0, (cudaStream_t)stream);
 }

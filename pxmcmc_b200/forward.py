@@ -192,6 +192,42 @@ class ForwardOperator:
         plan = self.transform._plan(p.shape[0])
         return RingPreds(plan.pix_to_ring(p), self, p.shape[0], "ring").scaled_(1.0 / (2 * self.transform.L - 1))
 
+    # Two REAL-valued chains as one complex chain (MYULA(real_pairs=True)).  With real data and a real inverse
+    # covariance every linear map of the synthesis path (ring FFTs, Legendre contractions, the data-fidelity residual) is
+    # complex-linear AND maps real fields to real fields, so z = x_a + i x_b travels through it as (result_a) + i (result_b):
+    # the transforms of two chains for the price of one.  The reference computes the same real chain in complex
+    # arithmetic with a zero imaginary part (pys2let returns complex arrays, experiments/earthtopography/main.py:80-123).
+    # Both chains see the same data d, i.e. the packed problem has the data (1 + i) d.
+    def _pairable(self):
+        """None when two real chains may be packed into one complex chain, else the reason why not"""
+        t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
+        if self.setting != "synthesis" or self._diag is None:
+            return "real chain pairs need the synthesis setting and a diagonal covariance"
+        if type(m) is not Identity:
+            return "real chain pairs need the Identity measurement"
+        if (type(t).inverse is not SphericalWaveletTransform.inverse
+                or type(t).inverse_adjoint is not SphericalWaveletTransform.inverse_adjoint or not hasattr(t, "_plan")):
+            return "real chain pairs need the library's axisymmetric wavelet synthesis (a real operator)"
+        if np.iscomplexobj(self.data) or np.any(np.asarray(self._diag).imag != 0):
+            return "real chain pairs need real data and a real noise level"
+        return None
+
+    def paired(self):
+        """the operator of the packed problem: same transform and measurement objects, data (1 + i) d"""
+        why = self._pairable()
+        if why is not None:
+            raise ValueError(why)
+        import copy
+
+        op = copy.copy(self)
+        op.data = np.asarray(self.data, dtype=float) * (1.0 + 1.0j)
+        op._dev = None
+        for c in ("_ring_data_cache", "_harm_b_cache", "_ic_rings_cache"):
+            if hasattr(op, c):
+                delattr(op, c)
+        op._is_paired = True
+        return op
+
     def _forward_synthesis(self, X):
         if self._fused():
             return self.measurement._forward_from_harmonic(self.transform._inverse_harmonic(X))

@@ -433,8 +433,63 @@ class MYULA(PxMCMC):
 
     graph_run = True  # run(): replay the iteration as a CUDA graph when the noise is generated on the device
 
-    def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), **kw):
+    def __init__(self, forward, prox, mcmcparams=PxMCMCParams(), *, real_pairs=False, **kw):
+        """`real_pairs=True` (extension; an even number of chains, real data, real noise level, `complex=False`, the
+        library's synthesis-setting L1 prior): real chain 2k travels in the real and chain 2k+1 in the imaginary part
+        of ONE complex chain on the device.  Every linear operator of the synthesis path is complex-linear and maps
+        real fields to real fields, so the two parts never mix: the transforms of two chains for the price of one (the
+        reference carries the same real chain as a complex array with a zero imaginary part).  `run()`, the tracked
+        arrays, checkpoints and start points stay in the ordinary [nchains, n] form; `engine` is the sampler that
+        iterates on the packed state, `pack` / `unpack` convert.  Chain c draws the Philox stream it would draw
+        unpacked."""
         super().__init__(forward, prox, mcmcparams, **kw)
+        self.real_pairs = bool(real_pairs)
+        self._pair_engine = self._make_pair_engine() if self.real_pairs else None
+
+    # ------------------------------------------------------------------ real chain pairs
+    def _make_pair_engine(self):
+        import copy
+
+        if type(self) is not MYULA:
+            raise ValueError("real_pairs is a MYULA mode")
+        if self.nchains < 2 or self.nchains % 2:
+            raise ValueError("real_pairs needs an even number of chains")
+        if self.complex:
+            raise ValueError("real_pairs: the noise must be real (complex=False)")
+        if self._fused_prox() is None or not hasattr(self.forward, "paired"):
+            raise ValueError("real_pairs needs the library's forward operator and synthesis-setting L1 prior")
+        eng = copy.copy(self)
+        eng.forward = self.forward.paired()  # ValueError with the reason when the operator cannot be paired
+        eng.nchains = self.nchains // 2
+        eng.real_pairs, eng._pair_engine, eng._is_pair_engine = False, None, True
+        eng._spill = None
+        return eng
+
+    @property
+    def engine(self):
+        """the sampler whose `iterate` / `capture` / `iterate_host` act on the device representation of the chains:
+        the packed one in `real_pairs` mode, else this sampler itself"""
+        return self._pair_engine if self._pair_engine is not None else self
+
+    @staticmethod
+    def pack(X):
+        """[2k, n] real-valued chains -> [k, n] complex: chain 2c + i chain (2c+1)"""
+        x = D.to_dev_c(X)
+        if x.dim() != 2 or x.shape[0] % 2:
+            raise ValueError("pack: an even number of chains [nchains, n]")
+        if bool(torch.any(x.imag != 0)):
+            raise ValueError("pack: the chains must be real-valued")
+        return torch.complex(x[0::2].real, x[1::2].real).contiguous()
+
+    @staticmethod
+    def unpack(Xp):
+        """[k, n] packed chains -> [2k, n] complex tensors with zero imaginary parts"""
+        xp = D.to_dev_c(Xp)
+        xp = xp.unsqueeze(0) if xp.dim() == 1 else xp
+        out = torch.zeros((2 * xp.shape[0], xp.shape[1]), dtype=xp.dtype, device=xp.device)
+        out[0::2] = xp.real
+        out[1::2] = xp.imag
+        return out
 
     def _propose_dev(self, Xd, proxd, gradgd, out=None):
         """X' = (1-d/l) X + (d/l) prox - d gradg + sqrt(2d) w, one fused kernel;
@@ -444,13 +499,22 @@ class MYULA(PxMCMC):
             Tv, Ts = self._fused_prox()
         else:
             Tv, Ts = None, 0.0
+        pair = getattr(self, "_is_pair_engine", False)  # packed real chain pairs: kernel modes 4 (Philox) / 5 (injected)
+        if pair and proxd is not None:
+            raise ValueError("real_pairs: the prox is the library's fused soft threshold")
+        mode = 4 if pair else (3 if self.complex else 2)
         if self.noise == "host":
-            w_re, w_im = self._host_noise(n)
-            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im, noise_mode=1, out=out)
+            if pair:  # the draw of the unpacked sampler (one randn over all real chains, chain-major), then packed
+                w = np.random.randn(2 * self.nchains, n)
+                w_re, w_im = D.to_dev_f(np.ascontiguousarray(w[0::2])), D.to_dev_f(np.ascontiguousarray(w[1::2]))
+            else:
+                w_re, w_im = self._host_noise(n)
+            out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda, w_re=w_re, w_im=w_im,
+                                     noise_mode=5 if pair else 1, out=out)
         elif getattr(self, "_dstep", None) is not None:
             # graph mode: the step lives on the device and is advanced by the captured graph itself
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
-                                     noise_mode=3 if self.complex else 2, seed=self.seed, stream0=self.stream0,
+                                     noise_mode=mode, seed=self.seed, stream0=self.stream0,
                                      dstep=self._dstep, out=out)
         else:
             # chain-group calls of one iteration (iterate_host) share a step; their Philox streams are
@@ -459,14 +523,16 @@ class MYULA(PxMCMC):
             if off is None:
                 self._step_counter += 1
             out = D.myula_update_dev(Xd, proxd, gradgd, Tv, Ts, self.delta, self.lmda,
-                                     noise_mode=3 if self.complex else 2, seed=self.seed, step=self._step_counter,
-                                     stream0=self.stream0 + (off or 0), out=out)
+                                     noise_mode=mode, seed=self.seed, step=self._step_counter,
+                                     stream0=self.stream0 + (2 if pair else 1) * (off or 0), out=out)
         return out
 
     def run(self, start_point=None, *, checkpoint=None, checkpoint_every=0, resume=None):
         """the loop of pxmcmc/mcmc.py:150-183.  Extensions (keyword-only): `checkpoint` = file written every
         `checkpoint_every` iterations (and at the end); `resume` = such a file: the chain continues exactly as if it
         had never stopped (same Philox steps / same numpy RNG stream, tracked arrays restored)."""
+        if self._pair_engine is not None:
+            return self._run_pairs(start_point, checkpoint, checkpoint_every, resume)
         i = 0
         j = 0
         if resume is not None:
@@ -509,6 +575,51 @@ class MYULA(PxMCMC):
             X_curr, curr_preds = X_curr.clone(), curr_preds.clone()
             graphed.release()
         self._final_state = (X_curr, curr_preds)
+        print("\nDONE")
+
+    def _run_pairs(self, start_point, checkpoint, checkpoint_every, resume):
+        """`run()` in `real_pairs` mode: the loop of pxmcmc/mcmc.py:150-183 on the packed state; samples are unpacked
+        where they are tracked or checkpointed (every `ngap`-th iteration), so the tracked arrays are the ordinary ones"""
+        eng = self._pair_engine
+        i = 0
+        j = 0
+        if resume is not None:
+            i, j, X_curr, _ = self.load_checkpoint(resume)
+        else:
+            X_curr, _ = self._initial_sample(start_point)
+        eng._step_counter = self._step_counter
+        Xp = self.pack(X_curr)
+        Pp = eng._initial_preds(Xp)
+        graphed = None
+        if self.graph_run and self.noise == "device" and eng._native():
+            graphed = eng.capture(Xp, Pp, iterations=1)
+        while j < self.nsamples:
+            if graphed is not None:
+                graphed.step()
+                Xp, Pp = graphed._state_raw()
+            else:
+                Xp, Pp = eng.iterate(Xp, Pp)
+            if i >= self.nburn:
+                if self.ngap == 0 or (i - self.nburn) % self.ngap == 0:
+                    self._track_dev(j, self.unpack(Xp), self.unpack(eng._pix(Pp)))
+                    j += 1
+                if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                    self._track_flush()
+                    self._print_progress(j - 1, np.ravel(self.logPi)[j - 1], L2=np.ravel(self.L2s)[j - 1],
+                                         prior=np.ravel(self.priors)[j - 1])
+            else:
+                if self.verbosity > 0 and (i + 1) % self.verbosity == 0:
+                    print("Burning in...")
+            i += 1
+            self._step_counter = eng._step_counter
+            if checkpoint is not None and checkpoint_every and i % checkpoint_every == 0:
+                self.save_checkpoint(checkpoint, i, j, self.unpack(Xp), self.unpack(eng._pix(Pp)))
+        if checkpoint is not None:
+            self.save_checkpoint(checkpoint, i, j, self.unpack(Xp), self.unpack(eng._pix(Pp)))
+        self._track_flush()
+        self._final_state = (self.unpack(Xp), self.unpack(eng._pix(Pp)))
+        if graphed is not None:
+            graphed.release()
         print("\nDONE")
 
     def iterate(self, X_curr, curr_preds, out=None):

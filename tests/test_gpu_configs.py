@@ -258,6 +258,37 @@ def test_config5_myula_L256_chain_batch(px, pool):
         assert rel_l2(Xr[c], Xn[c]) < 1e-12 and rel_l2(Prp[c], Pn[c]) < 1e-12, f"ring-carried predictions, chain {c}"
 
 
+def test_config5_real_chain_pairs_L256(px, pool):
+    """the same sweep on REAL data (the earth-topography drivers' case) with MYULA(real_pairs=True): two real chains
+    travel as one complex chain on the device; every real chain against its own oracle iteration (which, like the
+    reference, carries it as a complex array with a zero imaginary part) with the same injected noise"""
+    L, B, J, nch = 256, 1.5, 2, 4
+    data = np.ascontiguousarray(unit_rms_map(px, L).real)
+    data /= np.sqrt(np.mean(data ** 2))
+    op = px.forward.SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J, nchains=nch)
+    prm = px.mcmc.PxMCMCParams(delta=1e-6, lmda=1e-6, mu=1.0, nsamples=1, verbosity=0, track=[])
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J)
+    m = px.mcmc.MYULA(op, reg, prm, nchains=nch, real_pairs=True)
+    eng = m.engine
+    assert eng is not m and eng.nchains == nch // 2
+    rng = np.random.default_rng(2)
+    X = rng.laplace(size=(nch, op.nparams)) * np.array([1.0, 1e-3, 1e-6, 1e-5])[:, None]
+    Xd = m._state(X.astype(complex))
+    P = op.forward(Xd).cpu().numpy()
+    np.random.seed(77)
+    w = np.random.randn(nch * op.nparams).reshape(nch, op.nparams)
+    Xp = m.pack(Xd)
+    Pp = eng._initial_preds(Xp)
+    np.random.seed(77)
+    Xn, Pn = eng.iterate(Xp, Pp)
+    Xn, Pn = m.unpack(Xn).cpu().numpy(), m.unpack(eng._pix(Pn)).cpu().numpy()
+    assert np.all(Xn.imag == 0) and np.all(Pn.imag == 0)
+    jobs = [(data, 1.0, L, B, J, 1e-6, 1e-6, 1.0, X[c].astype(complex), P[c], w[c]) for c in range(nch)]
+    for c, (gradg, prox, Xo, Po, _) in enumerate(pool.map(_w_myula_synthesis, jobs)):
+        assert rel_l2(Xn[c], Xo) < TOL, f"state chain {c}: {rel_l2(Xn[c], Xo):.2e}"
+        assert rel_l2(Pn[c], Po) < TOL, f"predictions chain {c}: {rel_l2(Pn[c], Po):.2e}"
+
+
 # ------------------------------------------------------------------ config 2
 def test_config2_pxmala_analysis_L256_iteration(px, pool):
     """earthtopography PxMALA, wavelet analysis prior L1("analysis", Psi, Psi^dagger, T), L=256 B=1.5, complex

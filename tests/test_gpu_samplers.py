@@ -426,3 +426,84 @@ def test_ring_mode_is_refused_when_it_does_not_apply(px):
     assert not op2._ring_fusable()
     op3, _, _ = _ring_case(px, 0.1, 1, L=L, B=2.0)
     assert op3._ring_fusable()
+
+
+# ------------------------------------------------------------------ real chain pairs
+def _pairs_case(px, nchains, real_pairs, noise="device", L=20, B=1.5, J=2, sig=0.3, nsamples=3, nburn=4, ngap=3,
+                track=("logposterior", "L2", "prior", "chain", "predictions")):
+    rng = np.random.default_rng(12)
+    flm = rng.standard_normal(L * L) + 1j * rng.standard_normal(L * L)
+    data = np.ascontiguousarray(px.sht.inverse(flm, L).ravel().real)  # a real field, as the drivers' data are
+    op = px.forward.SphericalWaveletTransformOperator(data, sig, "synthesis", L, B, J, nchains=nchains)
+    p = px.mcmc.PxMCMCParams(nsamples=nsamples, nburn=nburn, ngap=ngap, delta=1e-4, lmda=2e-3, mu=30.0, verbosity=0,
+                             track=list(track))
+    reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, p.lmda * p.mu, L=L, B=B, J_min=J)
+    return px.mcmc.MYULA(op, reg, p, noise=noise, nchains=nchains, seed=5, stream0=3, real_pairs=real_pairs), op
+
+
+@pytest.mark.parametrize("noise", ["device", "host"])
+def test_real_chain_pairs_are_the_unpacked_chains(px, noise):
+    """MYULA(real_pairs=True): two real chains per complex device chain (every linear operator of the synthesis path
+    is complex-linear and real) -- the tracked arrays are those of the ordinary sampler, in which every real chain
+    travels as a complex chain with a zero imaginary part as in the reference; same noise streams"""
+    nch = 6
+    a, op = _pairs_case(px, nch, True, noise)
+    b, _ = _pairs_case(px, nch, False, noise)
+    start = np.random.default_rng(4).laplace(size=(nch, op.nparams)) * 0.05
+    np.random.seed(9)
+    a.run(start)
+    np.random.seed(9)
+    b.run(start)
+    assert a.engine is not a and a.engine.nchains == nch // 2 and b.engine is b
+    assert a.chain.shape == b.chain.shape == (nch, 3, op.nparams)
+    for c in range(nch):
+        assert rel_l2(a.chain[c], b.chain[c]) < 1e-12, f"chain {c}"
+        assert rel_l2(a.preds[c], b.preds[c]) < 1e-12
+    assert np.allclose(a.logPi, b.logPi, rtol=1e-11) and np.allclose(a.L2s, b.L2s, rtol=1e-11)
+    assert np.allclose(a.priors, b.priors, rtol=1e-12)
+
+
+def test_real_chain_pairs_checkpoint_resume(px, tmp_path):
+    """a real_pairs run resumed from its checkpoint by a new sampler continues the chains bit for bit"""
+    nch = 4
+    a, op = _pairs_case(px, nch, True, nsamples=6, nburn=2, ngap=2)
+    start = np.random.default_rng(4).laplace(size=(nch, op.nparams)) * 0.05
+    a.run(start)
+    ck = str(tmp_path / "ck.npz")
+    b, _ = _pairs_case(px, nch, True, nsamples=6, nburn=2, ngap=2)
+    b.nsamples = 3
+    b.run(start, checkpoint=ck)
+    c, _ = _pairs_case(px, nch, True, nsamples=6, nburn=2, ngap=2)
+    c.run(resume=ck)
+    assert np.array_equal(a.chain, c.chain) and np.array_equal(a.logPi, c.logPi)
+
+
+def test_real_chain_pairs_are_refused_when_they_do_not_apply(px):
+    L, B, J = 12, 2.0, 2
+    rng = np.random.default_rng(1)
+    real = rng.standard_normal(L * (2 * L - 1))
+    p = px.mcmc.PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-4, lmda=1e-3, mu=1.0, verbosity=0, track=[])
+
+    def make(data, nchains=2, params=p, cls=None, setting="synthesis", **kw):
+        op = px.forward.SphericalWaveletTransformOperator(data, 0.1, setting, L, B, J, nchains=nchains)
+        if setting == "synthesis":
+            reg = px.prior.S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, 1e-3, L=L, B=B, J_min=J)
+        else:
+            reg = px.prior.L1("analysis", op.transform.inverse, op.transform.inverse_adjoint, 1e-3)
+        return (cls or px.mcmc.MYULA)(op, reg, params, noise="device", nchains=nchains, real_pairs=True, **kw)
+
+    make(real)  # fine
+    with pytest.raises(ValueError):
+        make(real + 0j)  # complex data: the reference's covariance rule makes the noise level complex
+    with pytest.raises(ValueError):
+        make(real, nchains=3)
+    with pytest.raises(ValueError):
+        make(real, setting="analysis")
+    with pytest.raises(ValueError):
+        make(real, cls=px.mcmc.PxMALA)
+    pc = px.mcmc.PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-4, lmda=1e-3, mu=1.0, verbosity=0, track=[], complex=True)
+    with pytest.raises(ValueError):
+        make(real, params=pc)
+    m = make(real, nchains=4)
+    with pytest.raises(ValueError):
+        m.pack(np.ones((4, 5)) * (1 + 1j))
