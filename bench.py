@@ -307,10 +307,12 @@ def release_plans():
     torch.cuda.empty_cache()
 
 
-def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=100, e2e_steps=0):
+def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=100, e2e_steps=0, real=False):
     """`steps` MYULA iterations of `nch` chains on this GPU (config 5 / the BASELINE metric): device-resident value, per-stage
     device times, optional sustained blocks and the end-to-end figure through host buffers.  Chain c of the job draws
-    Philox stream c whatever the sharding."""
+    Philox stream c whatever the sharding.  `real`: REAL-valued data (the drivers' `_mw_` input route,
+    experiments/earthtopography/main.py:83-85) and MYULA(real_pairs=True): the `nch` real chains travel as nch / 2
+    complex device chains."""
     import ctypes as C
 
     torch = ctx.torch
@@ -323,13 +325,22 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     L, B, J_min = args.L, args.B, args.J_min
     data = sht.inverse(synthetic_flm(L), L).ravel()
     data = data / np.sqrt(np.mean(np.abs(data) ** 2))  # complex, as on the reference's HEALPix path
+    if real:
+        data = np.ascontiguousarray(data.real)
+        data = data / np.sqrt(np.mean(data ** 2))
     op = SphericalWaveletTransformOperator(data, 1.0, "synthesis", L, B, J_min, nchains=nch)
     prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-6, lmda=1e-6, mu=1.0, verbosity=0, track=[])
     reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J_min)
-    m = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234, stream0=philox_stream0(total_chains, ctx.world, ctx.rank))
+    outer = MYULA(op, reg, prm, noise="device", nchains=nch, seed=1234, stream0=philox_stream0(total_chains, ctx.world, ctx.rank),
+                  real_pairs=real)
+    m = outer.engine  # the sampler that iterates on the device representation (nch / 2 packed chains when `real`)
+    nch_dev = m.nchains
+    op = m.forward
     ncoef, npix = op.nparams, L * (2 * L - 1)
     rng = np.random.default_rng(7 + ctx.rank)
     X = D.to_dev_c(rng.laplace(size=(nch, ncoef)))
+    if real:
+        X = outer.pack(X)
     # the form MYULA.run carries the predictions in: ring-Fourier coefficients of the image when the operator allows it
     # (Identity measurement, inverse covariance constant along rings: the pixel-side ring-FFT pair of consecutive
     # iterations cancels), pixels otherwise (--no-ring-fusion)
@@ -363,9 +374,10 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     _lib.check(_lib.lib.pxm_profile_end(ms_kind, cnt_kind))
     launches = _lib.lib.pxm_launch_count() - l0
     ms, leg, fft, el = ctx.reduce([ms, ms_kind[0], ms_kind[1], ms_kind[2]])
-    out = {"nch": nch, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches), "ring_mode": ring_mode, "pred_kind": pred_kind,
+    out = {"nch": nch, "nch_dev": nch_dev, "ncoef": ncoef, "npix": npix, "ms": ms, "steps": steps, "launches": int(launches),
+           "ring_mode": ring_mode, "pred_kind": pred_kind,
            "stage_ms": {"legendre": leg / steps, "ring_fft": fft / steps, "elementwise": el / steps},
-           "counts": [int(c) for c in cnt_kind], "table_bytes": int(op.transform._plan(nch).table_bytes)}
+           "counts": [int(c) for c in cnt_kind], "table_bytes": int(op.transform._plan(nch_dev).table_bytes)}
     # sustained rate: `blocks` blocks of `block_iters` iterations, each timed on the device; median over blocks of the
     # max over ranks (>= 1000 iterations, median of 5)
     if blocks:
@@ -387,8 +399,8 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     out["finite"] = bool(torch.isfinite(torch.view_as_real(X)).all().item())
     # ---- end to end through pinned host buffers, rank-local -------------------------------------------------
     if e2e_steps:
-        Xh = torch.empty((nch, ncoef), dtype=torch.complex128).pin_memory()
-        Ph = torch.empty((nch, npix), dtype=torch.complex128).pin_memory()
+        Xh = torch.empty((nch_dev, ncoef), dtype=torch.complex128).pin_memory()
+        Ph = torch.empty((nch_dev, npix), dtype=torch.complex128).pin_memory()
         Xh.copy_(X.cpu())
         Ph.copy_(m._pix(P).cpu())
         Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
@@ -406,9 +418,9 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
         e2e_s = max(w0.elapsed_time(w1) / 1e3, time.perf_counter() - t0)
         out["e2e_s"] = ctx.reduce([e2e_s])[0]
         out["e2e_steps"] = e2e_steps
-        out["e2e_bytes"] = (ncoef + npix) * nch * 16
+        out["e2e_bytes"] = (ncoef + npix) * nch_dev * 16
         del Xh, Ph, Xo, Po
-    del m, op, reg, X, P
+    del m, outer, op, reg, X, P
     return out
 
 
@@ -621,6 +633,29 @@ def run_ours(args):
                           e2e_steps=max(1, min(args.steps, args.e2e_steps)))
     release_plans()
     extras = {}
+    if not args.no_extras and not args.no_real_pairs and nch % 2 == 0:
+        # the same sweep on REAL-valued data (the drivers' `_mw_` route): two real chains per complex device chain
+        rp = measure_chains(ctx, args, nch, nch * world, args.steps, blocks=min(args.blocks, 3), block_iters=args.block_iters,
+                            e2e_steps=max(1, min(args.steps, args.e2e_steps)), real=True)
+        release_plans()
+        ms_step = rp["ms"] / rp["steps"]
+        extras["real_data_pairs"] = {
+            "workload": f"{workload_name(L, B, J_min)} with REAL-valued data (experiments/earthtopography/main.py:83-85, the `_mw_` "
+                        f"input route): MYULA(real_pairs=True), {nch} real chains per GPU as {nch // 2} complex device chains "
+                        "(the linear operators of the synthesis path are complex-linear and real, so chain 2k rides in the real "
+                        "and chain 2k+1 in the imaginary part; the reference carries every real chain as a complex array with "
+                        "a zero imaginary part)",
+            "value": world * nch * rp["steps"] / (rp["ms"] / 1e3), "unit": UNIT, "ms_per_step": ms_step, "steps": rp["steps"],
+            "stage_ms_per_step": rp["stage_ms"], "gpu_launches": rp["launches"], "finite": rp["finite"],
+            "predictions": rp.get("pred_kind"),
+            "e2e": {"value": world * nch * rp["e2e_steps"] / rp["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": rp["e2e_bytes"],
+                    "d2h_bytes_per_step": rp["e2e_bytes"], "steps": rp["e2e_steps"],
+                    "api": "MYULA(real_pairs=True).engine.iterate_host on the packed host state (16 B per PAIR of real coefficients)"},
+            "parity": "tests/test_gpu_configs.py::test_config5_real_chain_pairs_L256 (every real chain against its own oracle "
+                      "iteration, <= 1e-10), tests/test_gpu_samplers.py::test_real_chain_pairs_*"}
+        if "sustained_ms_per_step" in rp:
+            extras["real_data_pairs"]["sustained"] = {"value": world * nch / (rp["sustained_ms_per_step"] / 1e3), "unit": UNIT,
+                                                      "ms_per_step": rp["sustained_ms_per_step"]}
     if world > 1 and not args.no_extras:
         # config 5 as BASELINE.json words it: 64 chains in TOTAL, 64/N per GPU (strong scaling of the chain sweep)
         total = args.strong_total
@@ -973,6 +1008,7 @@ def main():
     ap.add_argument("--block-iters", type=int, default=100)
     ap.add_argument("--strong-total", type=int, default=64, help="chains in TOTAL of the strong-scaling split (config 5)")
     ap.add_argument("--no-ring-fusion", action="store_true", help="carry the predictions as pixels (the reference's literal composition)")
+    ap.add_argument("--no-real-pairs", action="store_true", help="skip the real-data / packed-chain-pairs leg (key `real_data_pairs`)")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no per-chain / config 1-4 / strong-split legs)")
     ap.add_argument("--ref-L", type=int, default=256, help="bandlimit of the bounded CPU sample")
     ap.add_argument("--ref-procs", type=int, default=64)
