@@ -204,7 +204,7 @@ class PxMCMC:
             + " - ".join([f"{k}: {kwargs[k]:.8e}" for k in kwargs]),
         )
 
-    def _initial_sample(self, initial_sample=None):
+    def _initial_sample(self, initial_sample=None, want_preds=True):
         """Laplace draw (or the user's 1-D start point), and its predictions
         (pxmcmc/mcmc.py:97-111).  Returns device tensors [nchains, .]."""
         n = self.forward.nparams
@@ -229,7 +229,7 @@ class PxMCMC:
                 if np.ndim(X) == 1 and self.nchains > 1:
                     X = np.tile(X, (self.nchains, 1))
         Xd = self._state(X)
-        return Xd, D.to_dev_c(self._forward_dev(Xd))
+        return Xd, (D.to_dev_c(self._forward_dev(Xd)) if want_preds else None)
 
     def _initialise_tracking_arrays(self):
         """pxmcmc/mcmc.py:113-128 (leading chain axis only when nchains > 1)"""
@@ -586,7 +586,7 @@ class MYULA(PxMCMC):
         if resume is not None:
             i, j, X_curr, _ = self.load_checkpoint(resume)
         else:
-            X_curr, _ = self._initial_sample(start_point)
+            X_curr, _ = self._initial_sample(start_point, want_preds=False)  # the packed engine computes its own
         eng._step_counter = self._step_counter
         Xp = self.pack(X_curr)
         Pp = eng._initial_preds(Xp)

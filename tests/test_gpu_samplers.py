@@ -507,3 +507,25 @@ def test_real_chain_pairs_are_refused_when_they_do_not_apply(px):
     m = make(real, nchains=4)
     with pytest.raises(ValueError):
         m.pack(np.ones((4, 5)) * (1 + 1j))
+
+
+def test_real_chain_pairs_host_pipeline_does_not_depend_on_the_grouping(px):
+    """engine.iterate_host on the packed host state: chain groups flowing through the copy / compute pipeline draw the
+    Philox streams of their real chains (stream0 + 2 * packed chain, + 1), whatever the grouping"""
+    import torch
+
+    nch = 8
+    a, op = _pairs_case(px, nch, True, track=())
+    b, _ = _pairs_case(px, nch, True, track=())
+    X = np.random.default_rng(8).laplace(size=(nch, op.nparams)) * 0.05
+    Xp = a.pack(X)
+    Pp = a.engine._pix(a.engine._initial_preds(Xp))
+    Xh, Ph = Xp.cpu().pin_memory(), Pp.cpu().pin_memory()
+    X1, P1 = a.engine.iterate_host(Xh, Ph, groups=1)
+    X2, P2 = b.engine.iterate_host(Xh, Ph, groups=[1, 2, 1])
+    X1, P1, X2, P2 = (np.asarray(t.cpu() if hasattr(t, "cpu") else t) for t in (X1, P1, X2, P2))
+    assert np.array_equal(X1, X2) and np.array_equal(P1, P2)
+    # and they are the chains of the device-resident iteration
+    c, _ = _pairs_case(px, nch, True, track=())
+    X3, P3 = c.engine.iterate(Xp, c.engine._initial_preds(Xp))
+    assert rel_l2(X3.cpu().numpy(), X1) < 1e-12 and rel_l2(c.engine._pix(P3).cpu().numpy(), P1) < 1e-12
