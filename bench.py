@@ -399,11 +399,18 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
     out["finite"] = bool(torch.isfinite(torch.view_as_real(X)).all().item())
     # ---- end to end through pinned host buffers, rank-local -------------------------------------------------
     if e2e_steps:
+        # state in, state out: the chain state travels host -> device -> host every step; the predictions the gradient
+        # needs are recomputed from the state on the device (MYULA.iterate_host(X): as `chain_step` of the reference,
+        # a state is mapped to a state).  `--e2e-with-preds` also moves the pixel-space predictions both ways (round 1's form).
+        with_preds = bool(getattr(args, "e2e_with_preds", False))
         Xh = torch.empty((nch_dev, ncoef), dtype=torch.complex128).pin_memory()
-        Ph = torch.empty((nch_dev, npix), dtype=torch.complex128).pin_memory()
         Xh.copy_(X.cpu())
-        Ph.copy_(m._pix(P).cpu())
-        Xo, Po = torch.empty_like(Xh).pin_memory(), torch.empty_like(Ph).pin_memory()
+        Xo = torch.empty_like(Xh).pin_memory()
+        Ph = Po = None
+        if with_preds:
+            Ph = torch.empty((nch_dev, npix), dtype=torch.complex128).pin_memory()
+            Ph.copy_(m._pix(P).cpu())
+            Po = torch.empty_like(Ph).pin_memory()
         m.iterate_host(Xh, Ph, Xo, Po)  # warm-up
         ctx.barrier()
         w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -418,7 +425,8 @@ def measure_chains(ctx, args, nch, total_chains, steps, blocks=0, block_iters=10
         e2e_s = max(w0.elapsed_time(w1) / 1e3, time.perf_counter() - t0)
         out["e2e_s"] = ctx.reduce([e2e_s])[0]
         out["e2e_steps"] = e2e_steps
-        out["e2e_bytes"] = (ncoef + npix) * nch_dev * 16
+        out["e2e_bytes"] = (ncoef + (npix if with_preds else 0)) * nch_dev * 16
+        out["e2e_with_preds"] = with_preds
         del Xh, Ph, Xo, Po
     del m, outer, op, reg, X, P
     return out
@@ -757,7 +765,10 @@ def run_ours(args):
             "traffic_source": tsrc,
             "e2e": {"value": world * nch * main["e2e_steps"] / main["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": main["e2e_bytes"],
                     "d2h_bytes_per_step": main["e2e_bytes"], "steps": main["e2e_steps"],
-                    "api": "MYULA.iterate_host: pinned host state+predictions -> device -> one iteration -> host, "
+                    "api": ("MYULA.iterate_host(X, preds): pinned host state + predictions -> device -> one iteration -> host, "
+                            if main.get("e2e_with_preds") else
+                            "MYULA.iterate_host(X): pinned host state -> device -> one iteration (the predictions behind the gradient "
+                            "are recomputed from the state on the device) -> new state to the host, ") +
                            "chain groups pipelined over three streams (H2D | kernels | D2H); PCIe-bound" +
                            ("; all ranks share the host's PCIe / memory bandwidth (one NUMA node): this figure does not scale with N" if world > 1 else "")},
             "clocks": main["clocks"],
@@ -1009,6 +1020,7 @@ def main():
     ap.add_argument("--strong-total", type=int, default=64, help="chains in TOTAL of the strong-scaling split (config 5)")
     ap.add_argument("--no-ring-fusion", action="store_true", help="carry the predictions as pixels (the reference's literal composition)")
     ap.add_argument("--no-real-pairs", action="store_true", help="skip the real-data / packed-chain-pairs leg (key `real_data_pairs`)")
+    ap.add_argument("--e2e-with-preds", action="store_true", help="end-to-end leg: move the pixel-space predictions over PCIe too (round 1's form)")
     ap.add_argument("--no-extras", action="store_true", help="only the headline workload (no per-chain / config 1-4 / strong-split legs)")
     ap.add_argument("--ref-L", type=int, default=256, help="bandlimit of the bounded CPU sample")
     ap.add_argument("--ref-procs", type=int, default=64)

@@ -651,10 +651,15 @@ class MYULA(PxMCMC):
             raise ValueError("capture() needs noise='device' (host RNG draws cannot be recorded)")
         return GraphedChain(self, X_curr, curr_preds, iterations)
 
-    def iterate_host(self, X_host, preds_host, X_out=None, preds_out=None, groups=None):
+    def iterate_host(self, X_host, preds_host=None, X_out=None, preds_out=None, groups=None):
         """The same iteration through HOST buffers (pinned torch CPU tensors or numpy
         arrays [nchains, .]): copies the state in, runs the kernels, copies the new
         state and predictions back.  This is the end-to-end path bench.py times.
+
+        `preds_host=None`: state in, state out -- the predictions of the incoming state are recomputed on the device
+        (in the form the run loops carry them, see `_initial_preds`) instead of travelling over PCIe, and the new
+        predictions are returned only when `preds_out` is given; `chain_step` of the reference likewise maps a state to
+        a state (pxmcmc/mcmc.py:185-201).
 
         With several chains the batch is cut into `groups` chain groups (a count, or a list of group
         sizes) that flow through a
@@ -664,6 +669,8 @@ class MYULA(PxMCMC):
         the grouping: chains are independent and chain c always draws Philox stream stream0 + c."""
         dv = D.dev()
         xh = X_host if D.is_dev(X_host) else torch.from_numpy(np.ascontiguousarray(X_host, dtype=np.complex128))
+        if preds_host is None:
+            return self._iterate_host_state(xh.unsqueeze(0) if xh.dim() == 1 else xh, X_out, preds_out, groups)
         ph = preds_host if D.is_dev(preds_host) else torch.from_numpy(np.ascontiguousarray(preds_host, dtype=np.complex128))
         if xh.dim() == 1:
             xh, ph = xh.unsqueeze(0), ph.unsqueeze(0)
@@ -727,6 +734,68 @@ class MYULA(PxMCMC):
             self._group_offset = None
         s_out.synchronize()
         return X_out, preds_out
+
+    def _iterate_host_state(self, xh, X_out, preds_out, groups):
+        """`iterate_host` without predictions on the way in (and, unless `preds_out` is given, on the way out): the same
+        three-stream pipeline over chain groups"""
+        dv = D.dev()
+        nch = xh.shape[0]
+        if groups is None:
+            groups = 8 if (nch >= 64 and nch % 8 == 0) else (4 if (nch >= 16 and nch % 4 == 0) else 1)
+        if isinstance(groups, int):
+            if nch % groups or self.noise != "device" and groups > 1:
+                groups = 1
+            sizes = [nch // groups] * groups
+        else:
+            sizes = [int(g) for g in groups]
+            if sum(sizes) != nch or min(sizes) < 1:
+                raise ValueError("group sizes must be positive and add up to the number of chains")
+            if self.noise != "device":
+                sizes = [nch]
+        if X_out is None:
+            X_out = torch.empty_like(xh).pin_memory()
+        as_t = lambda a: torch.from_numpy(a) if isinstance(a, np.ndarray) else a  # numpy outputs are filled in place
+        xo = as_t(X_out).reshape(xh.shape)
+        po = None if preds_out is None else as_t(preds_out).reshape(nch, -1)
+        st = getattr(self, "_pipe_streams", None)
+        if st is None:
+            st = self._pipe_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        s_in, s_out = st
+        s_cmp = torch.cuda.current_stream()
+        s_in.wait_stream(s_cmp)
+        starts = [sum(sizes[:g]) for g in range(len(sizes))]
+        if self.noise == "device":
+            self._step_counter += 1
+        staged = []
+        for g in range(len(sizes)):
+            with torch.cuda.stream(s_in):
+                sl = slice(starts[g], starts[g] + sizes[g])
+                Xd = xh[sl].to(dv, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            staged.append((sl, Xd, ev))
+        try:
+            for g, (sl, Xd, ev) in enumerate(staged):
+                s_cmp.wait_event(ev)
+                Xd.record_stream(s_cmp)
+                if self.noise == "device":
+                    self._group_offset = starts[g]
+                Xn, Pn = self.iterate(Xd, self._initial_preds(Xd))
+                if po is not None:
+                    Pn = self._pix(Pn)
+                done = torch.cuda.Event()
+                done.record(s_cmp)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    Xn.record_stream(s_out)
+                    xo[sl].copy_(Xn, non_blocking=True)
+                    if po is not None:
+                        Pn.record_stream(s_out)
+                        po[sl].copy_(Pn, non_blocking=True)
+        finally:
+            self._group_offset = None
+        s_out.synchronize()
+        return (X_out, preds_out) if preds_out is not None else X_out
 
     def chain_step(self, X, proxf, gradg):
         """One proposal from (X, prox(X), gradg) (pxmcmc/mcmc.py:185-201)."""

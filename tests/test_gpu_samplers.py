@@ -529,3 +529,18 @@ def test_real_chain_pairs_host_pipeline_does_not_depend_on_the_grouping(px):
     c, _ = _pairs_case(px, nch, True, track=())
     X3, P3 = c.engine.iterate(Xp, c.engine._initial_preds(Xp))
     assert rel_l2(X3.cpu().numpy(), X1) < 1e-12 and rel_l2(c.engine._pix(P3).cpu().numpy(), P1) < 1e-12
+
+
+def test_host_iteration_state_in_state_out(px):
+    """MYULA.iterate_host(X): only the state crosses PCIe; the predictions behind the gradient are recomputed on the
+    device -- the same new state as with the predictions passed in, whatever the grouping"""
+    op, reg, prm = _ring_case(px, 0.7, 4)
+    mk = lambda: px.mcmc.MYULA(op, reg, prm, noise="device", nchains=4, seed=3, stream0=5)
+    X = np.random.default_rng(2).laplace(size=(4, op.nparams)) * 1e-3 + 0j
+    a, b, c = mk(), mk(), mk()
+    P = a._forward_dev(a._state(X)).cpu().numpy()
+    X1, P1 = a.iterate_host(X, P)
+    X2 = np.asarray(b.iterate_host(X))
+    X3, P3 = c.iterate_host(X, None, None, np.empty_like(P), groups=[1, 3])
+    assert rel_l2(X2, X1) < 1e-12 and np.array_equal(np.asarray(X3), X2)
+    assert rel_l2(np.asarray(P3), P1) < 1e-12
