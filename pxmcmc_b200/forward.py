@@ -116,9 +116,14 @@ class ForwardOperator:
             return "harm"
         return "ring"
 
+    def _own_methods(self):
+        """True unless a user subclass overrides the methods the carried forms stand in for (it is then not bypassed)"""
+        return all(getattr(type(self), n) is getattr(ForwardOperator, n)
+                   for n in ("forward", "calc_gradg", "_forward_synthesis", "_gradg_synthesis", "_residual"))
+
     def _ring_fusable(self):
         t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
-        if not (self.fuse_ring and self.setting == "synthesis" and self._diag is not None):
+        if not (self.fuse_ring and self.setting == "synthesis" and self._diag is not None and self._own_methods()):
             return False
         if type(m) is not Identity or m.ndata != m.npix:
             return False
@@ -203,6 +208,8 @@ class ForwardOperator:
         t, m = getattr(self, "transform", None), getattr(self, "measurement", None)
         if self.setting != "synthesis" or self._diag is None:
             return "real chain pairs need the synthesis setting and a diagonal covariance"
+        if not self._own_methods():
+            return "real chain pairs need the library's forward / calc_gradg (a subclass overrides them)"
         if type(m) is not Identity:
             return "real chain pairs need the Identity measurement"
         if (type(t).inverse is not SphericalWaveletTransform.inverse

@@ -427,6 +427,14 @@ def test_ring_mode_is_refused_when_it_does_not_apply(px):
     op3, _, _ = _ring_case(px, 0.1, 1, L=L, B=2.0)
     assert op3._ring_fusable()
 
+    class MineOp(px.forward.SphericalWaveletTransformOperator):  # a user operator with its own gradient is not bypassed
+        def calc_gradg(self, preds):
+            return 3 * super().calc_gradg(preds)
+
+    assert not MineOp(data, 0.1, "synthesis", L, 2.0, 2)._ring_fusable()
+    with pytest.raises(ValueError):
+        MineOp(data, 0.1, "synthesis", L, 2.0, 2).paired()
+
 
 # ------------------------------------------------------------------ real chain pairs
 def _pairs_case(px, nchains, real_pairs, noise="device", L=20, B=1.5, J=2, sig=0.3, nsamples=3, nburn=4, ngap=3,
