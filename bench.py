@@ -664,6 +664,17 @@ def run_ours(args):
         if "sustained_ms_per_step" in rp:
             extras["real_data_pairs"]["sustained"] = {"value": world * nch / (rp["sustained_ms_per_step"] / 1e3), "unit": UNIT,
                                                       "ms_per_step": rp["sustained_ms_per_step"]}
+    if world == 1 and not args.no_extras and not args.no_ring_fusion:
+        # the reference's literal composition (predictions as pixels: 4 ring-FFT stages, 4 Legendre contractions per
+        # iteration) measured in the same run, for comparison with the carried form of `value`
+        a2 = argparse.Namespace(**vars(args))
+        a2.no_ring_fusion = True
+        lit = measure_chains(ctx, a2, nch, nch * world, args.steps)
+        release_plans()
+        extras["literal_composition"] = {"value": world * nch * lit["steps"] / (lit["ms"] / 1e3), "unit": UNIT,
+                                         "ms_per_step": lit["ms"] / lit["steps"], "stage_ms_per_step": lit["stage_ms"],
+                                         "gpu_launches": lit["launches"],
+                                         "note": "same workload, predictions carried as pixels (--no-ring-fusion)"}
     if world > 1 and not args.no_extras:
         # config 5 as BASELINE.json words it: 64 chains in TOTAL, 64/N per GPU (strong scaling of the chain sweep)
         total = args.strong_total
