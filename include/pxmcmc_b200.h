@@ -64,6 +64,10 @@ int pxm_wav_plan_bandlimits(const pxm_wav_plan* plan, int* out, int cap);
 int pxm_wav_plan_table_bytes_by_family(const pxm_wav_plan* plan, long long* out4);
 /* bytes of the Gram table G^m = (2L-1) Lambda^T Lambda behind pxm_wav_gram_gradient (0 until its first call builds it) */
 int pxm_wav_plan_gram_bytes(const pxm_wav_plan* plan, long long* out);
+/* per-ring weights w_t of the Gram table, G^m = (2L-1) Lambda^T diag(w) Lambda: the Gram form for a noise level that is
+ * constant along every ring (pxmcmc/forward.py:74-88 with the per-ring sigma of experiments/earthtopography/main.py:92-94);
+ * pxm_wav_gram_gradient then takes d_b = pxm_wav_pix_to_harm_adjoint(w . data).  h_w: L host doubles, NULL: w = 1. */
+int pxm_wav_set_gram_weights(pxm_wav_plan* plan, const double* h_w, int n);
 int pxm_wav_synthesis(pxm_wav_plan* plan, const void* d_coef, void* d_pix, int nbatch, void* stream);
 int pxm_wav_synthesis_adjoint(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);
 int pxm_wav_analysis(pxm_wav_plan* plan, const void* d_pix, void* d_coef, int nbatch, void* stream);

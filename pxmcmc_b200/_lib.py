@@ -34,6 +34,7 @@ SIGNATURES = {
     "pxm_wav_plan_bandlimits": (_i, [_vp, C.POINTER(_i), _i]),
     "pxm_wav_plan_table_bytes_by_family": (_i, [_vp, C.POINTER(_ll)]),
     "pxm_wav_plan_gram_bytes": (_i, [_vp, C.POINTER(_ll)]),
+    "pxm_wav_set_gram_weights": (_i, [_vp, C.POINTER(C.c_double), _i]),
     "pxm_wav_synthesis": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_synthesis_adjoint": (_i, [_vp, _vp, _vp, _i, _vp]),
     "pxm_wav_analysis": (_i, [_vp, _vp, _vp, _i, _vp]),

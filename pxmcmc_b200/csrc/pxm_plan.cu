@@ -727,19 +727,24 @@ struct pxm_wav_plan {
   Stage g_full;
   double* d_gram = nullptr;
   double* d_h2 = nullptr;
-  bool gram_built = false;
+  double* d_gram_w = nullptr;  // per-ring weights of the Gram table (pxm_wav_set_gram_weights), nullptr: all one
+  bool gram_built = false;     // the table holds the Gram matrices of the current weights
+  bool gram_alloc = false;
 
   int ensure_gram() {
     if (gram_built) return PXM_OK;
     PXM_TRY(ensure(syn));
-    pxm_make_table_layout(gramT, L, L, L, 0, 0, L, 0, 0, 1);
-    PXM_CUDA(cudaMalloc(&d_gram, std::max<size_t>(gramT.doubles, 1) * 8));
+    if (!gram_alloc) {
+      pxm_make_table_layout(gramT, L, L, L, 0, 0, L, 0, 0, 1);
+      PXM_CUDA(cudaMalloc(&d_gram, std::max<size_t>(gramT.doubles, 1) * 8));
+      PXM_CUDA(cudaMalloc(&d_h2, std::max<ull>(H.total, 1) * 8));
+      PXM_CUDA(cudaMemset(d_h2, 0, std::max<ull>(H.total, 1) * 8));
+      build_g_items(g_full, gramT, H, nld);
+      PXM_TRY(g_full.upload());
+      gram_alloc = true;
+    }
     PXM_CUDA(cudaMemset(d_gram, 0, std::max<size_t>(gramT.doubles, 1) * 8));
-    PXM_TRY(pxm_generate_gram(syn.full.T, d_tab, gramT, d_gram, (double)(2 * L - 1), 0));
-    PXM_CUDA(cudaMalloc(&d_h2, std::max<ull>(H.total, 1) * 8));
-    PXM_CUDA(cudaMemset(d_h2, 0, std::max<ull>(H.total, 1) * 8));
-    build_g_items(g_full, gramT, H, nld);
-    PXM_TRY(g_full.upload());
+    PXM_TRY(pxm_generate_gram(syn.full.T, d_tab, gramT, d_gram, (double)(2 * L - 1), 0, d_gram_w));
     gram_built = true;
     return PXM_OK;
   }
@@ -906,6 +911,7 @@ int pxm_wav_plan_destroy(pxm_wav_plan* p) {
   p->g_full.release();
   if (p->d_gram) cudaFree(p->d_gram);
   if (p->d_h2) cudaFree(p->d_h2);
+  if (p->d_gram_w) cudaFree(p->d_gram_w);
   if (p->d_tab) cudaFree(p->d_tab);
   if (p->d_ws) cudaFree(p->d_ws);
   delete p;
@@ -939,6 +945,25 @@ int pxm_wav_plan_table_bytes_by_family(const pxm_wav_plan* p, long long* out4) {
     for (const TableRef& tr : dirs[d]->scales) sc += (long long)tr.T.doubles * 8;
     out4[2 * d + 1] = sc;
   }
+  return PXM_OK;
+}
+
+// Per-ring weights w_t of the Gram table: G^m = (2L-1) Lambda^T diag(w) Lambda -- the data-fidelity gradient of a noise
+// level that is constant along every ring (pxm_wav_gram_gradient then takes b = A_inv^dagger(w d)).  h_w: L host
+// doubles, or NULL for w = 1.  The table is regenerated on the next pxm_wav_gram_gradient (about 1 ms at L = 256).
+int pxm_wav_set_gram_weights(pxm_wav_plan* p, const double* h_w, int n) {
+  PXM_REQUIRE(p != nullptr, "null plan");
+  PXM_REQUIRE(p->ps.sh.world == 1, "gram form: unsharded plans only");
+  PXM_REQUIRE(h_w == nullptr || n == p->L, "gram weights: one weight per ring");
+  PXM_CUDA(cudaDeviceSynchronize());  // the table may be in use by launches in flight
+  if (h_w == nullptr) {
+    if (p->d_gram_w) cudaFree(p->d_gram_w);
+    p->d_gram_w = nullptr;
+  } else {
+    if (!p->d_gram_w) PXM_CUDA(cudaMalloc(&p->d_gram_w, (size_t)p->L * 8));
+    PXM_CUDA(cudaMemcpy(p->d_gram_w, h_w, (size_t)p->L * 8, cudaMemcpyHostToDevice));
+  }
+  p->gram_built = false;
   return PXM_OK;
 }
 

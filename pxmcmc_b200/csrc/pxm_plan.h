@@ -83,7 +83,7 @@ void pxm_make_table_layout(PxmTableLayout& T, int grid_L, int rings, int lmax, i
 int pxm_generate_lambda(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
 int pxm_generate_w(const PxmTableLayout& T, double* d_tab, const double* d_g, cudaStream_t st);
 int pxm_generate_gram(const PxmTableLayout& Tl, const double* d_lam_tab, const PxmTableLayout& Tg, double* d_g_tab, double scale,
-                      cudaStream_t st);
+                      cudaStream_t st, const double* d_ring_weights = nullptr);
 
 // kernels' launchers -------------------------------------------------------------
 int pxm_legendre_pad_columns(int ncols);

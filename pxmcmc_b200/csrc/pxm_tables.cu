@@ -129,10 +129,11 @@ __global__ void k_c_to_tiles(const double* __restrict__ C, const unsigned long l
   }
 }
 
-// Gram tiles of the inverse transform: G^m[lam', lam] = scale * sum_t Lambda^m[t, m + lam'] Lambda^m[t, m + lam]
-// (rows and columns relative to |m|; one CTA per 32 x 16 output tile, one thread per entry)
+// Gram tiles of the inverse transform: G^m[lam', lam] = scale * sum_t w_t Lambda^m[t, m + lam'] Lambda^m[t, m + lam]
+// (rows and columns relative to |m|; one CTA per 32 x 16 output tile, one thread per entry; w == nullptr: w_t = 1)
 __global__ void k_gram_tiles(const double* __restrict__ lam_tab, double* __restrict__ g_tab, const PxmWigSlot* __restrict__ lslots,
-                             const PxmWigSlot* __restrict__ gslots, int rings, int lmax, int ntb_g, double scale) {
+                             const PxmWigSlot* __restrict__ gslots, int rings, int lmax, int ntb_g, double scale,
+                             const double* __restrict__ w) {
   const int si = blockIdx.z;
   const PxmWigSlot ls = lslots[si], gs = gslots[si];
   const int tb = blockIdx.y, lb = blockIdx.x;
@@ -148,7 +149,7 @@ __global__ void k_gram_tiles(const double* __restrict__ lam_tab, double* __restr
       const double* tile_row = lam_tab + ls.tile_off + (size_t)(t >> 5) * (size_t)ls.nlb * PXM_TILE_DOUBLES;
       const double a = tile_row[(size_t)(lbp - ls.lb0) * PXM_TILE_DOUBLES + pxm_tile_word(t & 31, cp)];
       const double b = tile_row[(size_t)(lb - ls.lb0) * PXM_TILE_DOUBLES + pxm_tile_word(t & 31, c)];
-      acc += a * b;
+      acc += (w ? w[t] : 1.0) * (a * b);
     }
   }
   g_tab[gs.tile_off + ((size_t)tb * gs.nlb + lb) * PXM_TILE_DOUBLES + pxm_tile_word(r, c)] = scale * acc;
@@ -363,7 +364,7 @@ extern "C" int pxm_debug_wigner_row_host(int grid_L, int ring, int m, int spin, 
 // G^m = scale * Lambda^T Lambda from the (already generated, unweighted, full-support) Lambda table `Tl` in `d_lam_tab`
 // into the layout `Tg` (same slots; rows = relative degrees) in `d_g_tab`
 int pxm_generate_gram(const PxmTableLayout& Tl, const double* d_lam_tab, const PxmTableLayout& Tg, double* d_g_tab, double scale,
-                      cudaStream_t st) {
+                      cudaStream_t st, const double* d_ring_weights) {
   if (Tl.nslots != Tg.nslots || Tl.l_lo != 0 || Tg.l_lo != 0) {
     pxm_set_error("gram tables need full-support Lambda tables with the same slots");
     return PXM_ERR_ARG;
@@ -375,7 +376,7 @@ int pxm_generate_gram(const PxmTableLayout& Tl, const double* d_lam_tab, const P
   int maxnlb = 0;
   for (int v : Tg.nlb) maxnlb = std::max(maxnlb, v);
   dim3 grid(std::max(maxnlb, 1), Tg.ntb, Tg.nslots);
-  k_gram_tiles<<<grid, 512, 0, st>>>(d_lam_tab, d_g_tab, dl.d, dg.d, Tl.rings, Tl.lmax, Tg.ntb, scale);
+  k_gram_tiles<<<grid, 512, 0, st>>>(d_lam_tab, d_g_tab, dl.d, dg.d, Tl.rings, Tl.lmax, Tg.ntb, scale, d_ring_weights);
   PXM_LAUNCHED();
   PXM_CUDA(cudaStreamSynchronize(st));
   dl.release();

@@ -233,6 +233,20 @@ class WaveletPlan:
         check(lib.pxm_wav_synthesis_to_harm(self.h, ptr(c2), ptr(harm), c2.shape[0], stream_ptr()))
         return harm
 
+    def set_gram_weights(self, w, key=None):
+        """per-ring weights of the Gram table (None: all one); `key` identifies them so that callers can tell whether the
+        table still is theirs (`gram_key`)"""
+        import ctypes as C
+
+        if w is None:
+            check(lib.pxm_wav_set_gram_weights(self.h, None, 0))
+        else:
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            check(lib.pxm_wav_set_gram_weights(self.h, w.ctypes.data_as(C.POINTER(C.c_double)), int(w.size)))
+        self.gram_key = key
+
+    gram_key = None
+
     def gram_gradient(self, harm, b_harm, ic, nb):
         out = torch.empty((nb, self.ncoefs), dtype=CDT, device=harm.device)
         check(lib.pxm_wav_gram_gradient(self.h, ptr(harm), ptr(b_harm), float(ic.real), float(ic.imag), ptr(out), nb, stream_ptr()))

@@ -111,10 +111,29 @@ class ForwardOperator:
         """'harm' (Gram form), 'ring', or None"""
         if not self._ring_fusable():
             return None
-        d = np.asarray(self._diag)
-        if self.fuse_gram and bool(np.all(d == d[0])):
+        if self.fuse_gram and self._gram_weights() is not False:
             return "harm"
         return "ring"
+
+    def _gram_weights(self):
+        """How the Gram form applies: None -- the inverse covariance is ONE constant c (G = n Lambda^T Lambda, g = c (G f - b));
+        (phase, w) -- it is constant along every ring with a common complex phase, ic_t = phase * w_t with w_t real
+        (the reference's per-ring noise levels, experiments/earthtopography/main.py:92-94; a complex data vector turns
+        the real variances into var (1 + i) / sqrt 2, pxmcmc/forward.py:80-82: a common phase): G = n Lambda^T diag(w) Lambda,
+        g = phase (G f - A_inv^dagger(w d)); False -- it does not (the phases differ)"""
+        c = getattr(self, "_gram_w_cache", None)
+        if c is None or c[0] is not self._diag:
+            d = np.asarray(self._diag)
+            if bool(np.all(d == d[0])):
+                r = None
+            else:
+                L = self.transform.L
+                ring = d.reshape(L, 2 * L - 1)[:, 0]
+                phase = ring[0] / abs(ring[0])
+                w = ring / phase
+                r = (complex(phase), np.ascontiguousarray(w.real)) if bool(np.all(np.abs(w.imag) <= 1e-13 * np.abs(w.real))) else False
+            self._gram_w_cache = c = (self._diag, r)
+        return c[1]
 
     def _own_methods(self):
         """True unless a user subclass overrides the methods the carried forms stand in for (it is then not bypassed)"""
@@ -174,6 +193,11 @@ class ForwardOperator:
             c = self._harm_b_cache = {}
         if nb not in c:
             data_d, _ = self._upload()
+            gw = self._gram_weights()
+            if gw:  # per-ring weights: b = A_inv^dagger(w d)
+                L = self.transform.L
+                wpix = D.to_dev_c(np.repeat(gw[1], 2 * L - 1).astype(complex))
+                data_d = data_d * wpix
             c[nb] = self.transform._plan(nb).pix_to_harm_adjoint(data_d.reshape(1, -1))
         return c[nb]
 
@@ -181,7 +205,14 @@ class ForwardOperator:
         """gradient of the data fidelity from ring- / harmonic-space predictions"""
         plan = self.transform._plan(R.nb)
         if R.kind == "harm":
-            return plan.gram_gradient(R.t, self._harm_b(R.nb), complex(np.asarray(self._diag)[0]), R.nb)
+            gw = self._gram_weights()
+            # the plan's Gram table carries this operator's ring weights (regenerated, ~1 ms, when another operator
+            # sharing the transform object has put its own there since)
+            key = None if not gw else (id(self._diag), len(gw[1]))
+            if plan.gram_key != key:
+                plan.set_gram_weights(None if not gw else gw[1], key)
+            ic = complex(np.asarray(self._diag)[0]) if not gw else gw[0]
+            return plan.gram_gradient(R.t, self._harm_b(R.nb), ic, R.nb)
         resid = plan.ring_resid(R.t, self._ring_data(R.nb), self._ic_rings(), R.nb)
         return plan.synthesis_adjoint_from_ring(resid, R.nb)
 

@@ -339,7 +339,7 @@ def _ring_case(px, sig, nchains, L=24, B=1.5, J=2, complex_data=True, **kw):
     return op, reg, prm
 
 
-@pytest.mark.parametrize("sig_kind,nchains", [("scalar", 1), ("scalar", 3), ("scalar_ring", 2), ("per_ring", 2)])
+@pytest.mark.parametrize("sig_kind,nchains", [("scalar", 1), ("scalar", 3), ("scalar_ring", 2), ("per_ring", 2), ("per_ring_ring", 2)])
 def test_ring_carried_predictions_equal_the_pixel_composition(px, sig_kind, nchains):
     """Identity measurement behind a wavelet synthesis: the ring FFT that ends Psi and the one that starts the next
     gradient cancel when the inverse covariance is constant along rings; the samplers then carry the predictions as ring
@@ -355,10 +355,12 @@ def test_ring_carried_predictions_equal_the_pixel_composition(px, sig_kind, ncha
     else:  # the reference's per-ring noise level sqrt(sigma^2 / pixel area) (experiments/earthtopography/main.py:92-94)
         sig = np.sqrt(0.05 / px.utils.calc_pixel_areas(L)).flatten()
     op, reg, prm = _ring_case(px, sig, nchains)
-    op.fuse_gram = sig_kind != "scalar_ring"
+    op.fuse_gram = sig_kind not in ("scalar_ring", "per_ring_ring")
     assert op._ring_fusable()
-    # one constant inverse covariance: harmonic (Gram) form, predictions carried as f_lm; per-ring constants: ring form
-    assert op._ring_kind() == {"scalar": "harm", "scalar_ring": "ring", "per_ring": "ring"}[sig_kind]
+    # harmonic (Gram) form, predictions carried as f_lm: one constant inverse covariance, or -- with per-ring weights in
+    # the Gram table -- constants along rings that share a complex phase; `fuse_gram = False`: ring form
+    assert op._ring_kind() == {"scalar": "harm", "scalar_ring": "ring", "per_ring": "harm", "per_ring_ring": "ring"}[sig_kind]
+    assert (op._gram_weights() is None) == sig_kind.startswith("scalar")
     rng = np.random.default_rng(3)
     X0 = D.to_dev_c(rng.laplace(size=(nchains, op.nparams)))
     ring = px.mcmc.MYULA(op, reg, prm, noise="device", nchains=nchains, seed=5)
