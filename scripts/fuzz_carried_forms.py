@@ -9,7 +9,6 @@ from pxmcmc_b200 import device as D
 from pxmcmc_b200.forward import SphericalWaveletTransformOperator
 from pxmcmc_b200.mcmc import MYULA, PxMCMCParams
 from pxmcmc_b200.prior import S2_Wavelets_L1
-from pxmcmc_b200.utils import calc_pixel_areas
 
 rng = np.random.default_rng(int(sys.argv[1]) if len(sys.argv) > 1 else 0)
 rel = lambda a, b: float(np.linalg.norm(np.ravel(a) - np.ravel(b)) / max(np.linalg.norm(np.ravel(b)), 1e-300))
@@ -24,25 +23,24 @@ worst = 0.0
 for L, B, J, nch in cases:
     npix = L * (2 * L - 1)
     prm = PxMCMCParams(nsamples=1, nburn=0, ngap=1, delta=1e-3, lmda=5e-3, mu=2.0, verbosity=0, track=[])
-    for kind in ("scalar", "per_ring", "real_pairs"):
+    for kind in ("scalar", "per_ring", "real_pairs", "real_pairs_ring"):
         try:
-            data = rng.standard_normal(npix) + (0 if kind == "real_pairs" else 1j * rng.standard_normal(npix))
-            if kind == "per_ring":
-                sig = np.sqrt(0.3 ** 2 / np.repeat(calc_pixel_areas(L).reshape(L, -1)[:, :1], 2 * L - 1, axis=1)).ravel() \
-                    if False else np.repeat(0.2 + rng.random(L), 2 * L - 1)
+            data = rng.standard_normal(npix) + (0 if kind.startswith("real_pairs") else 1j * rng.standard_normal(npix))
+            if kind in ("per_ring", "real_pairs_ring"):
+                sig = np.repeat(0.2 + rng.random(L), 2 * L - 1)
             else:
                 sig = 0.4
-            nc = nch + (nch % 2) if kind == "real_pairs" else nch
+            nc = nch + (nch % 2) if kind.startswith("real_pairs") else nch
             op = SphericalWaveletTransformOperator(data, sig, "synthesis", L, B, J, nchains=nc)
             reg = S2_Wavelets_L1("synthesis", op.transform.inverse, op.transform.inverse_adjoint, prm.lmda * prm.mu, L=L, B=B, J_min=J)
         except Exception as e:  # noqa: BLE001  (tilings with an empty scale: the reference's _multires_bandlimits fails the same way)
             print(f"L={L} B={B} J_min={J}: rejected ({type(e).__name__}: {e})")
             break
         X = rng.laplace(size=(nc, op.nparams)) * 0.05
-        if kind != "real_pairs":
+        if not kind.startswith("real_pairs"):
             X = X + 1j * rng.laplace(size=X.shape) * 0.05
         res = {}
-        for mode in ("pixels", "carried") + (("pairs",) if kind == "real_pairs" else ()):
+        for mode in ("pixels", "carried") + (("pairs",) if kind.startswith("real_pairs") else ()):
             m = MYULA(op, reg, prm, noise="device", nchains=nc, seed=11, stream0=2, real_pairs=(mode == "pairs"))
             op.fuse_ring = mode != "pixels"
             eng = m.engine
@@ -60,6 +58,6 @@ for L, B, J, nch in cases:
             e = max(rel(res[mode][0], res["pixels"][0]), rel(res[mode][1], res["pixels"][1]))
             worst = max(worst, e)
             flag = "" if e < 1e-11 else "   <-- FAIL"
-            print(f"L={L:3d} B={B} J_min={J} chains={nc} {kind:10s} {mode:8s} ({res[mode][2]}): {e:.2e}{flag}")
+            print(f"L={L:3d} B={B} J_min={J} chains={nc} {kind:15s} {mode:8s} ({res[mode][2]}): {e:.2e}{flag}")
 print(f"worst {worst:.2e}")
 sys.exit(0 if worst < 1e-11 else 1)
