@@ -432,3 +432,43 @@ def test_wavelet_power_weights_closed_form():
         w = prior.map_weights[off: off + Lj * (2 * Lj - 1)].reshape(Lj, -1)[:, 0]
         assert np.allclose(w, 2 * np.pi ** 2 * peak / (Pj * Lj * (2 * Lj - 1)) * np.sin(th), rtol=1e-12), j
         off += Lj * (2 * Lj - 1)
+
+
+# ------------------------------------------------------------------ algebra behind the carried forms (product: forward.py)
+def test_gram_of_the_mw_inverse_transform_is_diagonal_in_m(rng):
+    """What the harmonic (Gram) form of the data-fidelity gradient rests on (pxmcmc_b200/forward.py):
+    with a noise level that is constant along every ring, A_inv^dagger diag(w) A_inv does not couple different
+    azimuthal orders, and on each order it is (2L-1) Lambda^T diag(w_t) Lambda with the REAL colatitude factor
+    Lambda^m[t, l] = A_inv e_lm sampled at phi = 0 -- checked with the oracle's own transforms, no GPU involved"""
+    L = 7
+    n = 2 * L - 1
+    A = np.stack([ssht_ref.inverse(np.eye(L * L, dtype=complex)[i], L).ravel() for i in range(L * L)], axis=1)  # [npix, L^2]
+    w_ring = 0.3 + rng.random(L)
+    W = np.repeat(w_ring, n)
+    G = A.conj().T @ (W[:, None] * A)
+    ms = np.array([ssht_ref.ind2elm(i)[1] for i in range(L * L)])
+    off = G[ms[:, None] != ms[None, :]]
+    assert np.max(np.abs(off)) < 1e-12 * np.max(np.abs(G))
+    for m in range(-(L - 1), L):
+        idx = np.nonzero(ms == m)[0]
+        lam = A.reshape(L, n, L * L)[:, 0, :][:, idx]  # phi = 0 column: e^{i m 0} = 1
+        assert np.max(np.abs(lam.imag)) < 1e-13
+        assert np.allclose(G[np.ix_(idx, idx)], n * lam.real.T @ (w_ring[:, None] * lam.real), atol=1e-12)
+    # and the adjoint used on the way back is the plain conjugate transpose (Euclidean adjoint, as the reference's)
+    x, y = rng.standard_normal(L * L) + 0j, rng.standard_normal(L * n) + 0j
+    assert np.isclose(np.vdot(y, ssht_ref.inverse(x, L).ravel()), np.vdot(ssht_ref.inverse_adjoint(y.reshape(L, n), L), x))
+
+
+def test_wavelet_synthesis_and_its_adjoint_are_real_operators(rng):
+    """What MYULA(real_pairs=True) rests on: the axisymmetric wavelet synthesis and its adjoint are complex-linear and
+    map real fields to real fields, so two real chains can travel as the real and imaginary part of one complex chain"""
+    L, B, J = 12, 2.0, 1
+    t = R.WaveletTransform(L, B, J)
+    xa, xb = rng.standard_normal(t.ncoefs), rng.standard_normal(t.ncoefs)
+    pa, pb = t.inverse(xa.astype(complex)), t.inverse(xb.astype(complex))
+    assert np.max(np.abs(pa.imag)) < 1e-13 * np.max(np.abs(pa.real))
+    assert rel_l2(t.inverse(xa + 1j * xb), pa.real + 1j * pb.real) < 1e-13
+    ya, yb = rng.standard_normal(L * (2 * L - 1)), rng.standard_normal(L * (2 * L - 1))
+    ca, cb = t.inverse_adjoint(ya.astype(complex)), t.inverse_adjoint(yb.astype(complex))
+    assert np.max(np.abs(ca.imag)) < 1e-13 * np.max(np.abs(ca.real))
+    assert rel_l2(t.inverse_adjoint(ya + 1j * yb), ca.real + 1j * cb.real) < 1e-13
